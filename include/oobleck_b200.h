@@ -1,0 +1,160 @@
+/* oobleck_b200 -- C ABI of the B200-native kernel library behind Oobleck's pipeline-execution hot path.
+ *
+ * The reference (SymbioticLab/Oobleck @ 3b7a0c2f) has NO native boundary on this path: every stage layer is a
+ * torch.fx.GraphModule of HF GPT-2 modules run by torch eager (oobleck/execution/layer.py:144-145,
+ * oobleck/execution/pipeline.py:169-245), and every transfer is torch.distributed send/recv
+ * (pipeline.py:270-427).  The functions below are what a maintainer binds in place of those calls; each one
+ * cites the reference statement(s) it replaces.  INTEGRATION.md shows the Python (ctypes) side.
+ *
+ * Conventions
+ *   - every function returns 0 on success, <0 on error; oob_last_error() returns the message (thread local)
+ *   - all data pointers are CUDA device pointers owned by the caller (torch tensors' data_ptr()); `stream` is a
+ *     cudaStream_t passed as void*; nothing synchronises the device or allocates device memory
+ *   - "planes" are the split-bf16 representation of an fp32 matrix: [nplanes][rows][ld] bf16 with
+ *     x == p0 + p1 + p2 to 24 bits.  They are what the tcgen05 GEMMs consume; see DESIGN.md "Data layout".
+ */
+#ifndef OOBLECK_B200_H_
+#define OOBLECK_B200_H_
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+int oob_version(void);
+const char* oob_last_error(void);
+/* sizes of the scratch buffers the reductions below need, in floats */
+long oob_ln_bwd_partials_floats(int n_embd);
+long oob_colsum_partials_floats(int cols);
+
+/* ---- split planes --------------------------------------------------------------------------------------- */
+typedef struct oob_planes {
+  const void* base;   /* bf16 [nplanes][rows][ld] */
+  long rows, cols;    /* stored matrix shape */
+  long ld;            /* row stride in elements, multiple of 8 */
+  long plane_stride;  /* elements between planes, multiple of 8 */
+  int nplanes;
+} oob_planes;
+
+/* fp32 -> planes (flat); used for freshly initialised / received parameters (layer.py:26-37 init_tensors) */
+int oob_split_planes(const float* x, void* planes, long n, long plane_stride, int nplanes, void* stream);
+
+/* ---- GEMM: replaces torch.addmm / F.linear inside HF Conv1D + lm_head and their autograd backward --------
+ * D[M,N] = alpha * A.B (+bias) (+resid) (+D if accumulate), optional GELU / dGELU, fp32 and/or planes output.
+ * a_mn_major = 0: A stored [M,K];  1: A stored [K,M].   b_mn_major = 0: B stored [N,K];  1: B stored [K,N].
+ * nsplit = 1|2|3 planes per operand (3 = fp32-grade, the parity mode). */
+typedef struct oob_gemm_epilogue {
+  float* d; long ldd;
+  const float* bias;
+  const float* resid; long ldr;
+  int accumulate;
+  int act;                 /* 0 none, 1 GELU(new): d=pre-activation, planes=gelu;  2 dGELU: value*=gelu'(aux) */
+  const float* aux; long ldaux;
+  void* planes; long ldp; long plane_stride; int nplanes_out;
+  float alpha;
+} oob_gemm_epilogue;
+
+int oob_gemm(const oob_planes* a, int a_mn_major, const oob_planes* b, int b_mn_major, int M, int N, int K,
+             int nsplit, const oob_gemm_epilogue* epi, void* stream);
+
+/* ---- LayerNorm (HF ln_1 / ln_2 / ln_f, eps 1e-5): F.layer_norm and its backward ------------------------- */
+int oob_layernorm_fwd(const float* x, const float* gamma, const float* beta, float* y, void* y_planes,
+                      long plane_stride, int nplanes, float* mean, float* rstd, int rows, int n_embd, float eps,
+                      void* stream);
+/* dx = (dres ? dres : 0) + LN'(dy); dgamma/dbeta are ACCUMULATED (+=) */
+int oob_layernorm_bwd(const float* dy, const float* x, const float* mean, const float* rstd, const float* gamma,
+                      const float* dres, float* dx, void* dx_planes, long plane_stride, int nplanes, float* dgamma,
+                      float* dbeta, float* partials, int rows, int n_embd, void* stream);
+/* out[n] += sum_m a[m,n]  (bias gradients) */
+int oob_colsum_accumulate(const float* a, long lda, int rows, int cols, float* out, float* partials, void* stream);
+
+/* ---- attention (HF GPT2Attention eager: causal softmax(QK^T/sqrt(d))V, no dropout) ----------------------- */
+int oob_attention_fwd(const float* qkv, float* out, void* out_planes, long plane_stride, int nplanes, float* lse,
+                      int batch, int seq, int n_head, int head_dim, void* stream);
+int oob_attention_bwd(const float* qkv, const float* out, const float* dout, const float* lse, float* delta,
+                      float* dqkv, void* dqkv_planes, long plane_stride, int nplanes, int batch, int seq, int n_head,
+                      int head_dim, void* stream);
+
+/* ---- fx layer 0 (wte[ids] + wpe[pos]) and its backward --------------------------------------------------- */
+int oob_embedding_fwd(const long long* ids, const float* wte, const float* wpe, float* hidden, int rows, int seq,
+                      int n_embd, void* stream);
+int oob_embedding_bwd(const long long* ids, const float* dhidden, float* dwte, float* dwpe, int batch, int seq,
+                      int n_embd, void* stream);
+
+/* ---- fx layer L+1 tail: shifted CrossEntropyLoss(mean) on logits[M, ldl], gradient into planes ----------- */
+int oob_cross_entropy(const float* logits, long ldl, const long long* labels, int batch, int seq, int vocab,
+                      float* row_loss, float* loss, float* total_loss, void* dlogits_planes, long ldp,
+                      long plane_stride, int nplanes, void* stream);
+
+/* ---- optimizer: torch.optim.AdamW(fused=True).step() over one layer's flat parameter (pipeline.py:117-123) */
+int oob_adamw_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, void* planes,
+                   long plane_stride, int nplanes, long n, float lr, float beta1, float beta2, float eps,
+                   float weight_decay, int step, void* stream);
+
+/* ==== stage layers ===========================================================================================
+ * One call per stage layer per micro-batch: this is what PipelineExecution.forward_pass's
+ * ``for layer in self._layers: inputs = layer(inputs)`` (pipeline.py:188-189) and Layer.backward's
+ * torch.autograd.backward (layer.py:250-260) turn into.  The reference re-computes block forwards under
+ * checkpoint_wrapper (layer.py:93-94); here forward saves what backward needs into a caller-owned oob_block_ctx
+ * (one per in-flight micro-batch, 180 GB of HBM makes recomputation unnecessary). */
+typedef struct oob_dims {
+  int batch, seq;          /* micro-batch shape: M = batch*seq rows */
+  int n_embd, n_head;      /* head_dim = n_embd / n_head must be 64 */
+  int vocab, vocab_padded; /* vocab_padded: row stride of logits buffers, multiple of 64 */
+  float ln_eps;
+  int nsplit;              /* planes per GEMM operand: 3 = fp32-grade (parity), 2, 1 */
+} oob_dims;
+
+/* parameters of one stage layer: flat fp32 vector in HF ``layer.parameters()`` order (what FSDP's FlatParamHandle
+ * flattens, layer.py:96-111), its split planes [3][plane_stride] and the flat fp32 gradient (accumulated). */
+typedef struct oob_layer_params {
+  const float* w;
+  const void* w_planes;
+  long plane_stride;
+  float* g;
+} oob_layer_params;
+
+typedef struct oob_block_ctx {      /* saved activations of one micro-batch through one GPT2Block */
+  void* ln1_planes;  float* ln1_mean; float* ln1_rstd;   /* [3][M][E], [M], [M] */
+  float* qkv;                                            /* [M,3E] */
+  float* att; void* att_planes; float* lse;              /* [M,E], [3][M][E], [B,H,T] */
+  float* x2;                                             /* [M,E] hidden after the attention residual */
+  void* ln2_planes;  float* ln2_mean; float* ln2_rstd;
+  float* fc; void* gelu_planes;                          /* [M,4E] pre-activation, [3][M][4E] */
+} oob_block_ctx;
+
+typedef struct oob_bwd_scratch {    /* per-stage backward temporaries, reused by every layer / micro-batch */
+  float* dfc; void* dfc_planes;     /* [M,4E], [3][M][4E] */
+  float* dln;                       /* [M,E] */
+  float* dx2; void* dx2_planes;     /* [M,E], [3][M][E] */
+  float* datt;                      /* [M,E] */
+  float* delta;                     /* [B*H*T] */
+  float* dqkv; void* dqkv_planes;   /* [M,3E], [3][M][3E] */
+  float* partials;                  /* max(oob_ln_bwd_partials_floats(E), oob_colsum_partials_floats(4E)) floats */
+} oob_bwd_scratch;
+
+typedef struct oob_head_ctx {       /* ln_f + lm_head + loss for one micro-batch */
+  void* lnf_planes; float* mean; float* rstd;            /* [3][M][E], [M], [M] */
+  float* logits;                                         /* [M, vocab_padded] */
+  void* dlogits_planes;                                  /* [3][M][vocab_padded] */
+  float* row_loss;                                       /* [M] */
+  float* loss;                                           /* [1] this micro-batch's mean loss */
+} oob_head_ctx;
+
+/* y[M,E] = GPT2Block(x[M,E]) */
+int oob_block_forward(const oob_dims* d, const oob_layer_params* p, const float* x, float* y, oob_block_ctx* ctx,
+                      void* stream);
+/* dx (fp32 + planes) = dBlock/dx . dy ; parameter gradients accumulate into p->g */
+int oob_block_backward(const oob_dims* d, const oob_layer_params* p, const float* x, const oob_block_ctx* ctx,
+                       const float* dy, const void* dy_planes, oob_bwd_scratch* s, float* dx, void* dx_planes,
+                       void* stream);
+/* loss = CE(lm_head(ln_f(x)), shift(labels)); also produces dloss/dlogits (scaled by 1/(B(T-1))) in ctx.
+ * total_loss (may be NULL) += loss  -- pipeline.py:196-201 */
+int oob_head_forward(const oob_dims* d, const oob_layer_params* p, const float* x, const long long* labels,
+                     oob_head_ctx* ctx, float* total_loss, void* stream);
+int oob_head_backward(const oob_dims* d, const oob_layer_params* p, const float* x, const oob_head_ctx* ctx,
+                      oob_bwd_scratch* s, float* dx, void* dx_planes, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* OOBLECK_B200_H_ */

@@ -1,0 +1,99 @@
+// Host launcher for the tcgen05 split-bf16 GEMM: builds the TMA tensor maps and picks the stage count.
+#include <mutex>
+
+#include "gemm_sm100.cuh"
+
+namespace oob {
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  });
+  return fn;
+}
+
+// 3-D map over [planes][rows][ld] bf16; box = {64 elements, box_rows, box_planes}, SWIZZLE_128B.
+static int make_map(CUtensorMap* m, const PlaneMat& a, int box_rows, int box_planes) {
+  EncodeTiledFn enc = get_encode_fn();
+  OOB_CHECK(enc != nullptr, "cuTensorMapEncodeTiled entry point unavailable (no CUDA driver?)");
+  OOB_CHECK((a.ld % 8) == 0 && (a.plane_stride % 8) == 0, "split-plane operand strides must be multiples of 8");
+  OOB_CHECK((reinterpret_cast<uintptr_t>(a.base) & 15) == 0, "split-plane operand must be 16 B aligned");
+  OOB_CHECK(box_planes <= a.nplanes, "GEMM asks for %d planes, operand has %d", box_planes, a.nplanes);
+  cuuint64_t dims[3] = {(cuuint64_t)a.cols, (cuuint64_t)a.rows, (cuuint64_t)a.nplanes};
+  cuuint64_t strides[2] = {(cuuint64_t)a.ld * 2, (cuuint64_t)a.plane_stride * 2};
+  cuuint32_t box[3] = {64, (cuuint32_t)box_rows, (cuuint32_t)box_planes};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<bf16*>(a.base), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  OOB_CHECK(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed (%d): rows=%ld cols=%ld ld=%ld", (int)r, a.rows, a.cols,
+            a.ld);
+  return 0;
+}
+
+template <int BN, bool A_MN, bool B_MN>
+static int launch_t(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, cudaStream_t stream) {
+  static int max_smem = -1;
+  if (max_smem < 0) {
+    int dev = 0;
+    OOB_CUDA_OK(cudaGetDevice(&dev));
+    OOB_CUDA_OK(cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
+  }
+  static bool attr_set = false;
+  auto kern = gemm_bf16x3_kernel<BN, A_MN, B_MN>;
+  if (!attr_set) {
+    OOB_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
+    attr_set = true;
+  }
+  const int stage = gemm_stage_bytes<BN>(p.nsplit);
+  const int overhead = 1024 /*align slack*/ + 256 /*barriers*/;
+  int stages = (max_smem - overhead) / stage;
+  if (stages > 8) stages = 8;
+  OOB_CHECK(stages >= 2, "GEMM tile does not fit %d B of shared memory", max_smem);
+  const size_t smem = (size_t)stages * stage + overhead;
+  dim3 grid((p.N + BN - 1) / BN, (p.M + GEMM_BM - 1) / GEMM_BM);
+  kern<<<grid, GEMM_THREADS, smem, stream>>>(ta, tb, p, stages);
+  OOB_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+int gemm_launch(const PlaneMat& A, int a_mn, const PlaneMat& B, int b_mn, const GemmParams& p, cudaStream_t stream) {
+  OOB_CHECK(p.nsplit >= 1 && p.nsplit <= 3, "nsplit must be 1..3");
+  OOB_CHECK(p.M > 0 && p.N > 0 && p.K > 0, "empty GEMM %d x %d x %d", p.M, p.N, p.K);
+  constexpr int BN = 128;
+  CUtensorMap ta, tb;
+  int rc;
+  // K-major operand: stored [MN][K] -> box {64 k, tile rows, planes}; MN-major: stored [K][MN] -> box {64 mn, BK rows}
+  if (!a_mn) {
+    OOB_CHECK(A.rows >= p.M && A.cols >= p.K, "A (K-major) is %ld x %ld, need %d x %d", A.rows, A.cols, p.M, p.K);
+    rc = make_map(&ta, PlaneMat{A.base, (long)p.M, (long)p.K, A.ld, A.plane_stride, A.nplanes}, GEMM_BM, p.nsplit);
+  } else {
+    OOB_CHECK(A.rows >= p.K && A.cols >= p.M, "A (M-major) is %ld x %ld, need %d x %d", A.rows, A.cols, p.K, p.M);
+    rc = make_map(&ta, PlaneMat{A.base, (long)p.K, (long)p.M, A.ld, A.plane_stride, A.nplanes}, GEMM_BK, p.nsplit);
+  }
+  if (rc) return rc;
+  if (!b_mn) {
+    OOB_CHECK(B.rows >= p.N && B.cols >= p.K, "B (K-major) is %ld x %ld, need %d x %d", B.rows, B.cols, p.N, p.K);
+    rc = make_map(&tb, PlaneMat{B.base, (long)p.N, (long)p.K, B.ld, B.plane_stride, B.nplanes}, BN, p.nsplit);
+  } else {
+    OOB_CHECK(B.rows >= p.K && B.cols >= p.N, "B (N-major) is %ld x %ld, need %d x %d", B.rows, B.cols, p.K, p.N);
+    rc = make_map(&tb, PlaneMat{B.base, (long)p.K, (long)p.N, B.ld, B.plane_stride, B.nplanes}, GEMM_BK, p.nsplit);
+  }
+  if (rc) return rc;
+  if (!a_mn && !b_mn) return launch_t<BN, false, false>(ta, tb, p, stream);
+  if (!a_mn && b_mn) return launch_t<BN, false, true>(ta, tb, p, stream);
+  if (a_mn && !b_mn) return launch_t<BN, true, false>(ta, tb, p, stream);
+  return launch_t<BN, true, true>(ta, tb, p, stream);
+}
+
+}  // namespace oob

@@ -1,0 +1,187 @@
+// Stage-layer composition: one GPT2Block / head forward or backward = a fixed sequence of the kernels in this
+// library on one stream.  Mirrors the arithmetic of oracle/gpt2.py (which restates HF GPT2Block, the module the
+// reference's fx shards execute) and its autograd backward.
+#include "../../include/oobleck_b200.h"
+#include "kernels.h"
+
+using namespace oob;
+
+namespace {
+
+struct BlockOffsets {  // element offsets inside the flat parameter vector, HF GPT2Block.parameters() order
+  long ln1_w, ln1_b, attn_w, attn_b, proj_w, proj_b, ln2_w, ln2_b, fc_w, fc_b, proj2_w, proj2_b, total;
+  explicit BlockOffsets(long E) {
+    long o = 0;
+    ln1_w = o; o += E;
+    ln1_b = o; o += E;
+    attn_w = o; o += E * 3 * E;
+    attn_b = o; o += 3 * E;
+    proj_w = o; o += E * E;
+    proj_b = o; o += E;
+    ln2_w = o; o += E;
+    ln2_b = o; o += E;
+    fc_w = o; o += E * 4 * E;
+    fc_b = o; o += 4 * E;
+    proj2_w = o; o += 4 * E * E;
+    proj2_b = o; o += E;
+    total = o;
+  }
+};
+
+inline PlaneMat weight_planes(const oob_layer_params* p, long off, long rows, long cols) {
+  return PlaneMat{reinterpret_cast<const bf16*>(p->w_planes) + off, rows, cols, cols, p->plane_stride, 3};
+}
+inline PlaneMat act_planes(const void* base, long rows, long cols) {
+  return PlaneMat{reinterpret_cast<const bf16*>(base), rows, cols, cols, rows * cols, 3};
+}
+inline GemmEpilogue epi_none() {
+  GemmEpilogue e{};
+  e.alpha = 1.0f;
+  return e;
+}
+
+// D = A[M,K] . W[K,N] + bias (+resid), optional GELU planes
+int linear_fwd(const PlaneMat& a, const oob_layer_params* p, long w_off, long b_off, int M, int N, int K, int nsplit,
+               float* d, const float* resid, bf16* gelu_planes, cudaStream_t st) {
+  GemmParams gp{M, N, K, nsplit, epi_none()};
+  gp.epi.d = d; gp.epi.ldd = N;
+  gp.epi.bias = p->w + b_off;
+  gp.epi.resid = resid; gp.epi.ldr = N;
+  if (gelu_planes) {
+    gp.epi.act = ACT_GELU;
+    gp.epi.planes = gelu_planes; gp.epi.ldp = N; gp.epi.plane_stride = (long)M * N; gp.epi.nplanes_out = 3;
+  }
+  return gemm_launch(a, 0, weight_planes(p, w_off, K, N), 1, gp, st);
+}
+// dA[M,K] = dY[M,N] . W[K,N]^T  (optionally * gelu'(aux), planes out)
+int linear_dgrad(const PlaneMat& dy, const oob_layer_params* p, long w_off, int M, int N, int K, int nsplit, float* dA,
+                 const float* dgelu_aux, bf16* planes_out, cudaStream_t st) {
+  GemmParams gp{M, K, N, nsplit, epi_none()};
+  gp.epi.d = dA; gp.epi.ldd = K;
+  if (dgelu_aux) { gp.epi.act = ACT_DGELU; gp.epi.aux = dgelu_aux; gp.epi.ldaux = K; }
+  if (planes_out) { gp.epi.planes = planes_out; gp.epi.ldp = K; gp.epi.plane_stride = (long)M * K; gp.epi.nplanes_out = 3; }
+  return gemm_launch(dy, 0, weight_planes(p, w_off, K, N), 0, gp, st);
+}
+// dW[K,N] += A[M,K]^T . dY[M,N]
+int linear_wgrad(const PlaneMat& a, const PlaneMat& dy, const oob_layer_params* p, long w_off, int M, int N, int K,
+                 int nsplit, cudaStream_t st) {
+  GemmParams gp{K, N, M, nsplit, epi_none()};
+  gp.epi.d = p->g + w_off; gp.epi.ldd = N; gp.epi.accumulate = 1;
+  return gemm_launch(a, 1, dy, 1, gp, st);
+}
+
+int check_dims(const oob_dims* d) {
+  OOB_CHECK(d->n_embd % 8 == 0, "n_embd must be a multiple of 8");
+  OOB_CHECK(d->n_head > 0 && d->n_embd / d->n_head == 64 && d->n_embd % d->n_head == 0, "head_dim must be 64");
+  OOB_CHECK(d->nsplit >= 1 && d->nsplit <= 3, "nsplit must be 1..3");
+  OOB_CHECK(d->batch > 0 && d->seq > 1, "bad micro-batch shape");
+  return 0;
+}
+
+}  // namespace
+
+extern "C" {
+
+int oob_block_forward(const oob_dims* d, const oob_layer_params* p, const float* x, float* y, oob_block_ctx* c,
+                      void* stream) {
+  if (int rc = check_dims(d)) return rc;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  const int M = d->batch * d->seq, E = d->n_embd, ns = d->nsplit;
+  const BlockOffsets o(E);
+  const long ME = (long)M * E;
+  int rc;
+  if ((rc = layernorm_fwd(x, p->w + o.ln1_w, p->w + o.ln1_b, nullptr, (bf16*)c->ln1_planes, ME, 3, c->ln1_mean,
+                          c->ln1_rstd, M, E, d->ln_eps, st))) return rc;
+  if ((rc = linear_fwd(act_planes(c->ln1_planes, M, E), p, o.attn_w, o.attn_b, M, 3 * E, E, ns, c->qkv, nullptr,
+                       nullptr, st))) return rc;
+  if ((rc = attention_fwd(c->qkv, c->att, (bf16*)c->att_planes, ME, 3, c->lse, d->batch, d->seq, d->n_head, 64, st)))
+    return rc;
+  if ((rc = linear_fwd(act_planes(c->att_planes, M, E), p, o.proj_w, o.proj_b, M, E, E, ns, c->x2, x, nullptr, st)))
+    return rc;
+  if ((rc = layernorm_fwd(c->x2, p->w + o.ln2_w, p->w + o.ln2_b, nullptr, (bf16*)c->ln2_planes, ME, 3, c->ln2_mean,
+                          c->ln2_rstd, M, E, d->ln_eps, st))) return rc;
+  if ((rc = linear_fwd(act_planes(c->ln2_planes, M, E), p, o.fc_w, o.fc_b, M, 4 * E, E, ns, c->fc, nullptr,
+                       (bf16*)c->gelu_planes, st))) return rc;
+  if ((rc = linear_fwd(act_planes(c->gelu_planes, M, 4 * E), p, o.proj2_w, o.proj2_b, M, E, 4 * E, ns, y, c->x2,
+                       nullptr, st))) return rc;
+  return 0;
+}
+
+int oob_block_backward(const oob_dims* d, const oob_layer_params* p, const float* x, const oob_block_ctx* c,
+                       const float* dy, const void* dy_planes, oob_bwd_scratch* s, float* dx, void* dx_planes,
+                       void* stream) {
+  if (int rc = check_dims(d)) return rc;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  const int M = d->batch * d->seq, E = d->n_embd, ns = d->nsplit;
+  const BlockOffsets o(E);
+  const long ME = (long)M * E;
+  const PlaneMat dyp = act_planes(dy_planes, M, E);
+  int rc;
+  // ---- MLP ----
+  // d(fc pre-activation) = (dy . Wp2^T) * gelu'(fc)
+  if ((rc = linear_dgrad(dyp, p, o.proj2_w, M, E, 4 * E, ns, s->dfc, c->fc, (bf16*)s->dfc_planes, st))) return rc;
+  if ((rc = linear_wgrad(act_planes(c->gelu_planes, M, 4 * E), dyp, p, o.proj2_w, M, E, 4 * E, ns, st))) return rc;
+  if ((rc = colsum_accumulate(dy, E, M, E, p->g + o.proj2_b, s->partials, st))) return rc;
+  const PlaneMat dfcp = act_planes(s->dfc_planes, M, 4 * E);
+  if ((rc = linear_dgrad(dfcp, p, o.fc_w, M, 4 * E, E, ns, s->dln, nullptr, nullptr, st))) return rc;
+  if ((rc = linear_wgrad(act_planes(c->ln2_planes, M, E), dfcp, p, o.fc_w, M, 4 * E, E, ns, st))) return rc;
+  if ((rc = colsum_accumulate(s->dfc, 4 * E, M, 4 * E, p->g + o.fc_b, s->partials, st))) return rc;
+  // dx2 = dy + LN2'(dln)
+  if ((rc = layernorm_bwd(s->dln, c->x2, c->ln2_mean, c->ln2_rstd, p->w + o.ln2_w, dy, s->dx2, (bf16*)s->dx2_planes,
+                          ME, 3, p->g + o.ln2_w, p->g + o.ln2_b, s->partials, M, E, st))) return rc;
+  // ---- attention ----
+  const PlaneMat dx2p = act_planes(s->dx2_planes, M, E);
+  if ((rc = linear_dgrad(dx2p, p, o.proj_w, M, E, E, ns, s->datt, nullptr, nullptr, st))) return rc;
+  if ((rc = linear_wgrad(act_planes(c->att_planes, M, E), dx2p, p, o.proj_w, M, E, E, ns, st))) return rc;
+  if ((rc = colsum_accumulate(s->dx2, E, M, E, p->g + o.proj_b, s->partials, st))) return rc;
+  if ((rc = attention_bwd(c->qkv, c->att, s->datt, c->lse, s->delta, s->dqkv, (bf16*)s->dqkv_planes, (long)M * 3 * E, 3,
+                          d->batch, d->seq, d->n_head, 64, st))) return rc;
+  const PlaneMat dqkvp = act_planes(s->dqkv_planes, M, 3 * E);
+  if ((rc = linear_dgrad(dqkvp, p, o.attn_w, M, 3 * E, E, ns, s->dln, nullptr, nullptr, st))) return rc;
+  if ((rc = linear_wgrad(act_planes(c->ln1_planes, M, E), dqkvp, p, o.attn_w, M, 3 * E, E, ns, st))) return rc;
+  if ((rc = colsum_accumulate(s->dqkv, 3 * E, M, 3 * E, p->g + o.attn_b, s->partials, st))) return rc;
+  // dx = dx2 + LN1'(dln)
+  if ((rc = layernorm_bwd(s->dln, x, c->ln1_mean, c->ln1_rstd, p->w + o.ln1_w, s->dx2, dx, (bf16*)dx_planes, ME, 3,
+                          p->g + o.ln1_w, p->g + o.ln1_b, s->partials, M, E, st))) return rc;
+  return 0;
+}
+
+int oob_head_forward(const oob_dims* d, const oob_layer_params* p, const float* x, const long long* labels,
+                     oob_head_ctx* c, float* total_loss, void* stream) {
+  if (int rc = check_dims(d)) return rc;
+  OOB_CHECK(d->vocab_padded % 64 == 0 && d->vocab_padded >= d->vocab, "vocab_padded must be a multiple of 64");
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  const int M = d->batch * d->seq, E = d->n_embd, V = d->vocab, Vp = d->vocab_padded, ns = d->nsplit;
+  const long ME = (long)M * E;
+  int rc;
+  // flat layout: ln_f.weight [E], ln_f.bias [E], lm_head.weight [V,E]
+  if ((rc = layernorm_fwd(x, p->w, p->w + E, nullptr, (bf16*)c->lnf_planes, ME, 3, c->mean, c->rstd, M, E, d->ln_eps,
+                          st))) return rc;
+  GemmParams gp{M, V, E, ns, epi_none()};
+  gp.epi.d = c->logits; gp.epi.ldd = Vp;
+  if ((rc = gemm_launch(act_planes(c->lnf_planes, M, E), 0, weight_planes(p, 2 * E, V, E), 0, gp, st))) return rc;
+  return cross_entropy(c->logits, Vp, labels, d->batch, d->seq, V, c->row_loss, c->loss, total_loss,
+                       (bf16*)c->dlogits_planes, Vp, (long)M * Vp, 3, st);
+}
+
+int oob_head_backward(const oob_dims* d, const oob_layer_params* p, const float* x, const oob_head_ctx* c,
+                      oob_bwd_scratch* s, float* dx, void* dx_planes, void* stream) {
+  if (int rc = check_dims(d)) return rc;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  const int M = d->batch * d->seq, E = d->n_embd, V = d->vocab, Vp = d->vocab_padded, ns = d->nsplit;
+  const long ME = (long)M * E;
+  const PlaneMat dlog{reinterpret_cast<const bf16*>(c->dlogits_planes), M, Vp, Vp, (long)M * Vp, 3};
+  int rc;
+  // d(ln_f out)[M,E] = dlogits[M,V] . Wlm[V,E]
+  GemmParams g1{M, E, V, ns, epi_none()};
+  g1.epi.d = s->dln; g1.epi.ldd = E;
+  if ((rc = gemm_launch(dlog, 0, weight_planes(p, 2 * E, V, E), 1, g1, st))) return rc;
+  // dWlm[V,E] += dlogits^T . lnf
+  GemmParams g2{V, E, M, ns, epi_none()};
+  g2.epi.d = p->g + 2 * E; g2.epi.ldd = E; g2.epi.accumulate = 1;
+  if ((rc = gemm_launch(dlog, 1, act_planes(c->lnf_planes, M, E), 1, g2, st))) return rc;
+  return layernorm_bwd(s->dln, x, c->mean, c->rstd, p->w, nullptr, dx, (bf16*)dx_planes, ME, 3, p->g, p->g + E,
+                       s->partials, M, E, st);
+}
+
+}  // extern "C"

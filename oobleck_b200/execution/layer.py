@@ -1,0 +1,267 @@
+"""``Layer``: one stage layer materialised on a B200.
+
+Replaces oobleck/execution/layer.py:40-291.  The reference wraps a deep-copied fx GraphModule in an FSDP
+``FlatParamHandle`` and lets torch.autograd run it; here a layer is
+
+* one flat fp32 parameter vector in HF ``parameters()`` order (``_param_handle.flat_param`` keeps the reference's
+  attribute path so the reconfiguration / DP code that pokes it keeps working, engine.py:284-306),
+* its flat fp32 gradient (``flat_param.grad``), AdamW moments and the split-bf16 planes the tcgen05 GEMMs read,
+* per pipe-buffer activation contexts that the hand-written forward fills and the hand-written backward consumes
+  (no autograd graph, no checkpoint recompute -- layer.py:93-94 re-runs every block forward in backward).
+
+FSDP sharding inside a stage (layer.py:96-142, 167-225) is out of scope for this round: every BASELINE config runs
+one GPU per stage, which is the reference's ``NO_SHARD`` branch (layer.py:100-102).
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+
+import torch
+
+from .. import lib as L
+from ..module.model import StageLayerSpec
+
+
+from ..lib import OobBlockCtx, OobBwdScratch, OobDims, OobHeadCtx, OobLayerParams  # noqa: E402
+
+
+def _stream() -> C.c_void_p:
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _round8(n: int) -> int:
+    return (n + 7) // 8 * 8
+
+
+class StageWorkspace:
+    """Backward temporaries of one stage (``oob_bwd_scratch``) plus the two ping-pong gradient buffers that carry
+    d(hidden) from layer to layer.  Shared by all layers of the stage: backward is serial on one stream."""
+
+    def __init__(self, microbatch: int, seq: int, n_embd: int, n_head: int, device: torch.device):
+        M, E = microbatch * seq, n_embd
+        f32 = dict(dtype=torch.float32, device=device)
+        bf = dict(dtype=torch.bfloat16, device=device)
+        lib = L.load()
+        nparts = max(lib.oob_ln_bwd_partials_floats(E), lib.oob_colsum_partials_floats(4 * E))
+        self.t = {
+            "dfc": torch.empty(M, 4 * E, **f32), "dfc_planes": torch.empty(3, M, 4 * E, **bf),
+            "dln": torch.empty(M, E, **f32), "dx2": torch.empty(M, E, **f32), "dx2_planes": torch.empty(3, M, E, **bf),
+            "datt": torch.empty(M, E, **f32), "delta": torch.empty(microbatch * n_head * seq, **f32),
+            "dqkv": torch.empty(M, 3 * E, **f32), "dqkv_planes": torch.empty(3, M, 3 * E, **bf),
+            "partials": torch.empty(nparts, **f32),
+        }
+        self.scratch = OobBwdScratch(**{k: v.data_ptr() for k, v in self.t.items()})
+        self.dx = [torch.empty(M, E, **f32) for _ in range(2)]
+        self.dx_planes = [torch.empty(3, M, E, **bf) for _ in range(2)]
+        self.recv_planes = torch.empty(3, M, E, **bf)  # planes of a gradient received from the next stage
+        self.flip = 0
+
+    def next_dx(self):
+        self.flip ^= 1
+        return self.dx[self.flip], self.dx_planes[self.flip]
+
+
+@dataclass
+class HiddenGrad:
+    """Gradient w.r.t. a hidden state travelling backwards through a stage: fp32 + (optionally) its planes."""
+    grad: torch.Tensor
+    planes: torch.Tensor | None = None
+
+
+class _ParamHandle:
+    """Just enough of FSDP's FlatParamHandle for the callers that reach through ``layer._param_handle``."""
+
+    def __init__(self, flat_param: torch.Tensor, process_group):
+        self.flat_param = flat_param
+        self.process_group = process_group
+        self._sharding_strategy = "NO_SHARD"   # layer.py:100-102 when the per-layer group has one rank
+
+
+class Layer:
+    """Constructor keeps the reference's positional order (layer.py:71-78)."""
+
+    def __init__(self, layer_id: int, layer: StageLayerSpec, process_group=None, pre_stream=None, post_stream=None, *,
+                 microbatch_size: int, num_pipe_buffers: int, workspace: StageWorkspace | None = None,
+                 nsplit: int = 3, device: torch.device | None = None, seq_len: int | None = None):
+        L.load()  # fail loudly if the CUDA extension is missing
+        if not torch.cuda.is_available():
+            raise L.OobleckB200Error("oobleck_b200.Layer needs a CUDA device (there is no CPU path)")
+        self.layer_id = layer_id
+        self.spec = layer
+        self.device = device or torch.device("cuda", torch.cuda.current_device())
+        self._rank_index = process_group.rank_index() if hasattr(process_group, "rank_index") else 0
+        self._group_size = process_group.size() if hasattr(process_group, "size") else 1
+        if self._group_size != 1:
+            raise NotImplementedError("intra-stage FSDP sharding (layer.py:96-225) is out of scope this round")
+        self.pre_stream, self.post_stream = pre_stream, post_stream
+        self.nsplit = nsplit
+        self.mb = microbatch_size
+        self.T = seq_len or layer.n_positions
+        self.num_pipe_buffers = num_pipe_buffers
+        self.workspace = workspace
+
+        n = layer.num_params
+        self.numel = n
+        self.plane_stride = _round8(n)
+        flat = layer.init_flat().to(self.device)
+        flat.requires_grad_(False)
+        flat.grad = torch.zeros(n, dtype=torch.float32, device=self.device)
+        self._param_handle = _ParamHandle(flat, process_group)
+        self.exp_avg = torch.zeros(n, dtype=torch.float32, device=self.device)
+        self.exp_avg_sq = torch.zeros(n, dtype=torch.float32, device=self.device)
+        self.planes = torch.empty(3, self.plane_stride, dtype=torch.bfloat16, device=self.device)
+        self.refresh_planes()
+
+        E, V = layer.n_embd, layer.vocab_size
+        self.dims = OobDims(self.mb, self.T, E, layer.n_head, V, (V + 63) // 64 * 64, layer.layer_norm_epsilon, nsplit)
+        self._alloc_contexts()
+
+    # -- parameters ------------------------------------------------------------------------------------------------
+    @property
+    def flat_param(self) -> torch.Tensor:
+        return self._param_handle.flat_param
+
+    @property
+    def flat_grad(self) -> torch.Tensor:
+        return self._param_handle.flat_param.grad
+
+    def _params_struct(self) -> OobLayerParams:
+        return OobLayerParams(self.flat_param.data_ptr(), self.planes.data_ptr(), self.plane_stride,
+                              self.flat_grad.data_ptr())
+
+    def refresh_planes(self) -> None:
+        L.call("oob_split_planes", C.c_void_p(self.flat_param.data_ptr()), C.c_void_p(self.planes.data_ptr()),
+               self.numel, self.plane_stride, 3, _stream())
+
+    def load_flat_(self, flat: torch.Tensor) -> None:
+        """Install explicit weights (parity tests, reconfiguration copies)."""
+        assert flat.numel() == self.numel
+        self.flat_param.copy_(flat.to(self.device, torch.float32))
+        self.refresh_planes()
+
+    def zero_grad(self) -> None:
+        self.flat_grad.zero_()
+
+    def remove_tensors(self) -> None:  # layer.py:66-69
+        empty = torch.tensor([], device=self.device)
+        if self.flat_param.grad is not None:
+            self.flat_param.grad = None
+        self.flat_param.data = empty
+        self.planes = self.exp_avg = self.exp_avg_sq = empty
+        self.ctx_tensors, self.out = [], []
+
+    @classmethod
+    def create_layer_from_layer(cls, existing_layer: "Layer", process_group) -> "Layer":  # layer.py:41-64
+        existing_layer._param_handle.process_group = process_group
+        return existing_layer
+
+    # -- activations -----------------------------------------------------------------------------------------------
+    def _alloc_contexts(self) -> None:
+        M, E, H = self.mb * self.T, self.spec.n_embd, self.spec.n_head
+        f32 = dict(dtype=torch.float32, device=self.device)
+        bf = dict(dtype=torch.bfloat16, device=self.device)
+        self.ctx_tensors, self.ctx, self.out, self.saved_in = [], [], [], [None] * self.num_pipe_buffers
+        for _ in range(self.num_pipe_buffers):
+            if self.spec.kind == "block":
+                t = {"ln1_planes": torch.empty(3, M, E, **bf), "ln1_mean": torch.empty(M, **f32),
+                     "ln1_rstd": torch.empty(M, **f32), "qkv": torch.empty(M, 3 * E, **f32),
+                     "att": torch.empty(M, E, **f32), "att_planes": torch.empty(3, M, E, **bf),
+                     "lse": torch.empty(self.mb * H * self.T, **f32), "x2": torch.empty(M, E, **f32),
+                     "ln2_planes": torch.empty(3, M, E, **bf), "ln2_mean": torch.empty(M, **f32),
+                     "ln2_rstd": torch.empty(M, **f32), "fc": torch.empty(M, 4 * E, **f32),
+                     "gelu_planes": torch.empty(3, M, 4 * E, **bf)}
+                self.ctx.append(OobBlockCtx(**{k: v.data_ptr() for k, v in t.items()}))
+                self.out.append(torch.empty(self.mb, self.T, E, **f32))
+            elif self.spec.kind == "head":
+                Vp = self.dims.vocab_padded
+                t = {"lnf_planes": torch.empty(3, M, E, **bf), "mean": torch.empty(M, **f32),
+                     "rstd": torch.empty(M, **f32), "logits": torch.empty(M, Vp, **f32),
+                     "dlogits_planes": torch.empty(3, M, Vp, **bf), "row_loss": torch.empty(M, **f32),
+                     "loss": torch.zeros(1, **f32)}
+                self.ctx.append(OobHeadCtx(**{k: v.data_ptr() for k, v in t.items()}))
+                self.out.append(t["loss"])
+            else:
+                t = {}
+                self.ctx.append(None)
+                self.out.append(torch.empty(self.mb, self.T, E, **f32))
+            self.ctx_tensors.append(t)
+
+    # -- compute ---------------------------------------------------------------------------------------------------
+    def __call__(self, inputs: tuple, buffer_id: int = 0, total_loss: torch.Tensor | None = None) -> tuple:
+        return self.forward(inputs, buffer_id, total_loss)
+
+    def forward(self, inputs: tuple, buffer_id: int = 0, total_loss: torch.Tensor | None = None) -> tuple:
+        """tuple in, tuple out, like the fx shards (sharding.py:86-96)."""
+        kind = self.spec.kind
+        self.saved_in[buffer_id] = inputs
+        if kind == "embed":
+            input_ids, _attention_mask, labels = inputs
+            assert input_ids.dtype == torch.int64 and input_ids.is_contiguous()
+            y = self.out[buffer_id]
+            E = self.spec.n_embd
+            w = self.flat_param
+            L.call("oob_embedding_fwd", C.c_void_p(input_ids.data_ptr()), C.c_void_p(w.data_ptr()),
+                   C.c_void_p(w.data_ptr() + self.spec.vocab_size * E * 4), C.c_void_p(y.data_ptr()),
+                   self.mb * self.T, self.T, E, _stream())
+            return y, labels
+        hidden, labels = inputs
+        assert hidden.dtype == torch.float32 and hidden.is_contiguous()
+        p = self._params_struct()
+        if kind == "block":
+            y = self.out[buffer_id]
+            L.call("oob_block_forward", C.byref(self.dims), C.byref(p), C.c_void_p(hidden.data_ptr()),
+                   C.c_void_p(y.data_ptr()), C.byref(self.ctx[buffer_id]), _stream())
+            return y, labels
+        assert labels.dtype == torch.int64 and labels.is_contiguous()
+        L.call("oob_head_forward", C.byref(self.dims), C.byref(p), C.c_void_p(hidden.data_ptr()),
+               C.c_void_p(labels.data_ptr()), C.byref(self.ctx[buffer_id]),
+               C.c_void_p(0 if total_loss is None else total_loss.data_ptr()), _stream())
+        loss = self.ctx_tensors[buffer_id]["loss"][0]  # 0-dim view, like HF's scalar loss
+        return loss, self.ctx_tensors[buffer_id]["logits"]
+
+    def backward(self, buffer_id: int, grad: HiddenGrad | None) -> HiddenGrad | None:
+        """Hand-written backward of this layer for the micro-batch held in ``buffer_id`` (layer.py:250-260 runs
+        torch.autograd here).  Parameter gradients accumulate into ``flat_grad``."""
+        kind = self.spec.kind
+        inputs = self.saved_in[buffer_id]
+        ws = self.workspace
+        p = self._params_struct()
+        if kind == "head":
+            hidden = inputs[0]
+            dx, dxp = ws.next_dx()
+            L.call("oob_head_backward", C.byref(self.dims), C.byref(p), C.c_void_p(hidden.data_ptr()),
+                   C.byref(self.ctx[buffer_id]), C.byref(ws.scratch), C.c_void_p(dx.data_ptr()),
+                   C.c_void_p(dxp.data_ptr()), _stream())
+            return HiddenGrad(dx, dxp)
+        assert grad is not None
+        E = self.spec.n_embd
+        if kind == "block":
+            hidden = inputs[0]
+            if grad.planes is None:  # arrived from the next stage as fp32 only: split it here
+                dy_planes = ws.recv_planes
+                L.call("oob_split_planes", C.c_void_p(grad.grad.data_ptr()), C.c_void_p(dy_planes.data_ptr()),
+                       grad.grad.numel(), dy_planes.stride(0), 3, _stream())
+                grad = HiddenGrad(grad.grad, dy_planes)
+            dx, dxp = ws.next_dx()
+            if dx.data_ptr() == grad.grad.data_ptr():
+                dx, dxp = ws.next_dx()
+            L.call("oob_block_backward", C.byref(self.dims), C.byref(p), C.c_void_p(hidden.data_ptr()),
+                   C.byref(self.ctx[buffer_id]), C.c_void_p(grad.grad.data_ptr()), C.c_void_p(grad.planes.data_ptr()),
+                   C.byref(ws.scratch), C.c_void_p(dx.data_ptr()), C.c_void_p(dxp.data_ptr()), _stream())
+            return HiddenGrad(dx, dxp)
+        # embedding
+        input_ids = inputs[0]
+        g = self.flat_grad
+        L.call("oob_embedding_bwd", C.c_void_p(input_ids.data_ptr()), C.c_void_p(grad.grad.data_ptr()),
+               C.c_void_p(g.data_ptr()), C.c_void_p(g.data_ptr() + self.spec.vocab_size * E * 4), self.mb, self.T, E,
+               _stream())
+        return None
+
+    # -- data parallel -----------------------------------------------------------------------------------------------
+    def reduce_gradients(self, process_groups: dict) -> None:
+        """layer.py:272-291: SUM all-reduce of the flat gradient over the cross-replica group(s); never averaged.
+        With one GPU per stage there is exactly one (fsdp_index -> group) entry."""
+        assert len(process_groups) == 1, "sharded DP groups need the FSDP path (out of scope this round)"
+        for _, pg in process_groups.items():
+            torch.distributed.all_reduce(self.flat_grad, group=getattr(pg, "group", pg))

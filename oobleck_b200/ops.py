@@ -1,0 +1,65 @@
+"""Thin tensor-level wrappers over the C ABI (torch supplies device memory and streams only)."""
+from __future__ import annotations
+
+import ctypes as C
+
+import torch
+
+from . import lib as L
+
+NSPLIT_PARITY = 3  # fp32-grade split (6 tensor-core products); see csrc/common.cuh
+
+
+def _ptr(t):
+    return C.c_void_p(0 if t is None else t.data_ptr())
+
+
+def _stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def new_planes(rows: int, cols: int, nplanes: int = 3, device="cuda") -> torch.Tensor:
+    """bf16 [nplanes, rows, cols] split-plane buffer (cols must be a multiple of 8)."""
+    assert cols % 8 == 0, cols
+    return torch.empty((nplanes, rows, cols), dtype=torch.bfloat16, device=device)
+
+
+def planes_desc(p: torch.Tensor, rows=None, cols=None) -> L.Planes:
+    assert p.dtype == torch.bfloat16 and p.dim() == 3 and p.stride(2) == 1
+    return L.Planes(p.data_ptr(), rows if rows is not None else p.shape[1], cols if cols is not None else p.shape[2],
+                    p.stride(1), p.stride(0), p.shape[0])
+
+
+def split(x: torch.Tensor, out: torch.Tensor | None = None, nplanes: int = 3) -> torch.Tensor:
+    """fp32 [rows, cols] -> planes [nplanes, rows, cols]."""
+    x = x.contiguous()
+    rows, cols = x.shape
+    if out is None:
+        out = new_planes(rows, cols, nplanes, x.device)
+    L.call("oob_split_planes", _ptr(x), _ptr(out), x.numel(), out.stride(0), nplanes, _stream())
+    return out
+
+
+def planes_to_float(p: torch.Tensor) -> torch.Tensor:
+    return p.float().sum(0)
+
+
+def gemm(a: torch.Tensor, a_mn: bool, b: torch.Tensor, b_mn: bool, M: int, N: int, K: int, *, nsplit=NSPLIT_PARITY,
+         d=None, bias=None, resid=None, accumulate=False, act=L.ACT_NONE, aux=None, planes_out=None, alpha=1.0):
+    e = L.GemmEpilogue()
+    e.d = 0 if d is None else d.data_ptr()
+    e.ldd = 0 if d is None else d.stride(0)
+    e.bias = 0 if bias is None else bias.data_ptr()
+    e.resid = 0 if resid is None else resid.data_ptr()
+    e.ldr = 0 if resid is None else resid.stride(0)
+    e.accumulate = int(accumulate)
+    e.act = act
+    e.aux = 0 if aux is None else aux.data_ptr()
+    e.ldaux = 0 if aux is None else aux.stride(0)
+    e.planes = 0 if planes_out is None else planes_out.data_ptr()
+    e.ldp = 0 if planes_out is None else planes_out.stride(1)
+    e.plane_stride = 0 if planes_out is None else planes_out.stride(0)
+    e.nplanes_out = 0 if planes_out is None else planes_out.shape[0]
+    e.alpha = alpha
+    A, B = planes_desc(a), planes_desc(b)
+    L.call("oob_gemm", C.byref(A), int(a_mn), C.byref(B), int(b_mn), M, N, K, nsplit, C.byref(e), _stream())

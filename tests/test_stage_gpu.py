@@ -1,0 +1,134 @@
+"""Single-GPU parity of the CUDA stage layers against the oracle (oracle/gpt2.py == HF GPT-2 math), through
+``oobleck_b200.execution.layer.Layer`` -> C ABI.  Tolerance: north_star's 1e-4 rtol (fp32)."""
+import pytest
+import torch
+
+pytestmark = [pytest.mark.gpu, pytest.mark.timeout(600)]
+
+if not torch.cuda.is_available():
+    pytest.skip("needs CUDA", allow_module_level=True)
+
+from oobleck_b200.execution.layer import HiddenGrad, Layer, StageWorkspace  # noqa: E402
+from oobleck_b200.module.model import OobleckModel  # noqa: E402
+from oracle import gpt2 as og  # noqa: E402
+
+RTOL = 1e-4
+
+
+def close(got, want, name, rtol=RTOL):
+    got, want = got.detach().double().cpu(), want.detach().double().cpu()
+    scale = want.abs().max().clamp_min(1e-30)
+    err = ((got - want).abs().max() / scale).item()
+    assert err < rtol, f"{name}: max|err|/max|ref| = {err:.3e}"
+    return err
+
+
+def build(cfg, mb, nbuf=2, nsplit=3):
+    d = og.GPT2Dims(**cfg)
+    olayers = og.build_layers(d)
+    og.init_layers_(olayers)
+    # make LayerNorm/bias parameters non-trivial
+    g = torch.Generator().manual_seed(7)
+    for l in olayers:
+        for n, p in l.named_parameters():
+            if n.endswith("_b") or n.startswith("ln_"):
+                with torch.no_grad():
+                    p.add_(torch.randn(p.shape, generator=g) * 0.05)
+    model = OobleckModel("gpt2", {"input_ids": None, "attention_mask": None, "labels": None}, None, "test",
+                         dict(n_embd=d.n_embd, n_head=d.n_head, n_layer=d.n_layer, n_positions=d.n_positions,
+                              vocab_size=d.vocab_size))
+    assert len(model.layers) == d.n_layer + 2
+    ws = StageWorkspace(mb, d.n_positions, d.n_embd, d.n_head, torch.device("cuda"))
+    layers = []
+    for i, spec in enumerate(model.layers):
+        assert spec.num_params == sum(p.numel() for p in olayers[i].parameters())
+        l = Layer(i, spec, None, None, None, microbatch_size=mb, num_pipe_buffers=nbuf, workspace=ws, nsplit=nsplit)
+        l.load_flat_(og.flat_params(olayers[i]))
+        layers.append(l)
+    return d, olayers, layers
+
+
+@pytest.mark.parametrize("cfg,mb", [
+    (dict(n_embd=128, n_head=2, n_layer=2, n_positions=64, vocab_size=503), 2),
+    (dict(n_embd=256, n_head=4, n_layer=3, n_positions=256, vocab_size=1000), 3),
+    (dict(n_embd=768, n_head=12, n_layer=2, n_positions=1024, vocab_size=50257), 1),
+])
+def test_stage_forward_backward_parity(cfg, mb):
+    d, olayers, layers = build(cfg, mb)
+    total = torch.zeros(1, device="cuda")
+    ref_total = 0.0
+    n_mb = 2
+    for k in range(n_mb):  # two micro-batches: gradients must accumulate
+        batch = og.synthetic_batch(mb, d.n_positions, d.vocab_size, index=k)
+        x = (batch["input_ids"], batch["attention_mask"], batch["labels"])
+        hidden_ref = []
+        for ol in olayers:
+            x = ol(*x)
+            hidden_ref.append(x[0])
+        x[0].backward()
+        ref_total += x[0].item()
+
+        buf = k % 2
+        cx = tuple(t.cuda() for t in (batch["input_ids"], batch["attention_mask"], batch["labels"]))
+        for i, l in enumerate(layers):
+            cx = l(cx, buffer_id=buf, total_loss=total)
+            if i < len(layers) - 1:
+                close(cx[0], hidden_ref[i], f"mb{k} hidden after layer {i}")
+        close(cx[0], hidden_ref[-1], f"mb{k} loss")
+        close(cx[1].view(mb, d.n_positions, -1)[..., :d.vocab_size], x[1], f"mb{k} logits")
+        g = None
+        for l in reversed(layers):
+            g = l.backward(buf, g)
+        assert g is None
+    torch.cuda.synchronize()
+    assert abs(total.item() - ref_total) < RTOL * abs(ref_total)
+    worst = 0.0
+    for i, (l, ol) in enumerate(zip(layers, olayers)):
+        worst = max(worst, close(l.flat_grad, og.flat_grads(ol), f"flat grad of layer {i}"))
+    print(f"worst grad err {worst:.3e}")
+
+
+def test_stage_split_levels_accuracy():
+    """nsplit=3 must be the most accurate; nsplit=1 is plain bf16 and must NOT meet the parity tolerance."""
+    cfg = dict(n_embd=256, n_head=4, n_layer=2, n_positions=128, vocab_size=777)
+    errs = {}
+    for ns in (3, 2, 1):
+        d, olayers, layers = build(cfg, 2, nsplit=ns)
+        batch = og.synthetic_batch(2, d.n_positions, d.vocab_size)
+        x = (batch["input_ids"], batch["attention_mask"], batch["labels"])
+        for ol in olayers:
+            x = ol(*x)
+        cx = tuple(t.cuda() for t in (batch["input_ids"], batch["attention_mask"], batch["labels"]))
+        for l in layers[:-1]:
+            cx = l(cx, buffer_id=0)
+        ref_h = None
+        x2 = (batch["input_ids"], batch["attention_mask"], batch["labels"])
+        for ol in olayers[:-1]:
+            x2 = ol(*x2)
+        errs[ns] = ((cx[0].cpu().double() - x2[0].double()).abs().max() / x2[0].double().abs().max()).item()
+    print(errs)
+    assert errs[3] < 1e-5 and errs[3] <= errs[2] <= errs[1]
+    assert errs[1] > 1e-4
+
+
+def test_adamw_layer_step_matches_oracle():
+    import ctypes as C
+
+    from oobleck_b200 import lib as L
+    from oracle import optim as oo
+    cfg = dict(n_embd=128, n_head=2, n_layer=1, n_positions=64, vocab_size=300)
+    d, olayers, layers = build(cfg, 1)
+    l = layers[1]
+    p = l.flat_param.clone().cpu()
+    m, v = torch.zeros_like(p), torch.zeros_like(p)
+    for step in range(1, 4):
+        g = torch.randn(l.numel)
+        l.flat_grad.copy_(g)
+        lr = 1e-3 * step
+        L.call("oob_adamw_step", C.c_void_p(l.flat_param.data_ptr()), C.c_void_p(l.flat_grad.data_ptr()),
+               C.c_void_p(l.exp_avg.data_ptr()), C.c_void_p(l.exp_avg_sq.data_ptr()), C.c_void_p(l.planes.data_ptr()),
+               l.plane_stride, 3, l.numel, lr, 0.9, 0.999, 1e-8, 0.01, step,
+               C.c_void_p(torch.cuda.current_stream().cuda_stream))
+        oo.adamw_step_(p, g, m, v, step, lr)
+        close(l.flat_param, p, f"param after step {step}", rtol=1e-6)
+    close(l.planes[:, :l.numel].float().sum(0), p, "planes track the parameters", rtol=1e-6)
