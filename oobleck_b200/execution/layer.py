@@ -81,6 +81,13 @@ class _ParamHandle:
 class Layer:
     """Constructor keeps the reference's positional order (layer.py:71-78)."""
 
+    device_type = "cuda"
+
+    @classmethod
+    def make_workspace(cls, model, microbatch_size: int, device) -> "StageWorkspace":
+        spec = model.layers[0]
+        return StageWorkspace(microbatch_size, spec.n_positions, spec.n_embd, spec.n_head, torch.device(device))
+
     def __init__(self, layer_id: int, layer: StageLayerSpec, process_group=None, pre_stream=None, post_stream=None, *,
                  microbatch_size: int, num_pipe_buffers: int, workspace: StageWorkspace | None = None,
                  nsplit: int = 3, device: torch.device | None = None, seq_len: int | None = None):
@@ -172,7 +179,7 @@ class Layer:
                      "ln2_rstd": torch.empty(M, **f32), "fc": torch.empty(M, 4 * E, **f32),
                      "gelu_planes": torch.empty(3, M, 4 * E, **bf)}
                 self.ctx.append(OobBlockCtx(**{k: v.data_ptr() for k, v in t.items()}))
-                self.out.append(torch.empty(self.mb, self.T, E, **f32))
+                self.out.append(torch.empty(self.mb, self.T, E, **f32).requires_grad_(True))
             elif self.spec.kind == "head":
                 Vp = self.dims.vocab_padded
                 t = {"lnf_planes": torch.empty(3, M, E, **bf), "mean": torch.empty(M, **f32),
@@ -184,7 +191,7 @@ class Layer:
             else:
                 t = {}
                 self.ctx.append(None)
-                self.out.append(torch.empty(self.mb, self.T, E, **f32))
+                self.out.append(torch.empty(self.mb, self.T, E, **f32).requires_grad_(True))
             self.ctx_tensors.append(t)
 
     # -- compute ---------------------------------------------------------------------------------------------------
