@@ -22,6 +22,11 @@ extern "C" {
 
 int oob_version(void);
 const char* oob_last_error(void);
+/* instrumentation used by bench.py: kernels launched so far by this library, and CUDA-event timing of every
+ * tcgen05 GEMM launch between begin/end (events are recorded on the launching stream; end synchronises them) */
+long oob_launch_count(void);
+int oob_gemm_timing_begin(void);
+int oob_gemm_timing_end(double* total_ms, double* total_flops, long* launches);
 /* sizes of the scratch buffers the reductions below need, in floats */
 long oob_ln_bwd_partials_floats(int n_embd);
 long oob_colsum_partials_floats(int cols);

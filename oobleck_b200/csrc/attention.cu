@@ -451,6 +451,7 @@ int attention_fwd(const float* qkv, float* out, bf16* out_planes, long plane_str
   attention_fwd_kernel<<<grid, 128, smem, s>>>(qkv, out, out_planes, plane_stride, nplanes, lse, T, H,
                                                1.0f / sqrtf((float)D));
   OOB_CUDA_OK(cudaGetLastError());
+  count_launch();
   return 0;
 }
 
@@ -468,14 +469,17 @@ int attention_bwd(const float* qkv, const float* out, const float* dout, const f
   const int total = B * T * H;
   attention_delta_kernel<<<(total + 7) / 8, 256, 0, s>>>(out, dout, delta, B, T, H);
   OOB_CUDA_OK(cudaGetLastError());
+  count_launch();
   dim3 grid((T + AT - 1) / AT, H, B);
   const float scale = 1.0f / sqrtf((float)D);
   attention_bwd_kv_kernel<<<grid, 128, smem_kv, s>>>(qkv, dout, lse, delta, dqkv, dqkv_planes, plane_stride, nplanes,
                                                      T, H, scale);
   OOB_CUDA_OK(cudaGetLastError());
+  count_launch();
   attention_bwd_q_kernel<<<grid, 128, smem_q, s>>>(qkv, dout, lse, delta, dqkv, dqkv_planes, plane_stride, nplanes, T,
                                                    H, scale);
   OOB_CUDA_OK(cudaGetLastError());
+  count_launch();
   return 0;
 }
 

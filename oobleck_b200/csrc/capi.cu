@@ -1,4 +1,5 @@
 // extern "C" surface of liboobleck_b200.so (declared in include/oobleck_b200.h).
+#include <atomic>
 #include <cstdarg>
 #include <cstdio>
 
@@ -13,6 +14,8 @@ void set_error(const char* fmt, ...) {
   vsnprintf(g_err, sizeof(g_err), fmt, ap);
   va_end(ap);
 }
+static std::atomic<long> g_launches{0};
+void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
 }  // namespace oob
 
 using namespace oob;
@@ -25,6 +28,11 @@ static inline PlaneMat PM(const oob_planes* p) {
 extern "C" {
 
 int oob_version(void) { return 100; }
+long oob_launch_count(void) { return g_launches.load(); }
+int oob_gemm_timing_begin(void) { return gemm_timing_begin(); }
+int oob_gemm_timing_end(double* total_ms, double* total_flops, long* launches) {
+  return gemm_timing_end(total_ms, total_flops, launches);
+}
 const char* oob_last_error(void) { return g_err; }
 long oob_ln_bwd_partials_floats(int n_embd) { return (long)LN_BWD_MAX_GRID * 2 * n_embd; }
 long oob_colsum_partials_floats(int cols) { return (long)COLSUM_MAX_PARTS * cols; }

@@ -11,6 +11,8 @@ namespace oob {
 // ---------------------------------------------------------------------------------------------
 // error plumbing (C-ABI returns int status; message via oob_last_error())
 void set_error(const char* fmt, ...);
+// number of kernels this library has launched (bench.py reports it as gpu_launches)
+void count_launch(int n = 1);
 #define OOB_CUDA_OK(expr)                                                                  \
   do {                                                                                     \
     cudaError_t _e = (expr);                                                               \

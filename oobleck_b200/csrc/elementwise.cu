@@ -46,6 +46,7 @@ int split_planes(const float* x, bf16* planes, long n, long plane_stride, int np
   if (blocks < 1) blocks = 1;
   split_kernel<<<blocks, 256, 0, s>>>(x, planes, n, plane_stride, nplanes);
   OOB_CUDA_OK(cudaGetLastError());
+  count_launch();
   return 0;
 }
 
@@ -120,6 +121,7 @@ int layernorm_fwd(const float* x, const float* gamma, const float* beta, float* 
   layernorm_fwd_kernel<<<(rows + 3) / 4, 128, 0, s>>>(x, gamma, beta, y, planes, plane_stride, nplanes, mean, rstd,
                                                       rows, E, eps);
   OOB_CUDA_OK(cudaGetLastError());
+  count_launch();
   return 0;
 }
 
@@ -234,8 +236,10 @@ int layernorm_bwd(const float* dy, const float* x, const float* mean, const floa
   layernorm_bwd_kernel<<<grid, 256, 0, s>>>(dy, x, mean, rstd, gamma, dres, dx, planes, plane_stride, nplanes,
                                             partials, rows, E);
   OOB_CUDA_OK(cudaGetLastError());
+  count_launch();
   colreduce_finalize_kernel<<<(2 * E + 255) / 256, 256, 0, s>>>(partials, grid, 2 * E, dgamma, dbeta, E);
   OOB_CUDA_OK(cudaGetLastError());
+  count_launch();
   return 0;
 }
 
@@ -275,8 +279,10 @@ int colsum_accumulate(const float* a, long lda, int rows, int cols, float* out, 
   dim3 grid((cols / 4 + 63) / 64, gy), block(64, 4);
   colsum_partial_kernel<<<grid, block, 0, s>>>(a, lda, rows, cols, partials);
   OOB_CUDA_OK(cudaGetLastError());
+  count_launch();
   colreduce_finalize_kernel<<<(cols + 255) / 256, 256, 0, s>>>(partials, gy, cols, out, out, cols);
   OOB_CUDA_OK(cudaGetLastError());
+  count_launch();
   return 0;
 }
 
@@ -302,6 +308,7 @@ int embedding_fwd(const long long* ids, const float* wte, const float* wpe, floa
   if (rows <= 0) return 0;
   embedding_fwd_kernel<<<(rows + 7) / 8, 256, 0, s>>>(ids, wte, wpe, out, rows, T, E);
   OOB_CUDA_OK(cudaGetLastError());
+  count_launch();
   return 0;
 }
 
@@ -336,8 +343,10 @@ int embedding_bwd(const long long* ids, const float* dx, float* dwte, float* dwp
   if (rows <= 0) return 0;
   embedding_bwd_wte_kernel<<<(rows + 7) / 8, 256, 0, s>>>(ids, dx, dwte, rows, E);
   OOB_CUDA_OK(cudaGetLastError());
+  count_launch();
   embedding_bwd_wpe_kernel<<<(T + 7) / 8, 256, 0, s>>>(dx, dwpe, B, T, E);
   OOB_CUDA_OK(cudaGetLastError());
+  count_launch();
   return 0;
 }
 
@@ -431,8 +440,10 @@ int cross_entropy(const float* logits, long ldl, const long long* labels, int B,
   cross_entropy_kernel<<<rows, 512, 0, s>>>(logits, ldl, labels, T, V, scale, row_loss, dplanes, ldp, plane_stride,
                                             nplanes);
   OOB_CUDA_OK(cudaGetLastError());
+  count_launch();
   loss_reduce_kernel<<<1, 1024, 0, s>>>(row_loss, rows, scale, loss, total_loss);
   OOB_CUDA_OK(cudaGetLastError());
+  count_launch();
   return 0;
 }
 
@@ -505,6 +516,7 @@ int adamw_step(float* p, const float* g, float* m, float* v, bf16* planes, long 
   adamw_kernel<<<(int)blocks, 256, 0, s>>>(p, g, m, v, planes, plane_stride, nplanes, n, lr, beta1, beta2, eps, wd,
                                            (float)bc1, (float)sqrt(bc2));
   OOB_CUDA_OK(cudaGetLastError());
+  count_launch();
   return 0;
 }
 

@@ -1,5 +1,6 @@
 // Host launcher for the tcgen05 split-bf16 GEMM: builds the TMA tensor maps and picks the stage count.
 #include <mutex>
+#include <vector>
 
 #include "gemm_sm100.cuh"
 
@@ -41,6 +42,33 @@ static int make_map(CUtensorMap* m, const PlaneMat& a, int box_rows, int box_pla
   return 0;
 }
 
+// ---- optional CUDA-event timing of every launch (roofline measurement) ----------------------------------------
+struct TimedLaunch { cudaEvent_t a, b; double flops; };
+static bool g_timing = false;
+static std::vector<TimedLaunch> g_timed;
+static std::vector<cudaEvent_t> g_event_pool;
+static cudaEvent_t get_event() {
+  if (!g_event_pool.empty()) { cudaEvent_t e = g_event_pool.back(); g_event_pool.pop_back(); return e; }
+  cudaEvent_t e; cudaEventCreate(&e); return e;
+}
+int gemm_timing_begin() { g_timed.clear(); g_timing = true; return 0; }
+int gemm_timing_end(double* total_ms, double* total_flops, long* launches) {
+  g_timing = false;
+  double ms = 0, fl = 0;
+  for (auto& t : g_timed) {
+    OOB_CUDA_OK(cudaEventSynchronize(t.b));
+    float x = 0;
+    OOB_CUDA_OK(cudaEventElapsedTime(&x, t.a, t.b));
+    ms += x; fl += t.flops;
+    g_event_pool.push_back(t.a); g_event_pool.push_back(t.b);
+  }
+  if (total_ms) *total_ms = ms;
+  if (total_flops) *total_flops = fl;
+  if (launches) *launches = (long)g_timed.size();
+  g_timed.clear();
+  return 0;
+}
+
 template <int BN, bool A_MN, bool B_MN>
 static int launch_t(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, cudaStream_t stream) {
   static int max_smem = -1;
@@ -62,8 +90,12 @@ static int launch_t(const CUtensorMap& ta, const CUtensorMap& tb, const GemmPara
   OOB_CHECK(stages >= 2, "GEMM tile does not fit %d B of shared memory", max_smem);
   const size_t smem = (size_t)stages * stage + overhead;
   dim3 grid((p.N + BN - 1) / BN, (p.M + GEMM_BM - 1) / GEMM_BM);
+  TimedLaunch tl{};
+  if (g_timing) { tl.a = get_event(); tl.b = get_event(); tl.flops = 2.0 * p.M * p.N * p.K; cudaEventRecord(tl.a, stream); }
   kern<<<grid, GEMM_THREADS, smem, stream>>>(ta, tb, p, stages);
   OOB_CUDA_OK(cudaGetLastError());
+  if (g_timing) { cudaEventRecord(tl.b, stream); g_timed.push_back(tl); }
+  count_launch();
   return 0;
 }
 

@@ -343,4 +343,8 @@ struct PlaneMat {
 int gemm_launch(const PlaneMat& A, int a_mn_major, const PlaneMat& B, int b_mn_major, const GemmParams& p,
                 cudaStream_t stream);
 
+// CUDA-event instrumentation of GEMM launches (bench.py roofline): see oob_gemm_timing_begin/end
+int gemm_timing_begin();
+int gemm_timing_end(double* total_ms, double* total_flops, long* launches);
+
 }  // namespace oob

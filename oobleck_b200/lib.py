@@ -65,6 +65,9 @@ _P, _L, _I, _F = C.c_void_p, C.c_long, C.c_int, C.c_float
 _SIGNATURES = {
     "oob_version": (C.c_int, []),
     "oob_last_error": (C.c_char_p, []),
+    "oob_launch_count": (C.c_long, []),
+    "oob_gemm_timing_begin": (_I, []),
+    "oob_gemm_timing_end": (_I, [C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_long)]),
     "oob_ln_bwd_partials_floats": (C.c_long, [_I]),
     "oob_colsum_partials_floats": (C.c_long, [_I]),
     "oob_split_planes": (_I, [_P, _P, _L, _L, _I, _P]),
