@@ -159,6 +159,23 @@ int oob_head_forward(const oob_dims* d, const oob_layer_params* p, const float* 
 int oob_head_backward(const oob_dims* d, const oob_layer_params* p, const float* x, const oob_head_ctx* ctx,
                       oob_bwd_scratch* s, float* dx, void* dx_planes, void* stream);
 
+/* ==== inter-stage P2P over NVLink (csrc/p2p.cu) =================================================================
+ * Replaces PipelineCommunication._send/_recv (pipeline.py:270-286) and everything built on them: one mailbox per
+ * neighbour, cudaMalloc'ed by its owner and mapped into the neighbour via CUDA IPC; a message is `nslots`-deep
+ * ring-buffered, written by the sender's copy kernel directly into the receiver's HBM and published with a
+ * release flag; the receiver's kernel spins on the flag, copies out and acknowledges.  `seq` is the 1-based message
+ * number on that link; a message may consist of several tensors (first/last mark its ends). */
+long oob_p2p_header_bytes(void);
+int oob_p2p_alloc(long ring_bytes, void** mailbox, void* ipc_handle_out /* 64 bytes */);
+int oob_p2p_open(const void* ipc_handle /* 64 bytes */, void** peer_mailbox);
+int oob_p2p_close(void* peer_mailbox);
+int oob_p2p_free(void* mailbox);
+int oob_p2p_abort(void* mailbox, void* stream);
+int oob_p2p_send(const void* src, long bytes, void* my_mailbox, void* peer_mailbox, int nslots, long slot_bytes,
+                 long offset_in_slot, unsigned seq, int first, int last, void* stream);
+int oob_p2p_recv(void* dst, long bytes, void* my_mailbox, void* peer_mailbox, int nslots, long slot_bytes,
+                 long offset_in_slot, unsigned seq, int first, int last, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

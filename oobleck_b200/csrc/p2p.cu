@@ -1,0 +1,191 @@
+// Inter-stage activation / gradient exchange as direct NVLink peer-memory writes (replaces the blocking
+// ncclSend/ncclRecv per tuple member of oobleck/execution/pipeline.py:270-286, 331-333, 383-387, 391-427).
+//
+// Every rank owns one cudaMalloc'ed "mailbox" per neighbour, mapped into the neighbour with CUDA IPC:
+//
+//     [ flags[64] | acks[64] | counters[8] | abort | pad ][ ring: nslots x slot_bytes ]
+//       ^ written by the peer            ^ local scratch            ^ written by the peer (payload)
+//
+//   send(n):  (sender's stream) wait local acks[slot] >= n - nslots   -- the peer has drained the slot
+//             copy payload -> peer ring[slot] with 128-bit stores over NVLink, __threadfence_system
+//             last CTA: st.release.sys peer flags[slot] = n
+//   recv(n):  (receiver's stream) spin ld.acquire.sys local flags[slot] >= n, copy ring[slot] -> destination,
+//             last CTA: st.release.sys peer acks[slot] = n
+//
+// No NCCL rendezvous per message, no host synchronisation: both kernels are ordinary stream work, so the copy
+// overlaps the 1F1B compute on the dedicated copy streams the host side gives them.
+#include "../../include/oobleck_b200.h"
+#include <cstring>
+
+#include "kernels.h"
+
+using namespace oob;
+
+namespace {
+
+constexpr int P2P_MAX_SLOTS = 64;
+struct MailboxHeader {
+  unsigned flags[P2P_MAX_SLOTS];
+  unsigned acks[P2P_MAX_SLOTS];
+  unsigned counters[8];
+  unsigned abort;
+  unsigned pad[119];
+};
+static_assert(sizeof(MailboxHeader) == 1024, "mailbox header must stay 1 KiB");
+
+__device__ __forceinline__ unsigned ld_acquire_sys(const unsigned* p) {
+  unsigned v;
+  asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release_sys(unsigned* p, unsigned v) {
+  asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+
+// wait until *word >= target (wrap-safe), or the local abort word is set
+__device__ __forceinline__ void spin_until(const unsigned* word, unsigned target, const unsigned* abort_word) {
+  if (threadIdx.x == 0) {
+    unsigned ns = 32;
+    while ((int)(ld_acquire_sys(word) - target) < 0) {
+      if (ld_acquire_sys(abort_word)) break;
+      __nanosleep(ns);
+      if (ns < 1024) ns <<= 1;
+    }
+  }
+  __syncthreads();
+  __threadfence_system();
+}
+
+__device__ __forceinline__ void copy_bytes(const char* src, char* dst, long bytes) {
+  const long n16 = bytes >> 4;
+  const int4* s = reinterpret_cast<const int4*>(src);
+  int4* d = reinterpret_cast<int4*>(dst);
+  const long stride = (long)gridDim.x * blockDim.x;
+  long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  // 4 independent 128-bit accesses in flight per thread
+  for (; i + 3 * stride < n16; i += 4 * stride) {
+    int4 a = s[i], b = s[i + stride], c = s[i + 2 * stride], e = s[i + 3 * stride];
+    d[i] = a; d[i + stride] = b; d[i + 2 * stride] = c; d[i + 3 * stride] = e;
+  }
+  for (; i < n16; i += stride) d[i] = s[i];
+  if (blockIdx.x == 0 && threadIdx.x < (bytes & 15)) dst[(n16 << 4) + threadIdx.x] = src[(n16 << 4) + threadIdx.x];
+}
+
+// signal: after all CTAs finished their part, the last one publishes `value` at `word` (system scope)
+__device__ __forceinline__ void publish_when_all_done(unsigned* counter, unsigned* word, unsigned value) {
+  __threadfence_system();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const unsigned done = atomicAdd(counter, 1u);
+    if (done == gridDim.x - 1) {
+      *counter = 0;
+      __threadfence_system();
+      if (word) st_release_sys(word, value);
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256)
+p2p_send_kernel(const char* __restrict__ src, char* __restrict__ peer_dst, long bytes, const unsigned* local_ack,
+                unsigned ack_needed, int wait_ack, unsigned* peer_flag, unsigned seq, unsigned* counter,
+                const unsigned* abort_word) {
+  if (wait_ack) spin_until(local_ack, ack_needed, abort_word);
+  copy_bytes(src, peer_dst, bytes);
+  publish_when_all_done(counter, peer_flag, seq);
+}
+
+__global__ void __launch_bounds__(256)
+p2p_recv_kernel(const char* __restrict__ local_src, char* __restrict__ dst, long bytes, const unsigned* local_flag,
+                unsigned seq, int wait_flag, unsigned* peer_ack, unsigned* counter, const unsigned* abort_word) {
+  if (wait_flag) spin_until(local_flag, seq, abort_word);
+  copy_bytes(local_src, dst, bytes);
+  publish_when_all_done(counter, peer_ack, seq);
+}
+
+}  // namespace
+
+extern "C" {
+
+long oob_p2p_header_bytes(void) { return (long)sizeof(MailboxHeader); }
+
+int oob_p2p_alloc(long ring_bytes, void** mailbox, void* ipc_handle_out) {
+  OOB_CHECK(mailbox && ipc_handle_out && ring_bytes >= 0, "oob_p2p_alloc: bad arguments");
+  void* p = nullptr;
+  const size_t total = sizeof(MailboxHeader) + (size_t)ring_bytes;
+  OOB_CUDA_OK(cudaMalloc(&p, total));
+  OOB_CUDA_OK(cudaMemset(p, 0, sizeof(MailboxHeader)));
+  cudaIpcMemHandle_t h;
+  OOB_CUDA_OK(cudaIpcGetMemHandle(&h, p));
+  memcpy(ipc_handle_out, &h, sizeof(h));
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "ipc handle size");
+  *mailbox = p;
+  return 0;
+}
+
+int oob_p2p_open(const void* ipc_handle, void** peer_mailbox) {
+  cudaIpcMemHandle_t h;
+  memcpy(&h, ipc_handle, sizeof(h));
+  OOB_CUDA_OK(cudaIpcOpenMemHandle(peer_mailbox, h, cudaIpcMemLazyEnablePeerAccess));
+  return 0;
+}
+
+int oob_p2p_close(void* peer_mailbox) {
+  OOB_CUDA_OK(cudaIpcCloseMemHandle(peer_mailbox));
+  return 0;
+}
+
+int oob_p2p_free(void* mailbox) {
+  OOB_CUDA_OK(cudaFree(mailbox));
+  return 0;
+}
+
+/* make every spinning kernel on this rank's mailbox give up (peer lost); callable from the listener thread */
+int oob_p2p_abort(void* mailbox, void* stream) {
+  static const unsigned one = 1;
+  MailboxHeader* h = reinterpret_cast<MailboxHeader*>(mailbox);
+  OOB_CUDA_OK(cudaMemcpyAsync(&h->abort, &one, sizeof(one), cudaMemcpyHostToDevice, reinterpret_cast<cudaStream_t>(stream)));
+  return 0;
+}
+
+/* one tensor of message `seq` (1-based) -> peer ring slot.  first/last mark the first / last tensor of the message:
+ * the first waits for the slot to be free, the last publishes the flag. */
+int oob_p2p_send(const void* src, long bytes, void* my_mailbox, void* peer_mailbox, int nslots, long slot_bytes,
+                 long offset_in_slot, unsigned seq, int first, int last, void* stream) {
+  OOB_CHECK(nslots >= 1 && nslots <= P2P_MAX_SLOTS, "oob_p2p_send: nslots out of range");
+  OOB_CHECK(offset_in_slot + bytes <= slot_bytes && (offset_in_slot & 15) == 0, "oob_p2p_send: payload does not fit the slot");
+  OOB_CHECK((reinterpret_cast<uintptr_t>(src) & 15) == 0, "oob_p2p_send: source must be 16 B aligned");
+  MailboxHeader* mine = reinterpret_cast<MailboxHeader*>(my_mailbox);
+  MailboxHeader* peer = reinterpret_cast<MailboxHeader*>(peer_mailbox);
+  const int slot = (int)((seq - 1) % (unsigned)nslots);
+  char* dst = reinterpret_cast<char*>(peer + 1) + (long)slot * slot_bytes + offset_in_slot;
+  int blocks = (int)((bytes / 16 + 256 * 4 - 1) / (256 * 4));
+  blocks = blocks < 1 ? 1 : (blocks > 64 ? 64 : blocks);
+  const int wait_ack = first && seq > (unsigned)nslots;
+  p2p_send_kernel<<<blocks, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      reinterpret_cast<const char*>(src), dst, bytes, &mine->acks[slot], seq - (unsigned)nslots, wait_ack,
+      last ? &peer->flags[slot] : nullptr, seq, &mine->counters[0], &mine->abort);
+  OOB_CUDA_OK(cudaGetLastError());
+  count_launch();
+  return 0;
+}
+
+int oob_p2p_recv(void* dst, long bytes, void* my_mailbox, void* peer_mailbox, int nslots, long slot_bytes,
+                 long offset_in_slot, unsigned seq, int first, int last, void* stream) {
+  OOB_CHECK(nslots >= 1 && nslots <= P2P_MAX_SLOTS, "oob_p2p_recv: nslots out of range");
+  OOB_CHECK(offset_in_slot + bytes <= slot_bytes && (offset_in_slot & 15) == 0, "oob_p2p_recv: payload does not fit the slot");
+  OOB_CHECK((reinterpret_cast<uintptr_t>(dst) & 15) == 0, "oob_p2p_recv: destination must be 16 B aligned");
+  MailboxHeader* mine = reinterpret_cast<MailboxHeader*>(my_mailbox);
+  MailboxHeader* peer = reinterpret_cast<MailboxHeader*>(peer_mailbox);
+  const int slot = (int)((seq - 1) % (unsigned)nslots);
+  const char* src = reinterpret_cast<const char*>(mine + 1) + (long)slot * slot_bytes + offset_in_slot;
+  int blocks = (int)((bytes / 16 + 256 * 4 - 1) / (256 * 4));
+  blocks = blocks < 1 ? 1 : (blocks > 64 ? 64 : blocks);
+  p2p_recv_kernel<<<blocks, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      src, reinterpret_cast<char*>(dst), bytes, &mine->flags[slot], seq, first, last ? &peer->acks[slot] : nullptr,
+      &mine->counters[1], &mine->abort);
+  OOB_CUDA_OK(cudaGetLastError());
+  count_launch();
+  return 0;
+}
+
+}  // extern "C"

@@ -110,6 +110,7 @@ class PipelineExecution:
     def forward_pass(self, buffer_id: int):
         inputs: tuple = self.pipeline.pipe_buffers["inputs"][buffer_id]
         zero_grads(inputs)
+        self.pipeline.communication.transport.before_compute()
         if self.pipeline.is_last_stage() and self.total_loss is None:
             self.total_loss = torch.zeros((), dtype=torch.float32, device=self.pipeline.device)
         for layer in self._layers:
@@ -191,13 +192,29 @@ class DistTransport:
                                        requires_grad=bool(req.item() == 1) and dt.is_floating_point))
         return tuple(buffers)
 
-    def send_tensors(self, tensors, dest_rank: int):
+    def send_tuple(self, tensors, dest_rank: int, kind: str):
         for t in tensors:
             self._send(t, dest_rank)
 
-    def recv_tensors(self, buffers, src_rank: int):
+    def _recv_into(self, buffers, src_rank: int):
         for b in buffers:
             self._recv(b.detach() if b.requires_grad else b, src_rank)
+
+    def recv_activation_tuple(self, recv_buf: tuple, src_rank: int) -> tuple:
+        """The receive buffer is reused for every micro-batch and cloned into the pipe buffer (:378-387)."""
+        self._recv_into(recv_buf, src_rank)
+        recvd = []
+        for buffer in recv_buf:
+            t = buffer.clone().detach()
+            t.requires_grad = buffer.requires_grad
+            recvd.append(t)
+        return tuple(recvd)
+
+    def recv_gradient_tuple(self, recv_buf: tuple, src_rank: int) -> None:
+        self._recv_into(recv_buf, src_rank)
+
+    def before_compute(self) -> None:
+        """Called before a forward / backward pass is enqueued; blocking transports have nothing to order."""
 
 
 class PipelineCommunication:
@@ -225,19 +242,14 @@ class PipelineCommunication:
         if not self.sent_activation_meta:
             self.transport.send_meta(outputs, self.next_rank)
             self.sent_activation_meta = True
-        self.transport.send_tensors(outputs, self.next_rank)
+        self.transport.send_tuple(outputs, self.next_rank, "act")
 
     def recv_activations(self, buffer_id: int):
         if self.activation_recv_buf is None:
             self.activation_recv_buf = self.transport.recv_meta(self.prev_rank)
         assert isinstance(self.activation_recv_buf, tuple)
-        self.transport.recv_tensors(self.activation_recv_buf, self.prev_rank)
-        recvd = []
-        for buffer in self.activation_recv_buf:   # the receive buffer is reused for every micro-batch (:378-387)
-            t = buffer.clone().detach()
-            t.requires_grad = buffer.requires_grad
-            recvd.append(t)
-        self.pipeline.pipe_buffers["inputs"][buffer_id] = tuple(recvd)
+        self.pipeline.pipe_buffers["inputs"][buffer_id] = self.transport.recv_activation_tuple(
+            self.activation_recv_buf, self.prev_rank)
 
     def send_gradients(self, buffer_id: int):
         inputs = self.pipeline.pipe_buffers["inputs"][buffer_id]
@@ -249,7 +261,7 @@ class PipelineCommunication:
                 continue
             assert buffer.grad is not None
             grads.append(buffer.grad)
-        self.transport.send_tensors(grads, self.prev_rank)
+        self.transport.send_tuple(grads, self.prev_rank, "grad")
         self.pipeline.pipe_buffers["inputs"][buffer_id] = None   # :404
 
     def recv_gradients(self, buffer_id: int):
@@ -257,7 +269,7 @@ class PipelineCommunication:
         assert isinstance(outputs, tuple)
         if self.grad_recv_buf is None:     # :407-424
             self.grad_recv_buf = tuple(torch.zeros_like(t, requires_grad=False) for t in outputs if t.requires_grad)
-        self.transport.recv_tensors(self.grad_recv_buf, self.next_rank)
+        self.transport.recv_gradient_tuple(self.grad_recv_buf, self.next_rank)
 
 
 class OobleckPipeline:

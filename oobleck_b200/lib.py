@@ -87,6 +87,14 @@ _SIGNATURES = {
     "oob_head_forward": (_I, [C.POINTER(OobDims), C.POINTER(OobLayerParams), _P, _P, C.POINTER(OobHeadCtx), _P, _P]),
     "oob_head_backward": (_I, [C.POINTER(OobDims), C.POINTER(OobLayerParams), _P, C.POINTER(OobHeadCtx),
                                C.POINTER(OobBwdScratch), _P, _P, _P]),
+    "oob_p2p_header_bytes": (C.c_long, []),
+    "oob_p2p_alloc": (_I, [_L, C.POINTER(C.c_void_p), _P]),
+    "oob_p2p_open": (_I, [_P, C.POINTER(C.c_void_p)]),
+    "oob_p2p_close": (_I, [_P]),
+    "oob_p2p_free": (_I, [_P]),
+    "oob_p2p_abort": (_I, [_P, _P]),
+    "oob_p2p_send": (_I, [_P, _L, _P, _P, _I, _L, _L, C.c_uint, _I, _I, _P]),
+    "oob_p2p_recv": (_I, [_P, _L, _P, _P, _I, _L, _L, C.c_uint, _I, _I, _P]),
 }
 
 _lib = None

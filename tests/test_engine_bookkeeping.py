@@ -1,0 +1,124 @@
+"""Product bookkeeping (oobleck_b200.execution.engine / pipeline / planning) bit-exact against golden vectors produced
+by the reference's own Python and against the tables in the reference's tests.  No GPU, no process group."""
+import json
+import os
+import types
+
+import pytest
+
+from oobleck_b200.execution import utils as U
+from oobleck_b200.execution.dataloader import OobleckSampler
+from oobleck_b200.execution.engine import DataParallelEngine, ReconfigurationEngine
+from oobleck_b200.execution.pipeline import OobleckPipeline
+from oobleck_b200.planning.pipeline_template import PipelineTemplate, StageExecutionResult
+from oracle import bookkeeping as bk
+
+G = os.path.join(os.path.dirname(__file__), "golden")
+NUM_LAYERS = 34
+
+
+def load(name):
+    return json.load(open(os.path.join(G, name + ".json")))
+
+
+def product_template(num_stages, gpn, nodes) -> PipelineTemplate:
+    """tests/conftest.py:144-213 dummy template, expressed with the product's template classes."""
+    o = bk.dummy_template(NUM_LAYERS, num_stages, gpn, nodes)
+    stages = [StageExecutionResult(s._layer_indices, s._num_gpus) for s in o.get_stages()]
+    return PipelineTemplate(stages, 0.1, NUM_LAYERS, nodes, gpn)
+
+
+class FakeEngine:
+    def __init__(self, gpn, templates):
+        self._num_gpus_per_node = gpn
+        self._pipeline_templates = templates
+        self._agent_pipe = None
+
+
+def fake_pipelines(gpn, templates):
+    pipes, used = [], 0
+    for pid, t in enumerate(templates):
+        n = t._num_nodes * gpn
+        pipes.append(OobleckPipeline(pid, t, list(range(used, used + n)), None, 0, None,
+                                     layer_cls=types.SimpleNamespace(device_type="cpu")))
+        used += n
+    return pipes
+
+
+def test_rank_grid_matches_oracle():
+    for gpn, stages, nodes in [(1, 4, 4), (4, 2, 1), (4, 4, 3), (2, 5, 4), (4, 5, 5)]:
+        t, o = product_template(stages, gpn, nodes), bk.dummy_template(NUM_LAYERS, stages, gpn, nodes)
+        ranks = list(range(3, 3 + nodes * gpn))
+        assert t.get_rank_grid(ranks) == o.get_rank_grid(ranks)
+
+
+def test_reconfiguration_policy_golden():
+    cases = load("reconfigure")
+    for c in cases:
+        gpn = c["gpus_per_node"]
+        templates = [product_template(i, gpn, i) for i in range(2, 6)]
+        eng = FakeEngine(gpn, templates)
+        eng._pipeline = None
+        re = ReconfigurationEngine(eng, fake_pipelines(gpn, templates), start_listener=False)
+        got = re.plan_new_ranks(list(c["failed"]))
+        assert got == c["result"]["ranks"], c
+
+
+def test_reconfiguration_insufficient_ranks():
+    templates = [product_template(2, 1, 2)]
+    eng = FakeEngine(1, templates)
+    re = ReconfigurationEngine(eng, fake_pipelines(1, templates), start_listener=False)
+    with pytest.raises(RuntimeError, match="insufficient"):
+        re.plan_new_ranks([1])
+
+
+def test_dp_groups_golden():
+    for c in load("dp_groups"):
+        gpn = c["gpus_per_node"]
+        templates = []
+        for n, k, s in zip(c["nodes"], c["num_pipelines"], c["stages"]):
+            templates += [product_template(s, gpn, n)] * k
+        eng = FakeEngine(gpn, templates)
+        created = []
+        dpe = DataParallelEngine(eng, fake_pipelines(gpn, templates), new_group=lambda r: created.append(list(r)) or len(created))
+        got = {str(l): {str(f): pg.ranks for f, pg in d.items()} for l, d in dpe._dp_process_groups.items()}
+        assert got == c["groups"]
+        # communicators are created once per distinct rank set, in the reference's first-use order
+        dedup = []
+        for r in c["order"]:
+            if r not in dedup:
+                dedup.append(r)
+        assert created == dedup and len(created) <= len(c["order"])
+
+
+def test_sampler_golden():
+    for c in load("sampler"):
+        for pi, want in enumerate(c["batches"]):
+            s = OobleckSampler(range(c["num_samples"]), c["microbatch_size"], pi, c["num_microbatches"], 0, c["epoch"],
+                               c["shuffle"])
+            assert [list(b) for b in s] == want
+            assert s.epoch == c["epoch"] + 1 and s.num_iterations_done == 0   # dataloader.py:99-100
+
+
+def test_dtype_wire_ids_golden():
+    want = load("dtype_ids")
+    assert {str(k).replace("torch.", ""): v for k, v in U.DTYPE_TO_ID.items()} == want
+    assert [U.DTYPE_TO_ID[d] for d in U.ID_TO_DTYPE] == list(range(len(U.ID_TO_DTYPE)))
+
+
+def test_pipeline_wiring_matches_oracle():
+    t = product_template(4, 1, 4)
+    for me in range(4):
+        import oobleck_b200.execution.pipeline as P
+        orig = P._my_rank
+        P._my_rank = lambda me=me: me
+        try:
+            p = OobleckPipeline(0, t, [0, 1, 2, 3], None, 0, None, layer_cls=types.SimpleNamespace(device_type="cpu"))
+            p.initialize_distributed_fsdp()
+            p.initialize_distributed_pipeline()
+            _, prev, nxt = bk.pipeline_neighbours(p.rank_grid, me)
+            assert (p.communication.prev_rank, p.communication.next_rank) == (prev, nxt)
+            mine = [lid for lid, pg in p._per_layer_pgs.items() if pg.rank_index() >= 0]
+            assert mine == bk.my_layers(p.rank_grid, me)
+        finally:
+            P._my_rank = orig
