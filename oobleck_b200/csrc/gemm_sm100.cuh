@@ -142,18 +142,21 @@ __device__ __forceinline__ void epilogue_store32(float (&x)[32], const GemmEpilo
 
 // Accumulation scheme.  The tensor core's fp32 accumulator TRUNCATES on every accumulate (measured on B200: the
 // error of a K=1600 six-product GEMM grew linearly with the number of MMAs, ~2^-25.7 per MMA, and did not depend
-// on the split level).  To keep fp32-grade results for any K the contraction is cut into chunks of
-// GEMM_CHUNK_KB k-blocks; within a chunk the leading product p0q0 accumulates in one TMEM region ("main") and
-// the small correction products in another ("corr"), and after every chunk the epilogue warps fold
-// main + corr into fp32 registers with round-to-nearest adds (promotion).  Two TMEM buffers (2 x 2 x BN columns)
-// let the MMA warp run one chunk ahead of the fold.
-constexpr int GEMM_CHUNK_KB = 4;   // 4 x 64 = 256 contraction elements = 16 main MMAs per chunk
+// on the split level).  To keep fp32-grade results for any K:
+//   * the leading product p0q0 ("main") is accumulated in chunks of GEMM_CHUNK_KB k-blocks; after every chunk the
+//     epilogue warps fold the chunk into fp32 registers with round-to-nearest adds (promotion).  Two TMEM buffers
+//     let the MMA warp run one chunk ahead of the fold;
+//   * the correction products ("corr", 2^-8 of main and smaller) accumulate over the whole contraction in a third
+//     TMEM region -- their truncation error is 2^-8 smaller still -- and are folded once at the end.
+// TMEM: main[2] + corr = 3 x BN columns.  (First version folded main+corr every 4 k-blocks: the extra TMEM reads
+// cost 35% of the GEMM's throughput -- profiles/README.md.)
+constexpr int GEMM_CHUNK_KB = 8;   // 8 x 64 = 512 contraction elements = 32 main MMAs per chunk
 
 template <int BN, bool A_MN, bool B_MN>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
                    const GemmParams p, const int num_stages) {
-  static_assert(BN == 128, "TMEM budget: 2 buffers x (main + corr) x BN columns must be <= 512");
+  static_assert(BN == 128, "TMEM budget: (2 main buffers + corr) x BN columns must be <= 512");
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   // carve: [stage ring][barriers]
   const int nsplit = p.nsplit;
@@ -232,10 +235,12 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_const
           mbar_wait(&tmem_empty_bar[buf], ((c >> 1) - 1) & 1);
           tc_fence_after();
         }
-        const uint32_t t_main = tmem_base + (uint32_t)(buf * 2 * BN);
-        const uint32_t t_corr = t_main + BN;
+        const uint32_t t_main = tmem_base + (uint32_t)(buf * BN);
+        const uint32_t t_corr = tmem_base + (uint32_t)(2 * BN);
         const int kb_end = min(kb + GEMM_CHUNK_KB, num_kb);
-        bool first_main = true, first_corr = true;
+        bool first_main = true;
+        const bool first_corr_chunk = (c == 0);
+        bool first_corr = first_corr_chunk;
         for (; kb < kb_end; ++kb) {
           const int s = kb % num_stages;
           mbar_wait(&full_bar[s], (kb / num_stages) & 1);
@@ -286,17 +291,18 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_const
       const int buf = c & 1;
       mbar_wait(&tmem_full_bar[buf], (c >> 1) & 1);
       tc_fence_after();
-      const uint32_t t_main = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(buf * 2 * BN);
+      const uint32_t t_lane = tmem_base + ((uint32_t)(quarter * 32) << 16);
+      const bool last_chunk = (c == num_chunks - 1);
 #pragma unroll
       for (int g = 0; g < BN / 32; ++g) {
-        uint32_t v[32], w[32];
-        tmem_ld_32x32(t_main + g * 32, v);
-        if (has_corr) tmem_ld_32x32(t_main + BN + g * 32, w);
+        uint32_t v[32];
+        tmem_ld_32x32(t_lane + (uint32_t)(buf * BN + g * 32), v);
         tmem_ld_wait();
-        if (has_corr) {
 #pragma unroll
-          for (int j = 0; j < 32; ++j) racc[g * 32 + j] += __uint_as_float(v[j]) + __uint_as_float(w[j]);
-        } else {
+        for (int j = 0; j < 32; ++j) racc[g * 32 + j] += __uint_as_float(v[j]);
+        if (has_corr && last_chunk) {   // the last chunk's commit also covers every correction MMA
+          tmem_ld_32x32(t_lane + (uint32_t)(2 * BN + g * 32), v);
+          tmem_ld_wait();
 #pragma unroll
           for (int j = 0; j < 32; ++j) racc[g * 32 + j] += __uint_as_float(v[j]);
         }
