@@ -44,7 +44,7 @@ int oob_split_planes(const float* x, void* planes, long n, long plane_stride, in
 int oob_gemm(const oob_planes* a, int a_mn, const oob_planes* b, int b_mn, int M, int N, int K, int nsplit,
              const oob_gemm_epilogue* e, void* stream) {
   OOB_CHECK(a && b && e, "oob_gemm: null argument");
-  GemmParams p;
+  GemmParams p{};
   p.M = M; p.N = N; p.K = K; p.nsplit = nsplit;
   p.epi.d = e->d; p.epi.ldd = e->ldd; p.epi.bias = e->bias; p.epi.resid = e->resid; p.epi.ldr = e->ldr;
   p.epi.accumulate = e->accumulate; p.epi.act = e->act; p.epi.aux = e->aux; p.epi.ldaux = e->ldaux;

@@ -1,8 +1,10 @@
 // Host launcher for the tcgen05 split-bf16 GEMM: builds the TMA tensor maps and picks the stage count.
+#include <cstdlib>
 #include <mutex>
 #include <vector>
 
 #include "gemm_sm100.cuh"
+#include "gemm_sm100_2cta.cuh"
 
 namespace oob {
 
@@ -99,7 +101,51 @@ static int launch_t(const CUtensorMap& ta, const CUtensorMap& tb, const GemmPara
   return 0;
 }
 
-int gemm_launch(const PlaneMat& A, int a_mn, const PlaneMat& B, int b_mn, const GemmParams& p, cudaStream_t stream) {
+template <int BN, bool A_MN, bool B_MN>
+static int launch2_t(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, cudaStream_t stream) {
+  static int max_smem = -1;
+  if (max_smem < 0) {
+    int dev = 0;
+    OOB_CUDA_OK(cudaGetDevice(&dev));
+    OOB_CUDA_OK(cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
+  }
+  static bool attr_set = false;
+  auto kern = gemm_bf16x3_2cta_kernel<BN, A_MN, B_MN>;
+  if (!attr_set) {
+    OOB_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
+    attr_set = true;
+  }
+  const int stage = gemm2_stage_bytes<BN>(p.nsplit);
+  const int overhead = 1024 + 256;
+  int stages = (max_smem - overhead) / stage;
+  if (stages > 8) stages = 8;
+  OOB_CHECK(stages >= 2, "2-CTA GEMM tile does not fit %d B of shared memory", max_smem);
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(2 * ((p.M + 2 * GEMM_BM - 1) / (2 * GEMM_BM)), (p.N + BN - 1) / BN);
+  cfg.blockDim = dim3(GEMM_THREADS);
+  cfg.dynamicSmemBytes = (size_t)stages * stage + overhead;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  TimedLaunch tl{};
+  if (g_timing) { tl.a = get_event(); tl.b = get_event(); tl.flops = 2.0 * p.M * p.N * p.K; cudaEventRecord(tl.a, stream); }
+  OOB_CUDA_OK(cudaLaunchKernelEx(&cfg, kern, ta, tb, p, stages));
+  if (g_timing) { cudaEventRecord(tl.b, stream); g_timed.push_back(tl); }
+  count_launch();
+  return 0;
+}
+
+int gemm_launch(const PlaneMat& A, int a_mn, const PlaneMat& B, int b_mn, const GemmParams& p_in, cudaStream_t stream) {
+  GemmParams p = p_in;
+  static const int env_chunk = [] { const char* e = getenv("OOB_GEMM_CHUNK_KB"); return e ? atoi(e) : 0; }();
+  if (p.chunk_kb <= 0) p.chunk_kb = env_chunk;
+  static const int env_debug = [] { const char* e = getenv("OOB_GEMM_DEBUG"); return e ? atoi(e) : 0; }();
+  p.debug = env_debug;
   OOB_CHECK(p.nsplit >= 1 && p.nsplit <= 3, "nsplit must be 1..3");
   OOB_CHECK(p.M > 0 && p.N > 0 && p.K > 0, "empty GEMM %d x %d x %d", p.M, p.N, p.K);
   constexpr int BN = 128;
@@ -114,14 +160,22 @@ int gemm_launch(const PlaneMat& A, int a_mn, const PlaneMat& B, int b_mn, const 
     rc = make_map(&ta, PlaneMat{A.base, (long)p.K, (long)p.M, A.ld, A.plane_stride, A.nplanes}, GEMM_BK, p.nsplit);
   }
   if (rc) return rc;
+  static const int use_2cta = [] { const char* e = getenv("OOB_GEMM_2CTA"); return e ? atoi(e) : 0; }();
   if (!b_mn) {
     OOB_CHECK(B.rows >= p.N && B.cols >= p.K, "B (K-major) is %ld x %ld, need %d x %d", B.rows, B.cols, p.N, p.K);
-    rc = make_map(&tb, PlaneMat{B.base, (long)p.N, (long)p.K, B.ld, B.plane_stride, B.nplanes}, BN, p.nsplit);
+    rc = make_map(&tb, PlaneMat{B.base, (long)p.N, (long)p.K, B.ld, B.plane_stride, B.nplanes}, use_2cta ? BN / 2 : BN,
+                  p.nsplit);
   } else {
     OOB_CHECK(B.rows >= p.K && B.cols >= p.N, "B (N-major) is %ld x %ld, need %d x %d", B.rows, B.cols, p.K, p.N);
     rc = make_map(&tb, PlaneMat{B.base, (long)p.K, (long)p.N, B.ld, B.plane_stride, B.nplanes}, GEMM_BK, p.nsplit);
   }
   if (rc) return rc;
+  if (use_2cta) {
+    if (!a_mn && !b_mn) return launch2_t<BN, false, false>(ta, tb, p, stream);
+    if (!a_mn && b_mn) return launch2_t<BN, false, true>(ta, tb, p, stream);
+    if (a_mn && !b_mn) return launch2_t<BN, true, false>(ta, tb, p, stream);
+    return launch2_t<BN, true, true>(ta, tb, p, stream);
+  }
   if (!a_mn && !b_mn) return launch_t<BN, false, false>(ta, tb, p, stream);
   if (!a_mn && b_mn) return launch_t<BN, false, true>(ta, tb, p, stream);
   if (a_mn && !b_mn) return launch_t<BN, true, false>(ta, tb, p, stream);

@@ -47,6 +47,8 @@ struct GemmParams {
   int M, N, K;
   int nsplit;   // planes used from each operand (1..3)
   GemmEpilogue epi;
+  int chunk_kb; // promotion chunk in k-blocks (0 = default GEMM_CHUNK_KB)
+  int debug;    // diagnostics only (tools/gemm_sweep.py): 1 skip output stores, 2 single accumulator, 4 skip MMAs
 };
 
 constexpr int GEMM_BM = 128;
@@ -175,7 +177,8 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_const
   const int m0 = blockIdx.y * GEMM_BM;
   const int n0 = blockIdx.x * BN;
   const int num_kb = (p.K + GEMM_BK - 1) / GEMM_BK;
-  const int num_chunks = (num_kb + GEMM_CHUNK_KB - 1) / GEMM_CHUNK_KB;
+  const int chunk_kb = p.chunk_kb > 0 ? p.chunk_kb : GEMM_CHUNK_KB;
+  const int num_chunks = (num_kb + chunk_kb - 1) / chunk_kb;
   constexpr uint32_t TMEM_COLS = 4 * BN;  // 512
 
   if (warp == 0 && lane == 0) {
@@ -236,8 +239,8 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_const
           tc_fence_after();
         }
         const uint32_t t_main = tmem_base + (uint32_t)(buf * BN);
-        const uint32_t t_corr = tmem_base + (uint32_t)(2 * BN);
-        const int kb_end = min(kb + GEMM_CHUNK_KB, num_kb);
+        const uint32_t t_corr = (p.debug & 2) ? t_main : tmem_base + (uint32_t)(2 * BN);
+        const int kb_end = min(kb + chunk_kb, num_kb);
         bool first_main = true;
         const bool first_corr_chunk = (c == 0);
         bool first_corr = first_corr_chunk;
@@ -247,30 +250,40 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_const
           tc_fence_after();
           const uint32_t sa = smem_u32(smem + (size_t)s * stage_bytes);
           const uint32_t sb = sa + a_bytes;
+          // Issue order: the tensor pipe stalls whenever consecutive MMAs target different accumulators (measured:
+          // interleaving main/corr per k-step cost 1.5x), so each k-block issues all its "main" MMAs and all its
+          // "corr" MMAs as two runs, and alternate k-blocks swap the two runs -> one accumulator switch per k-block.
 #pragma unroll 1
-          for (int k = 0; k < GEMM_BK / 16; ++k) {
+          for (int pass = 0; pass < 2; ++pass) {
+            const bool do_main = ((pass ^ kb) & 1) == 0;
+            if (!do_main && nprod == 1) continue;
+            const int q_lo = do_main ? 0 : 1, q_hi = do_main ? 1 : nprod;
 #pragma unroll 1
-            for (int q = 0; q < nprod; ++q) {
-              const int pa = (kProdA >> (4 * q)) & 0xF, pb = (kProdB >> (4 * q)) & 0xF;
-              uint64_t da, db;
-              if constexpr (!A_MN) {
-                // K-major SW128: plane pa at +pa*BM*128B; 8-row groups 1024 B apart; k-step = 32 B inside the atom
-                da = make_smem_desc(sa + pa * GEMM_BM * 128 + k * 32, 0, 1024, SWZ_128B);
-              } else {
-                // MN-major SW128: [m-atom][plane][BK rows][128 B]; k-step = 16 rows = 2048 B
-                da = make_smem_desc(sa + pa * GEMM_BK * 128 + k * 2048, nsplit * GEMM_BK * 128, 1024, SWZ_128B);
-              }
-              if constexpr (!B_MN) {
-                db = make_smem_desc(sb + pb * BN * 128 + k * 32, 0, 1024, SWZ_128B);
-              } else {
-                db = make_smem_desc(sb + pb * GEMM_BK * 128 + k * 2048, nsplit * GEMM_BK * 128, 1024, SWZ_128B);
-              }
-              if (q == 0) {
-                umma_bf16(t_main, da, db, idesc, first_main ? 0u : 1u);
-                first_main = false;
-              } else {
-                umma_bf16(t_corr, da, db, idesc, first_corr ? 0u : 1u);
-                first_corr = false;
+            for (int k = 0; k < GEMM_BK / 16; ++k) {
+#pragma unroll 1
+              for (int q = q_lo; q < q_hi; ++q) {
+                const int pa = (kProdA >> (4 * q)) & 0xF, pb = (kProdB >> (4 * q)) & 0xF;
+                uint64_t da, db;
+                if constexpr (!A_MN) {
+                  // K-major SW128: plane pa at +pa*BM*128B; 8-row groups 1024 B apart; k-step = 32 B inside the atom
+                  da = make_smem_desc(sa + pa * GEMM_BM * 128 + k * 32, 0, 1024, SWZ_128B);
+                } else {
+                  // MN-major SW128: [m-atom][plane][BK rows][128 B]; k-step = 16 rows = 2048 B
+                  da = make_smem_desc(sa + pa * GEMM_BK * 128 + k * 2048, nsplit * GEMM_BK * 128, 1024, SWZ_128B);
+                }
+                if constexpr (!B_MN) {
+                  db = make_smem_desc(sb + pb * BN * 128 + k * 32, 0, 1024, SWZ_128B);
+                } else {
+                  db = make_smem_desc(sb + pb * GEMM_BK * 128 + k * 2048, nsplit * GEMM_BK * 128, 1024, SWZ_128B);
+                }
+                if (p.debug & 4) continue;
+                if (do_main || (p.debug & 2)) {
+                  umma_bf16(t_main, da, db, idesc, first_main ? 0u : 1u);
+                  first_main = false;
+                } else {
+                  umma_bf16(t_corr, da, db, idesc, first_corr ? 0u : 1u);
+                  first_corr = false;
+                }
               }
             }
           }
@@ -283,7 +296,7 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_const
     // ===================== epilogue (warps 2..5): promotion + fused output =====================
     const int quarter = warp & 3;             // TMEM lane quarter this warp may access
     const int row = m0 + quarter * 32 + lane;
-    const bool has_corr = nsplit > 1;
+    const bool has_corr = nsplit > 1 && !(p.debug & 2);
     float racc[BN];
 #pragma unroll
     for (int j = 0; j < BN; ++j) racc[j] = 0.f;
@@ -311,7 +324,7 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_const
       __syncwarp();
       if (lane == 0) mbar_arrive(&tmem_empty_bar[buf]);
     }
-    if (row < p.M) {
+    if (row < p.M && !(p.debug & 1)) {
 #pragma unroll
       for (int g = 0; g < BN / 32; ++g) {
         const int col0 = n0 + g * 32;

@@ -75,6 +75,11 @@ def _rank() -> int:
     return dist.get_rank() if dist.is_initialized() else 0
 
 
+# Communicators survive pipeline rebuilds: one per rank set for the life of the process.  (torch names group-local
+# groups by a hash of their ranks, so creating the same set twice would also collide in the rendezvous store.)
+_COMMUNICATORS: dict[tuple[int, ...], Any] = {}
+
+
 # ---- data parallel -------------------------------------------------------------------------------------------------
 class DataParallelEngine:
     def __init__(self, engine, pipelines: list[OobleckPipeline], new_group=None):
@@ -89,8 +94,19 @@ class DataParallelEngine:
         self._ranks_grid = ranks_grid
         # One communicator per DISTINCT rank set, created in first-use order (identical on every rank).  The reference
         # calls new_group once per (layer, fsdp_index) (:390-392); the mapping below is otherwise the same.
-        make = new_group or (lambda ranks: dist.new_group(ranks) if dist.is_initialized() and len(ranks) > 1 else None)
         my_rank = _rank()
+
+        def _make(ranks):
+            # group-local creation: only member ranks take part, so survivors can build communicators after a loss
+            # without re-creating the world group (engine.py:539-593 tears the NCCL world down and re-inits it)
+            if not dist.is_initialized() or len(ranks) <= 1 or my_rank not in ranks:
+                return None
+            key = tuple(sorted(ranks))
+            if key not in _COMMUNICATORS:
+                _COMMUNICATORS[key] = dist.new_group(list(key), use_local_synchronization=True)
+            return _COMMUNICATORS[key]
+
+        make = new_group or _make
         cache: dict[tuple[int, ...], Any] = {}
         self._dp_process_groups: dict[int, dict[int, RankGroup]] = defaultdict(dict)
         self._fsdp_indices: dict[int, list[int]] = defaultdict(list)
@@ -295,8 +311,7 @@ class ReconfigurationEngine:
         for work, layer in works:
             work.wait()
             layer.refresh_planes()
-        if dist.is_initialized():
-            dist.barrier()
+        # no world barrier (engine.py:308): a lost rank can never join it; the broadcasts above are the only ordering
         if torch.cuda.is_available():
             torch.cuda.synchronize()
 
