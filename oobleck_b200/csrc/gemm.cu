@@ -5,6 +5,7 @@
 
 #include "gemm_sm100.cuh"
 #include "gemm_sm100_2cta.cuh"
+#include "gemm_sm100_persistent.cuh"
 
 namespace oob {
 
@@ -140,6 +141,50 @@ static int launch2_t(const CUtensorMap& ta, const CUtensorMap& tb, const GemmPar
   return 0;
 }
 
+template <int BN, bool A_MN, bool B_MN, bool TWO_CTA>
+static int launchp_t(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, cudaStream_t stream) {
+  static int max_smem = -1, num_sms = 0;
+  if (max_smem < 0) {
+    int dev = 0;
+    OOB_CUDA_OK(cudaGetDevice(&dev));
+    OOB_CUDA_OK(cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
+    OOB_CUDA_OK(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
+  }
+  static bool attr_set = false;
+  auto kern = gemm_bf16x3_persistent_kernel<BN, A_MN, B_MN, TWO_CTA>;
+  if (!attr_set) {
+    OOB_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
+    attr_set = true;
+  }
+  const int stage = gemmp_stage_bytes<BN, TWO_CTA>(p.nsplit);
+  const int overhead = 1024 + 256;
+  int stages = (max_smem - overhead) / stage;
+  if (stages > 8) stages = 8;
+  OOB_CHECK(stages >= 2, "persistent GEMM tile does not fit %d B of shared memory", max_smem);
+  const int tile_m = TWO_CTA ? 2 * GEMM_BM : GEMM_BM;
+  const int tiles = ((p.M + tile_m - 1) / tile_m) * ((p.N + BN - 1) / BN);
+  const int max_units = TWO_CTA ? num_sms / 2 : num_sms;
+  const int units = tiles < max_units ? tiles : max_units;
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(TWO_CTA ? 2 * units : units);
+  cfg.blockDim = dim3(GEMM_THREADS);
+  cfg.dynamicSmemBytes = (size_t)stages * stage + overhead;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = TWO_CTA ? 2 : 1;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  TimedLaunch tl{};
+  if (g_timing) { tl.a = get_event(); tl.b = get_event(); tl.flops = 2.0 * p.M * p.N * p.K; cudaEventRecord(tl.a, stream); }
+  OOB_CUDA_OK(cudaLaunchKernelEx(&cfg, kern, ta, tb, p, stages));
+  if (g_timing) { cudaEventRecord(tl.b, stream); g_timed.push_back(tl); }
+  count_launch();
+  return 0;
+}
+
 int gemm_launch(const PlaneMat& A, int a_mn, const PlaneMat& B, int b_mn, const GemmParams& p_in, cudaStream_t stream) {
   GemmParams p = p_in;
   static const int env_chunk = [] { const char* e = getenv("OOB_GEMM_CHUNK_KB"); return e ? atoi(e) : 0; }();
@@ -170,6 +215,19 @@ int gemm_launch(const PlaneMat& A, int a_mn, const PlaneMat& B, int b_mn, const 
     rc = make_map(&tb, PlaneMat{B.base, (long)p.K, (long)p.N, B.ld, B.plane_stride, B.nplanes}, GEMM_BK, p.nsplit);
   }
   if (rc) return rc;
+  static const int use_persist = [] { const char* e = getenv("OOB_GEMM_PERSIST"); return e ? atoi(e) : 0; }();
+  if (use_persist && use_2cta) {
+    if (!a_mn && !b_mn) return launchp_t<BN, false, false, true>(ta, tb, p, stream);
+    if (!a_mn && b_mn) return launchp_t<BN, false, true, true>(ta, tb, p, stream);
+    if (a_mn && !b_mn) return launchp_t<BN, true, false, true>(ta, tb, p, stream);
+    return launchp_t<BN, true, true, true>(ta, tb, p, stream);
+  }
+  if (use_persist) {
+    if (!a_mn && !b_mn) return launchp_t<BN, false, false, false>(ta, tb, p, stream);
+    if (!a_mn && b_mn) return launchp_t<BN, false, true, false>(ta, tb, p, stream);
+    if (a_mn && !b_mn) return launchp_t<BN, true, false, false>(ta, tb, p, stream);
+    return launchp_t<BN, true, true, false>(ta, tb, p, stream);
+  }
   if (use_2cta) {
     if (!a_mn && !b_mn) return launch2_t<BN, false, false>(ta, tb, p, stream);
     if (!a_mn && b_mn) return launch2_t<BN, false, true>(ta, tb, p, stream);

@@ -48,7 +48,7 @@ struct GemmParams {
   int nsplit;   // planes used from each operand (1..3)
   GemmEpilogue epi;
   int chunk_kb; // promotion chunk in k-blocks (0 = default GEMM_CHUNK_KB)
-  int debug;    // diagnostics only (tools/gemm_sweep.py): 1 skip output stores, 2 single accumulator, 4 skip MMAs
+  int debug;    // diagnostics only (tools/gemm_sweep.py): 1 = skip the output stores
 };
 
 constexpr int GEMM_BM = 128;
@@ -60,11 +60,53 @@ __host__ __device__ constexpr int gemm_stage_bytes(int nsplit) {
   return nsplit * (GEMM_BM + BN) * GEMM_BK * 2;
 }
 
-// product list per split level (plane index of A / B for product q, one nibble each):
+// product list per split level (plane index of A / B for product q), see issue_kblock:
 //   q:      0 1 2 3 4 5
 //   A plane 0 0 1 1 0 2      B plane 0 1 0 1 2 0
-constexpr uint32_t kProdA = 0x201100u;
-constexpr uint32_t kProdB = 0x021010u;
+
+
+// ---------------------------------------------------------------------------------------------------------------
+// MMA issue for one k-block (64 contraction elements), fully unrolled with compile-time descriptor offsets.
+// The issuing thread is a single lane: every extra dependent instruction per MMA is ~4-6 clk of issue latency, and a
+// 128x128x16 MMA only lasts 64 clk.  (First version computed descriptors in a runtime triple loop: ~220 clk of issue
+// per MMA, the GEMM ran at 26% tensor-pipe utilisation -- profiles/README.md.)
+template <bool TWO_CTA>
+__device__ __forceinline__ void umma_any(uint32_t td, uint64_t da, uint64_t db, uint32_t idesc, uint32_t acc);
+
+template <int NS, int BROWS, bool A_MN, bool B_MN, bool TWO_CTA>
+__device__ __forceinline__ void issue_kblock(uint32_t sa, uint32_t sb, uint32_t t_main, uint32_t t_corr,
+                                             uint32_t idesc, uint32_t& acc_main, uint32_t& acc_corr) {
+  constexpr uint32_t A_PLANE = (A_MN ? GEMM_BK : GEMM_BM) * 128;   // bytes between planes inside a stage
+  constexpr uint32_t B_PLANE = (B_MN ? GEMM_BK : BROWS) * 128;
+  constexpr uint32_t A_KSTEP = A_MN ? 2048 : 32;                   // bytes per 16 contraction elements
+  constexpr uint32_t B_KSTEP = B_MN ? 2048 : 32;
+  constexpr uint32_t A_LBO = A_MN ? NS * GEMM_BK * 128 : 0;        // MN-major: distance between 64-wide atoms
+  constexpr uint32_t B_LBO = B_MN ? NS * GEMM_BK * 128 : 0;
+  constexpr int NPROD = NS == 1 ? 1 : (NS == 2 ? 3 : 6);
+  constexpr int PA[6] = {0, 0, 1, 1, 0, 2};
+  constexpr int PB[6] = {0, 1, 0, 1, 2, 0};
+  const uint64_t a_base = make_smem_desc(sa, A_LBO, 1024, SWZ_128B);
+  const uint64_t b_base = make_smem_desc(sb, B_LBO, 1024, SWZ_128B);
+#pragma unroll
+  for (int k = 0; k < GEMM_BK / 16; ++k) {   // leading product p0q0 -> "main"
+    umma_any<TWO_CTA>(t_main, a_base + ((k * A_KSTEP) >> 4), b_base + ((k * B_KSTEP) >> 4), idesc, acc_main);
+    acc_main = 1u;
+  }
+#pragma unroll
+  for (int k = 0; k < GEMM_BK / 16; ++k) {   // corrections -> "corr"
+#pragma unroll
+    for (int q = 1; q < NPROD; ++q) {
+      umma_any<TWO_CTA>(t_corr, a_base + ((PA[q] * A_PLANE + k * A_KSTEP) >> 4),
+                        b_base + ((PB[q] * B_PLANE + k * B_KSTEP) >> 4), idesc, acc_corr);
+      acc_corr = 1u;
+    }
+  }
+}
+
+template <>
+__device__ __forceinline__ void umma_any<false>(uint32_t td, uint64_t da, uint64_t db, uint32_t idesc, uint32_t acc) {
+  umma_bf16(td, da, db, idesc, acc);
+}
 
 // Fused epilogue for 32 consecutive columns of one output row held in registers.
 __device__ __forceinline__ void epilogue_store32(float (&x)[32], const GemmEpilogue& e, int row, int col0, int N) {
@@ -230,7 +272,6 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_const
     // ===================== MMA issuer =====================
     if (lane == 0) {
       constexpr uint32_t idesc = make_idesc_bf16(GEMM_BM, BN, A_MN ? 1 : 0, B_MN ? 1 : 0);
-      const int nprod = nsplit == 1 ? 1 : (nsplit == 2 ? 3 : 6);
       int kb = 0;
       for (int c = 0; c < num_chunks; ++c) {
         const int buf = c & 1;
@@ -239,54 +280,19 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_const
           tc_fence_after();
         }
         const uint32_t t_main = tmem_base + (uint32_t)(buf * BN);
-        const uint32_t t_corr = (p.debug & 2) ? t_main : tmem_base + (uint32_t)(2 * BN);
+        const uint32_t t_corr = tmem_base + (uint32_t)(2 * BN);
         const int kb_end = min(kb + chunk_kb, num_kb);
-        bool first_main = true;
-        const bool first_corr_chunk = (c == 0);
-        bool first_corr = first_corr_chunk;
+        uint32_t acc_main = 0u;                 // first main MMA of a chunk overwrites its buffer
+        uint32_t acc_corr = (c == 0) ? 0u : 1u; // corrections accumulate across the whole contraction
         for (; kb < kb_end; ++kb) {
           const int s = kb % num_stages;
           mbar_wait(&full_bar[s], (kb / num_stages) & 1);
           tc_fence_after();
           const uint32_t sa = smem_u32(smem + (size_t)s * stage_bytes);
           const uint32_t sb = sa + a_bytes;
-          // Issue order: the tensor pipe stalls whenever consecutive MMAs target different accumulators (measured:
-          // interleaving main/corr per k-step cost 1.5x), so each k-block issues all its "main" MMAs and all its
-          // "corr" MMAs as two runs, and alternate k-blocks swap the two runs -> one accumulator switch per k-block.
-#pragma unroll 1
-          for (int pass = 0; pass < 2; ++pass) {
-            const bool do_main = ((pass ^ kb) & 1) == 0;
-            if (!do_main && nprod == 1) continue;
-            const int q_lo = do_main ? 0 : 1, q_hi = do_main ? 1 : nprod;
-#pragma unroll 1
-            for (int k = 0; k < GEMM_BK / 16; ++k) {
-#pragma unroll 1
-              for (int q = q_lo; q < q_hi; ++q) {
-                const int pa = (kProdA >> (4 * q)) & 0xF, pb = (kProdB >> (4 * q)) & 0xF;
-                uint64_t da, db;
-                if constexpr (!A_MN) {
-                  // K-major SW128: plane pa at +pa*BM*128B; 8-row groups 1024 B apart; k-step = 32 B inside the atom
-                  da = make_smem_desc(sa + pa * GEMM_BM * 128 + k * 32, 0, 1024, SWZ_128B);
-                } else {
-                  // MN-major SW128: [m-atom][plane][BK rows][128 B]; k-step = 16 rows = 2048 B
-                  da = make_smem_desc(sa + pa * GEMM_BK * 128 + k * 2048, nsplit * GEMM_BK * 128, 1024, SWZ_128B);
-                }
-                if constexpr (!B_MN) {
-                  db = make_smem_desc(sb + pb * BN * 128 + k * 32, 0, 1024, SWZ_128B);
-                } else {
-                  db = make_smem_desc(sb + pb * GEMM_BK * 128 + k * 2048, nsplit * GEMM_BK * 128, 1024, SWZ_128B);
-                }
-                if (p.debug & 4) continue;
-                if (do_main || (p.debug & 2)) {
-                  umma_bf16(t_main, da, db, idesc, first_main ? 0u : 1u);
-                  first_main = false;
-                } else {
-                  umma_bf16(t_corr, da, db, idesc, first_corr ? 0u : 1u);
-                  first_corr = false;
-                }
-              }
-            }
-          }
+          if (nsplit == 3) issue_kblock<3, BN, A_MN, B_MN, false>(sa, sb, t_main, t_corr, idesc, acc_main, acc_corr);
+          else if (nsplit == 2) issue_kblock<2, BN, A_MN, B_MN, false>(sa, sb, t_main, t_corr, idesc, acc_main, acc_corr);
+          else issue_kblock<1, BN, A_MN, B_MN, false>(sa, sb, t_main, t_corr, idesc, acc_main, acc_corr);
           umma_commit(&empty_bar[s]);  // frees the ring slot once these MMAs have read it
         }
         umma_commit(&tmem_full_bar[buf]);  // chunk accumulators complete
@@ -296,7 +302,7 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_const
     // ===================== epilogue (warps 2..5): promotion + fused output =====================
     const int quarter = warp & 3;             // TMEM lane quarter this warp may access
     const int row = m0 + quarter * 32 + lane;
-    const bool has_corr = nsplit > 1 && !(p.debug & 2);
+    const bool has_corr = nsplit > 1;
     float racc[BN];
 #pragma unroll
     for (int j = 0; j < BN; ++j) racc[j] = 0.f;

@@ -59,6 +59,10 @@ __device__ __forceinline__ void umma_bf16_2sm(uint32_t tmem_d, uint64_t desc_a, 
       "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+template <>
+__device__ __forceinline__ void umma_any<true>(uint32_t td, uint64_t da, uint64_t db, uint32_t idesc, uint32_t acc) {
+  umma_bf16_2sm(td, da, db, idesc, acc);
+}
 // arrive on the barrier at this smem offset in both CTAs of the pair when the issued MMAs have completed
 __device__ __forceinline__ void umma_commit_2sm(uint64_t* bar) {
   const uint16_t mask = 0x3;
@@ -155,9 +159,8 @@ gemm_bf16x3_2cta_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_
     // ===================== MMA issuer (leader CTA only) =====================
     if (leader && lane == 0) {
       constexpr uint32_t idesc = make_idesc_bf16(2 * GEMM_BM, BN, A_MN ? 1 : 0, B_MN ? 1 : 0);
-      const int nprod = nsplit == 1 ? 1 : (nsplit == 2 ? 3 : 6);
       int kb = 0;
-      bool first_corr = true;
+      uint32_t acc_corr = 0u;
       for (int c = 0; c < num_chunks; ++c) {
         const int buf = c & 1;
         if (c >= 2) {
@@ -167,49 +170,16 @@ gemm_bf16x3_2cta_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_
         const uint32_t t_main = tmem_base + (uint32_t)(buf * BN);
         const uint32_t t_corr = tmem_base + (uint32_t)(2 * BN);
         const int kb_end = min(kb + chunk_kb, num_kb);
-        bool first_main = true;
+        uint32_t acc_main = 0u;
         for (; kb < kb_end; ++kb) {
           const int s = kb % num_stages;
           mbar_wait(&full_bar[s], (kb / num_stages) & 1);
           tc_fence_after();
           const uint32_t sa = smem_u32(smem + (size_t)s * stage_bytes);
           const uint32_t sb = sa + a_bytes;
-          // Issue order: the tensor pipe stalls whenever consecutive MMAs target different accumulators (measured:
-          // interleaving main/corr per k-step cost 1.5x), so each k-block issues all its "main" MMAs and all its
-          // "corr" MMAs as two runs, and alternate k-blocks swap the two runs -> one accumulator switch per k-block.
-#pragma unroll 1
-          for (int pass = 0; pass < 2; ++pass) {
-            const bool do_main = ((pass ^ kb) & 1) == 0;
-            if (!do_main && nprod == 1) continue;
-            const int q_lo = do_main ? 0 : 1, q_hi = do_main ? 1 : nprod;
-#pragma unroll 1
-            for (int k = 0; k < GEMM_BK / 16; ++k) {
-#pragma unroll 1
-              for (int q = q_lo; q < q_hi; ++q) {
-                const int pa = (kProdA >> (4 * q)) & 0xF, pb = (kProdB >> (4 * q)) & 0xF;
-                uint64_t da, db;
-                if constexpr (!A_MN) {
-                  // K-major SW128: plane pa at +pa*BM*128B; 8-row groups 1024 B apart; k-step = 32 B inside the atom
-                  da = make_smem_desc(sa + pa * GEMM_BM * 128 + k * 32, 0, 1024, SWZ_128B);
-                } else {
-                  // MN-major SW128: [m-atom][plane][BK rows][128 B]; k-step = 16 rows = 2048 B
-                  da = make_smem_desc(sa + pa * GEMM_BK * 128 + k * 2048, nsplit * GEMM_BK * 128, 1024, SWZ_128B);
-                }
-                if constexpr (!B_MN) {
-                  db = make_smem_desc(sb + pb * BNH * 128 + k * 32, 0, 1024, SWZ_128B);
-                } else {
-                  db = make_smem_desc(sb + pb * GEMM_BK * 128 + k * 2048, nsplit * GEMM_BK * 128, 1024, SWZ_128B);
-                }
-                if (do_main) {
-                  umma_bf16_2sm(t_main, da, db, idesc, first_main ? 0u : 1u);
-                  first_main = false;
-                } else {
-                  umma_bf16_2sm(t_corr, da, db, idesc, first_corr ? 0u : 1u);
-                  first_corr = false;
-                }
-              }
-            }
-          }
+          if (nsplit == 3) issue_kblock<3, BNH, A_MN, B_MN, true>(sa, sb, t_main, t_corr, idesc, acc_main, acc_corr);
+          else if (nsplit == 2) issue_kblock<2, BNH, A_MN, B_MN, true>(sa, sb, t_main, t_corr, idesc, acc_main, acc_corr);
+          else issue_kblock<1, BNH, A_MN, B_MN, true>(sa, sb, t_main, t_corr, idesc, acc_main, acc_corr);
           umma_commit_2sm(&empty_bar[s]);
         }
         umma_commit_2sm(&tmem_full_bar[buf]);
