@@ -26,8 +26,9 @@ static EncodeTiledFn get_encode_fn() {
   return fn;
 }
 
-// 3-D map over [planes][rows][ld] bf16; box = {64 elements, box_rows, box_planes}, SWIZZLE_128B.
-static int make_map(CUtensorMap* m, const PlaneMat& a, int box_rows, int box_planes) {
+// 3-D map over [planes][rows][ld] bf16; box = {bk elements, box_rows, box_planes}; bk = 64 -> SWIZZLE_128B,
+// bk = 32 -> SWIZZLE_64B (one smem row is exactly one swizzle span, see KCfg).
+static int make_map(CUtensorMap* m, const PlaneMat& a, int box_rows, int box_planes, int bk) {
   EncodeTiledFn enc = get_encode_fn();
   OOB_CHECK(enc != nullptr, "cuTensorMapEncodeTiled entry point unavailable (no CUDA driver?)");
   OOB_CHECK((a.ld % 8) == 0 && (a.plane_stride % 8) == 0, "split-plane operand strides must be multiples of 8");
@@ -35,10 +36,11 @@ static int make_map(CUtensorMap* m, const PlaneMat& a, int box_rows, int box_pla
   OOB_CHECK(box_planes <= a.nplanes, "GEMM asks for %d planes, operand has %d", box_planes, a.nplanes);
   cuuint64_t dims[3] = {(cuuint64_t)a.cols, (cuuint64_t)a.rows, (cuuint64_t)a.nplanes};
   cuuint64_t strides[2] = {(cuuint64_t)a.ld * 2, (cuuint64_t)a.plane_stride * 2};
-  cuuint32_t box[3] = {64, (cuuint32_t)box_rows, (cuuint32_t)box_planes};
+  cuuint32_t box[3] = {(cuuint32_t)bk, (cuuint32_t)box_rows, (cuuint32_t)box_planes};
   cuuint32_t estr[3] = {1, 1, 1};
   CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<bf16*>(a.base), dims, strides, box, estr,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, bk == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   OOB_CHECK(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed (%d): rows=%ld cols=%ld ld=%ld", (int)r, a.rows, a.cols,
             a.ld);
@@ -72,37 +74,7 @@ int gemm_timing_end(double* total_ms, double* total_flops, long* launches) {
   return 0;
 }
 
-template <int BN, bool A_MN, bool B_MN>
-static int launch_t(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, cudaStream_t stream) {
-  static int max_smem = -1;
-  if (max_smem < 0) {
-    int dev = 0;
-    OOB_CUDA_OK(cudaGetDevice(&dev));
-    OOB_CUDA_OK(cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
-  }
-  static bool attr_set = false;
-  auto kern = gemm_bf16x3_kernel<BN, A_MN, B_MN>;
-  if (!attr_set) {
-    OOB_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
-    attr_set = true;
-  }
-  const int stage = gemm_stage_bytes<BN>(p.nsplit);
-  const int overhead = 1024 /*align slack*/ + 256 /*barriers*/;
-  int stages = (max_smem - overhead) / stage;
-  if (stages > 8) stages = 8;
-  OOB_CHECK(stages >= 2, "GEMM tile does not fit %d B of shared memory", max_smem);
-  const size_t smem = (size_t)stages * stage + overhead;
-  dim3 grid((p.N + BN - 1) / BN, (p.M + GEMM_BM - 1) / GEMM_BM);
-  TimedLaunch tl{};
-  if (g_timing) { tl.a = get_event(); tl.b = get_event(); tl.flops = 2.0 * p.M * p.N * p.K; cudaEventRecord(tl.a, stream); }
-  kern<<<grid, GEMM_THREADS, smem, stream>>>(ta, tb, p, stages);
-  OOB_CUDA_OK(cudaGetLastError());
-  if (g_timing) { cudaEventRecord(tl.b, stream); g_timed.push_back(tl); }
-  count_launch();
-  return 0;
-}
-
-template <int BN, bool A_MN, bool B_MN>
+template <int BN, bool A_MN, bool B_MN, int BK>
 static int launch2_t(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, cudaStream_t stream) {
   static int max_smem = -1;
   if (max_smem < 0) {
@@ -111,15 +83,15 @@ static int launch2_t(const CUtensorMap& ta, const CUtensorMap& tb, const GemmPar
     OOB_CUDA_OK(cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
   }
   static bool attr_set = false;
-  auto kern = gemm_bf16x3_2cta_kernel<BN, A_MN, B_MN>;
+  auto kern = gemm_bf16x3_2cta_kernel<BN, A_MN, B_MN, BK>;
   if (!attr_set) {
     OOB_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
     attr_set = true;
   }
-  const int stage = gemm2_stage_bytes<BN>(p.nsplit);
+  const int stage = gemm2_stage_bytes<BN, BK>(p.nsplit);
   const int overhead = 1024 + 256;
   int stages = (max_smem - overhead) / stage;
-  if (stages > 8) stages = 8;
+  if (stages > 10) stages = 10;
   OOB_CHECK(stages >= 2, "2-CTA GEMM tile does not fit %d B of shared memory", max_smem);
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(2 * ((p.M + 2 * GEMM_BM - 1) / (2 * GEMM_BM)), (p.N + BN - 1) / BN);
@@ -141,7 +113,7 @@ static int launch2_t(const CUtensorMap& ta, const CUtensorMap& tb, const GemmPar
   return 0;
 }
 
-template <int BN, bool A_MN, bool B_MN, bool TWO_CTA>
+template <int BN, bool A_MN, bool B_MN, bool TWO_CTA, int BK>
 static int launchp_t(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, cudaStream_t stream) {
   static int max_smem = -1, num_sms = 0;
   if (max_smem < 0) {
@@ -151,15 +123,15 @@ static int launchp_t(const CUtensorMap& ta, const CUtensorMap& tb, const GemmPar
     OOB_CUDA_OK(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
   }
   static bool attr_set = false;
-  auto kern = gemm_bf16x3_persistent_kernel<BN, A_MN, B_MN, TWO_CTA>;
+  auto kern = gemm_bf16x3_persistent_kernel<BN, A_MN, B_MN, TWO_CTA, BK>;
   if (!attr_set) {
     OOB_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
     attr_set = true;
   }
-  const int stage = gemmp_stage_bytes<BN, TWO_CTA>(p.nsplit);
+  const int stage = gemmp_stage_bytes<BN, TWO_CTA, BK>(p.nsplit);
   const int overhead = 1024 + 256;
   int stages = (max_smem - overhead) / stage;
-  if (stages > 8) stages = 8;
+  if (stages > 10) stages = 10;
   OOB_CHECK(stages >= 2, "persistent GEMM tile does not fit %d B of shared memory", max_smem);
   const int tile_m = TWO_CTA ? 2 * GEMM_BM : GEMM_BM;
   const int tiles = ((p.M + tile_m - 1) / tile_m) * ((p.N + BN - 1) / BN);
@@ -194,50 +166,49 @@ int gemm_launch(const PlaneMat& A, int a_mn, const PlaneMat& B, int b_mn, const 
   OOB_CHECK(p.nsplit >= 1 && p.nsplit <= 3, "nsplit must be 1..3");
   OOB_CHECK(p.M > 0 && p.N > 0 && p.K > 0, "empty GEMM %d x %d x %d", p.M, p.N, p.K);
   constexpr int BN = 128;
+  // kernel selection (measured on B200, profiles/): 2-CTA pair tiles everywhere; persistent scheduling once a unit
+  // gets more than ~2 tiles; BK = 32 (SWIZZLE_64B, twice the ring depth) for the multi-plane modes.  Env vars
+  // override for experiments.
+  static const int env_2cta = [] { const char* e = getenv("OOB_GEMM_2CTA"); return e ? atoi(e) : -1; }();
+  static const int env_persist = [] { const char* e = getenv("OOB_GEMM_PERSIST"); return e ? atoi(e) : -1; }();
+  static const int env_bk = [] { const char* e = getenv("OOB_GEMM_BK"); return e ? atoi(e) : -1; }();
+  const int use_2cta = env_2cta >= 0 ? env_2cta : 1;
+  const long pair_tiles = (long)((p.M + 2 * GEMM_BM - 1) / (2 * GEMM_BM)) * ((p.N + BN - 1) / BN);
+  const int use_persist = !use_2cta ? 1 : (env_persist >= 0 ? env_persist : (pair_tiles > 2 * 74 ? 1 : 0));
+  const int bk = (env_bk == 32 || env_bk == 64) ? env_bk : 64;
   CUtensorMap ta, tb;
   int rc;
-  // K-major operand: stored [MN][K] -> box {64 k, tile rows, planes}; MN-major: stored [K][MN] -> box {64 mn, BK rows}
+  // K-major operand: stored [MN][K] -> box {bk k, tile rows, planes}; MN-major: stored [K][MN] -> box {bk mn, bk rows}
   if (!a_mn) {
     OOB_CHECK(A.rows >= p.M && A.cols >= p.K, "A (K-major) is %ld x %ld, need %d x %d", A.rows, A.cols, p.M, p.K);
-    rc = make_map(&ta, PlaneMat{A.base, (long)p.M, (long)p.K, A.ld, A.plane_stride, A.nplanes}, GEMM_BM, p.nsplit);
+    rc = make_map(&ta, PlaneMat{A.base, (long)p.M, (long)p.K, A.ld, A.plane_stride, A.nplanes}, GEMM_BM, p.nsplit, bk);
   } else {
     OOB_CHECK(A.rows >= p.K && A.cols >= p.M, "A (M-major) is %ld x %ld, need %d x %d", A.rows, A.cols, p.K, p.M);
-    rc = make_map(&ta, PlaneMat{A.base, (long)p.K, (long)p.M, A.ld, A.plane_stride, A.nplanes}, GEMM_BK, p.nsplit);
+    rc = make_map(&ta, PlaneMat{A.base, (long)p.K, (long)p.M, A.ld, A.plane_stride, A.nplanes}, bk, p.nsplit, bk);
   }
   if (rc) return rc;
-  static const int use_2cta = [] { const char* e = getenv("OOB_GEMM_2CTA"); return e ? atoi(e) : 0; }();
   if (!b_mn) {
     OOB_CHECK(B.rows >= p.N && B.cols >= p.K, "B (K-major) is %ld x %ld, need %d x %d", B.rows, B.cols, p.N, p.K);
     rc = make_map(&tb, PlaneMat{B.base, (long)p.N, (long)p.K, B.ld, B.plane_stride, B.nplanes}, use_2cta ? BN / 2 : BN,
-                  p.nsplit);
+                  p.nsplit, bk);
   } else {
     OOB_CHECK(B.rows >= p.K && B.cols >= p.N, "B (N-major) is %ld x %ld, need %d x %d", B.rows, B.cols, p.K, p.N);
-    rc = make_map(&tb, PlaneMat{B.base, (long)p.K, (long)p.N, B.ld, B.plane_stride, B.nplanes}, GEMM_BK, p.nsplit);
+    rc = make_map(&tb, PlaneMat{B.base, (long)p.K, (long)p.N, B.ld, B.plane_stride, B.nplanes}, bk, p.nsplit, bk);
   }
   if (rc) return rc;
-  static const int use_persist = [] { const char* e = getenv("OOB_GEMM_PERSIST"); return e ? atoi(e) : 0; }();
-  if (use_persist && use_2cta) {
-    if (!a_mn && !b_mn) return launchp_t<BN, false, false, true>(ta, tb, p, stream);
-    if (!a_mn && b_mn) return launchp_t<BN, false, true, true>(ta, tb, p, stream);
-    if (a_mn && !b_mn) return launchp_t<BN, true, false, true>(ta, tb, p, stream);
-    return launchp_t<BN, true, true, true>(ta, tb, p, stream);
-  }
+#define OOB_DISPATCH_MAJORS(FN, ...)                                                       \
+  do {                                                                                      \
+    if (!a_mn && !b_mn) return FN<BN, false, false, __VA_ARGS__>(ta, tb, p, stream);        \
+    if (!a_mn && b_mn) return FN<BN, false, true, __VA_ARGS__>(ta, tb, p, stream);          \
+    if (a_mn && !b_mn) return FN<BN, true, false, __VA_ARGS__>(ta, tb, p, stream);          \
+    return FN<BN, true, true, __VA_ARGS__>(ta, tb, p, stream);                              \
+  } while (0)
   if (use_persist) {
-    if (!a_mn && !b_mn) return launchp_t<BN, false, false, false>(ta, tb, p, stream);
-    if (!a_mn && b_mn) return launchp_t<BN, false, true, false>(ta, tb, p, stream);
-    if (a_mn && !b_mn) return launchp_t<BN, true, false, false>(ta, tb, p, stream);
-    return launchp_t<BN, true, true, false>(ta, tb, p, stream);
+    if (use_2cta) { if (bk == 64) OOB_DISPATCH_MAJORS(launchp_t, true, 64); else OOB_DISPATCH_MAJORS(launchp_t, true, 32); }
+    if (bk == 64) OOB_DISPATCH_MAJORS(launchp_t, false, 64); else OOB_DISPATCH_MAJORS(launchp_t, false, 32);
   }
-  if (use_2cta) {
-    if (!a_mn && !b_mn) return launch2_t<BN, false, false>(ta, tb, p, stream);
-    if (!a_mn && b_mn) return launch2_t<BN, false, true>(ta, tb, p, stream);
-    if (a_mn && !b_mn) return launch2_t<BN, true, false>(ta, tb, p, stream);
-    return launch2_t<BN, true, true>(ta, tb, p, stream);
-  }
-  if (!a_mn && !b_mn) return launch_t<BN, false, false>(ta, tb, p, stream);
-  if (!a_mn && b_mn) return launch_t<BN, false, true>(ta, tb, p, stream);
-  if (a_mn && !b_mn) return launch_t<BN, true, false>(ta, tb, p, stream);
-  return launch_t<BN, true, true>(ta, tb, p, stream);
+  if (bk == 64) OOB_DISPATCH_MAJORS(launch2_t, 64); else OOB_DISPATCH_MAJORS(launch2_t, 32);
+#undef OOB_DISPATCH_MAJORS
 }
 
 }  // namespace oob

@@ -52,13 +52,20 @@ struct GemmParams {
 };
 
 constexpr int GEMM_BM = 128;
-constexpr int GEMM_BK = 64;           // 64 bf16 = 128 B = one SWIZZLE_128B row
 constexpr int GEMM_THREADS = 192;
 
-template <int BN>
-__host__ __device__ constexpr int gemm_stage_bytes(int nsplit) {
-  return nsplit * (GEMM_BM + BN) * GEMM_BK * 2;
-}
+// K-block geometry.  One smem row holds BK contraction elements (K-major) or BK output elements (MN-major) and is
+// exactly one swizzle span: BK = 64 -> 128 B rows / SWIZZLE_128B, BK = 32 -> 64 B rows / SWIZZLE_64B (half-size
+// stages, twice as many of them: the 6-product parity mode needs the deeper ring to hide the TMA latency).
+template <int BK>
+struct KCfg {
+  static_assert(BK == 64 || BK == 32, "BK must be 64 (SWIZZLE_128B) or 32 (SWIZZLE_64B)");
+  static constexpr int ROWB = BK * 2;
+  static constexpr uint64_t SWZ = BK == 64 ? SWZ_128B : SWZ_64B;
+  static constexpr int SBO = 8 * ROWB;     // stride between 8-row groups
+  static constexpr int ATOM = BK;          // width (elements) of an MN-major atom = ROWB / 2
+  static constexpr int KSTEPS = BK / 16;   // MMAs (K = 16) per product per k-block
+};
 
 // product list per split level (plane index of A / B for product q), see issue_kblock:
 //   q:      0 1 2 3 4 5
@@ -73,27 +80,30 @@ __host__ __device__ constexpr int gemm_stage_bytes(int nsplit) {
 template <bool TWO_CTA>
 __device__ __forceinline__ void umma_any(uint32_t td, uint64_t da, uint64_t db, uint32_t idesc, uint32_t acc);
 
-template <int NS, int BROWS, bool A_MN, bool B_MN, bool TWO_CTA>
+template <int NS, int BROWS, bool A_MN, bool B_MN, bool TWO_CTA, int BK>
 __device__ __forceinline__ void issue_kblock(uint32_t sa, uint32_t sb, uint32_t t_main, uint32_t t_corr,
                                              uint32_t idesc, uint32_t& acc_main, uint32_t& acc_corr) {
-  constexpr uint32_t A_PLANE = (A_MN ? GEMM_BK : GEMM_BM) * 128;   // bytes between planes inside a stage
-  constexpr uint32_t B_PLANE = (B_MN ? GEMM_BK : BROWS) * 128;
-  constexpr uint32_t A_KSTEP = A_MN ? 2048 : 32;                   // bytes per 16 contraction elements
-  constexpr uint32_t B_KSTEP = B_MN ? 2048 : 32;
-  constexpr uint32_t A_LBO = A_MN ? NS * GEMM_BK * 128 : 0;        // MN-major: distance between 64-wide atoms
-  constexpr uint32_t B_LBO = B_MN ? NS * GEMM_BK * 128 : 0;
+  using C = KCfg<BK>;
+  // K-major : [plane][rows][ROWB]              , k-step = 32 B inside the row
+  // MN-major: [atom][plane][BK k-rows][ROWB]   , k-step = 16 rows, LBO = distance between atoms
+  constexpr uint32_t A_PLANE = (A_MN ? BK : GEMM_BM) * C::ROWB;
+  constexpr uint32_t B_PLANE = (B_MN ? BK : BROWS) * C::ROWB;
+  constexpr uint32_t A_KSTEP = A_MN ? 16 * C::ROWB : 32;
+  constexpr uint32_t B_KSTEP = B_MN ? 16 * C::ROWB : 32;
+  constexpr uint32_t A_LBO = A_MN ? NS * BK * C::ROWB : 0;
+  constexpr uint32_t B_LBO = B_MN ? NS * BK * C::ROWB : 0;
   constexpr int NPROD = NS == 1 ? 1 : (NS == 2 ? 3 : 6);
   constexpr int PA[6] = {0, 0, 1, 1, 0, 2};
   constexpr int PB[6] = {0, 1, 0, 1, 2, 0};
-  const uint64_t a_base = make_smem_desc(sa, A_LBO, 1024, SWZ_128B);
-  const uint64_t b_base = make_smem_desc(sb, B_LBO, 1024, SWZ_128B);
+  const uint64_t a_base = make_smem_desc(sa, A_LBO, C::SBO, C::SWZ);
+  const uint64_t b_base = make_smem_desc(sb, B_LBO, C::SBO, C::SWZ);
 #pragma unroll
-  for (int k = 0; k < GEMM_BK / 16; ++k) {   // leading product p0q0 -> "main"
+  for (int k = 0; k < C::KSTEPS; ++k) {   // leading product p0q0 -> "main"
     umma_any<TWO_CTA>(t_main, a_base + ((k * A_KSTEP) >> 4), b_base + ((k * B_KSTEP) >> 4), idesc, acc_main);
     acc_main = 1u;
   }
 #pragma unroll
-  for (int k = 0; k < GEMM_BK / 16; ++k) {   // corrections -> "corr"
+  for (int k = 0; k < C::KSTEPS; ++k) {   // corrections -> "corr"
 #pragma unroll
     for (int q = 1; q < NPROD; ++q) {
       umma_any<TWO_CTA>(t_corr, a_base + ((PA[q] * A_PLANE + k * A_KSTEP) >> 4),
@@ -194,163 +204,7 @@ __device__ __forceinline__ void epilogue_store32(float (&x)[32], const GemmEpilo
 //     TMEM region -- their truncation error is 2^-8 smaller still -- and are folded once at the end.
 // TMEM: main[2] + corr = 3 x BN columns.  (First version folded main+corr every 4 k-blocks: the extra TMEM reads
 // cost 35% of the GEMM's throughput -- profiles/README.md.)
-constexpr int GEMM_CHUNK_KB = 8;   // 8 x 64 = 512 contraction elements = 32 main MMAs per chunk
-
-template <int BN, bool A_MN, bool B_MN>
-__global__ void __launch_bounds__(GEMM_THREADS, 1)
-gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
-                   const GemmParams p, const int num_stages) {
-  static_assert(BN == 128, "TMEM budget: (2 main buffers + corr) x BN columns must be <= 512");
-  extern __shared__ __align__(1024) uint8_t smem_raw[];
-  // carve: [stage ring][barriers]
-  const int nsplit = p.nsplit;
-  const int a_bytes = nsplit * GEMM_BM * GEMM_BK * 2;
-  const int b_bytes = nsplit * BN * GEMM_BK * 2;
-  const int stage_bytes = a_bytes + b_bytes;
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + (size_t)num_stages * stage_bytes);
-  uint64_t* empty_bar = full_bar + num_stages;
-  uint64_t* tmem_full_bar = empty_bar + num_stages;   // [2]
-  uint64_t* tmem_empty_bar = tmem_full_bar + 2;        // [2]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
-
-  const int warp = threadIdx.x >> 5;
-  const int lane = threadIdx.x & 31;
-  const int m0 = blockIdx.y * GEMM_BM;
-  const int n0 = blockIdx.x * BN;
-  const int num_kb = (p.K + GEMM_BK - 1) / GEMM_BK;
-  const int chunk_kb = p.chunk_kb > 0 ? p.chunk_kb : GEMM_CHUNK_KB;
-  const int num_chunks = (num_kb + chunk_kb - 1) / chunk_kb;
-  constexpr uint32_t TMEM_COLS = 4 * BN;  // 512
-
-  if (warp == 0 && lane == 0) {
-    tma_prefetch_desc(&tma_a);
-    tma_prefetch_desc(&tma_b);
-    for (int s = 0; s < num_stages; ++s) {
-      mbar_init(&full_bar[s], 1);
-      mbar_init(&empty_bar[s], 1);
-    }
-    for (int b = 0; b < 2; ++b) {
-      mbar_init(&tmem_full_bar[b], 1);
-      mbar_init(&tmem_empty_bar[b], 4);  // one arrive per epilogue warp
-    }
-    mbar_fence_init();
-  }
-  if (warp == 1) tmem_alloc(tmem_slot, TMEM_COLS);
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
-
-  if (warp == 0) {
-    // ===================== TMA producer =====================
-    if (lane == 0) {
-      for (int kb = 0; kb < num_kb; ++kb) {
-        const int s = kb % num_stages;
-        if (kb >= num_stages) mbar_wait(&empty_bar[s], ((kb / num_stages) - 1) & 1);
-        uint8_t* sa = smem + (size_t)s * stage_bytes;
-        uint8_t* sb = sa + a_bytes;
-        mbar_arrive_expect_tx(&full_bar[s], stage_bytes);
-        const int k0 = kb * GEMM_BK;
-        if constexpr (!A_MN) {
-          tma_load_3d(sa, &tma_a, &full_bar[s], k0, m0, 0);  // box {64, BM, nsplit}
-        } else {
-#pragma unroll
-          for (int i = 0; i < GEMM_BM / 64; ++i)                // box {64 (M), BK rows, nsplit}
-            tma_load_3d(sa + (size_t)i * nsplit * GEMM_BK * 128, &tma_a, &full_bar[s], m0 + i * 64, k0, 0);
-        }
-        if constexpr (!B_MN) {
-          tma_load_3d(sb, &tma_b, &full_bar[s], k0, n0, 0);  // box {64, BN, nsplit}
-        } else {
-#pragma unroll
-          for (int i = 0; i < BN / 64; ++i)
-            tma_load_3d(sb + (size_t)i * nsplit * GEMM_BK * 128, &tma_b, &full_bar[s], n0 + i * 64, k0, 0);
-        }
-      }
-    }
-  } else if (warp == 1) {
-    // ===================== MMA issuer =====================
-    if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc_bf16(GEMM_BM, BN, A_MN ? 1 : 0, B_MN ? 1 : 0);
-      int kb = 0;
-      for (int c = 0; c < num_chunks; ++c) {
-        const int buf = c & 1;
-        if (c >= 2) {  // the fold of the chunk that used this buffer two chunks ago must be done
-          mbar_wait(&tmem_empty_bar[buf], ((c >> 1) - 1) & 1);
-          tc_fence_after();
-        }
-        const uint32_t t_main = tmem_base + (uint32_t)(buf * BN);
-        const uint32_t t_corr = tmem_base + (uint32_t)(2 * BN);
-        const int kb_end = min(kb + chunk_kb, num_kb);
-        uint32_t acc_main = 0u;                 // first main MMA of a chunk overwrites its buffer
-        uint32_t acc_corr = (c == 0) ? 0u : 1u; // corrections accumulate across the whole contraction
-        for (; kb < kb_end; ++kb) {
-          const int s = kb % num_stages;
-          mbar_wait(&full_bar[s], (kb / num_stages) & 1);
-          tc_fence_after();
-          const uint32_t sa = smem_u32(smem + (size_t)s * stage_bytes);
-          const uint32_t sb = sa + a_bytes;
-          if (nsplit == 3) issue_kblock<3, BN, A_MN, B_MN, false>(sa, sb, t_main, t_corr, idesc, acc_main, acc_corr);
-          else if (nsplit == 2) issue_kblock<2, BN, A_MN, B_MN, false>(sa, sb, t_main, t_corr, idesc, acc_main, acc_corr);
-          else issue_kblock<1, BN, A_MN, B_MN, false>(sa, sb, t_main, t_corr, idesc, acc_main, acc_corr);
-          umma_commit(&empty_bar[s]);  // frees the ring slot once these MMAs have read it
-        }
-        umma_commit(&tmem_full_bar[buf]);  // chunk accumulators complete
-      }
-    }
-  } else {
-    // ===================== epilogue (warps 2..5): promotion + fused output =====================
-    const int quarter = warp & 3;             // TMEM lane quarter this warp may access
-    const int row = m0 + quarter * 32 + lane;
-    const bool has_corr = nsplit > 1;
-    float racc[BN];
-#pragma unroll
-    for (int j = 0; j < BN; ++j) racc[j] = 0.f;
-    for (int c = 0; c < num_chunks; ++c) {
-      const int buf = c & 1;
-      mbar_wait(&tmem_full_bar[buf], (c >> 1) & 1);
-      tc_fence_after();
-      const uint32_t t_lane = tmem_base + ((uint32_t)(quarter * 32) << 16);
-      const bool last_chunk = (c == num_chunks - 1);
-#pragma unroll
-      for (int g = 0; g < BN / 32; ++g) {
-        uint32_t v[32];
-        tmem_ld_32x32(t_lane + (uint32_t)(buf * BN + g * 32), v);
-        tmem_ld_wait();
-#pragma unroll
-        for (int j = 0; j < 32; ++j) racc[g * 32 + j] += __uint_as_float(v[j]);
-        if (has_corr && last_chunk) {   // the last chunk's commit also covers every correction MMA
-          tmem_ld_32x32(t_lane + (uint32_t)(2 * BN + g * 32), v);
-          tmem_ld_wait();
-#pragma unroll
-          for (int j = 0; j < 32; ++j) racc[g * 32 + j] += __uint_as_float(v[j]);
-        }
-      }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&tmem_empty_bar[buf]);
-    }
-    if (row < p.M && !(p.debug & 1)) {
-#pragma unroll
-      for (int g = 0; g < BN / 32; ++g) {
-        const int col0 = n0 + g * 32;
-        if (col0 < p.N) {
-          float x[32];
-#pragma unroll
-          for (int j = 0; j < 32; ++j) x[j] = racc[g * 32 + j];
-          epilogue_store32(x, p.epi, row, col0, p.N);
-        }
-      }
-    }
-  }
-
-  tc_fence_before();
-  __syncthreads();
-  if (warp == 1) {
-    tc_fence_after();
-    tmem_dealloc(tmem_base, TMEM_COLS);
-  }
-}
+constexpr int GEMM_CHUNK_ELEMS = 512;   // contraction elements per promotion chunk = 32 main MMAs
 
 // Host side -----------------------------------------------------------------------------------------------------
 

@@ -73,22 +73,23 @@ __device__ __forceinline__ void umma_commit_2sm(uint64_t* bar) {
       : "memory");
 }
 
-template <int BN>
+template <int BN, int BK>
 __host__ __device__ constexpr int gemm2_stage_bytes(int nsplit) {
-  return nsplit * (GEMM_BM + BN / 2) * GEMM_BK * 2;   // per CTA
+  return nsplit * (GEMM_BM + BN / 2) * BK * 2;   // per CTA
 }
 
 // grid: x = 2 * ceil(M / 256) (cluster dims (2,1,1): the two CTAs of a pair are adjacent in x), y = ceil(N / BN)
-template <int BN, bool A_MN, bool B_MN>
+template <int BN, bool A_MN, bool B_MN, int BK>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_bf16x3_2cta_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
                         const GemmParams p, const int num_stages) {
   static_assert(BN == 128, "epilogue holds BN fp32 running sums per thread");
   constexpr int BNH = BN / 2;   // B rows staged by each CTA
+  using C = KCfg<BK>;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   const int nsplit = p.nsplit;
-  const int a_bytes = nsplit * GEMM_BM * GEMM_BK * 2;
-  const int b_bytes = nsplit * BNH * GEMM_BK * 2;
+  const int a_bytes = nsplit * GEMM_BM * BK * 2;
+  const int b_bytes = nsplit * BNH * BK * 2;
   const int stage_bytes = a_bytes + b_bytes;
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + (size_t)num_stages * stage_bytes);
@@ -104,8 +105,8 @@ gemm_bf16x3_2cta_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_
   const int m0 = (blockIdx.x >> 1) * (2 * GEMM_BM) + (int)rank * GEMM_BM;   // this CTA's 128 rows of the pair tile
   const int n0 = blockIdx.y * BN;                                           // pair tile columns
   const int nb0 = n0 + (int)rank * BNH;                                     // the half of B this CTA stages
-  const int num_kb = (p.K + GEMM_BK - 1) / GEMM_BK;
-  const int chunk_kb = p.chunk_kb > 0 ? p.chunk_kb : GEMM_CHUNK_KB;
+  const int num_kb = (p.K + BK - 1) / BK;
+  const int chunk_kb = p.chunk_kb > 0 ? p.chunk_kb : GEMM_CHUNK_ELEMS / BK;
   const int num_chunks = (num_kb + chunk_kb - 1) / chunk_kb;
   constexpr uint32_t TMEM_COLS = 512;   // main[2] + corr = 3 x BN columns, rounded to a power of two
 
@@ -138,20 +139,20 @@ gemm_bf16x3_2cta_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_
         uint8_t* sb = sa + a_bytes;
         if (leader) mbar_arrive_expect_tx(&full_bar[s], 2 * stage_bytes);
         const uint32_t bar = mapa_u32(smem_u32(&full_bar[s]), 0);
-        const int k0 = kb * GEMM_BK;
+        const int k0 = kb * BK;
         if constexpr (!A_MN) {
-          tma_load_3d_2sm(sa, &tma_a, bar, k0, m0, 0);  // box {64, 128, nsplit}
+          tma_load_3d_2sm(sa, &tma_a, bar, k0, m0, 0);  // box {BK, 128, nsplit}
         } else {
 #pragma unroll
-          for (int i = 0; i < GEMM_BM / 64; ++i)
-            tma_load_3d_2sm(sa + (size_t)i * nsplit * GEMM_BK * 128, &tma_a, bar, m0 + i * 64, k0, 0);
+          for (int i = 0; i < GEMM_BM / C::ATOM; ++i)
+            tma_load_3d_2sm(sa + (size_t)i * nsplit * BK * C::ROWB, &tma_a, bar, m0 + i * C::ATOM, k0, 0);
         }
         if constexpr (!B_MN) {
-          tma_load_3d_2sm(sb, &tma_b, bar, k0, nb0, 0);  // box {64, BN/2, nsplit}
+          tma_load_3d_2sm(sb, &tma_b, bar, k0, nb0, 0);  // box {BK, BN/2, nsplit}
         } else {
 #pragma unroll
-          for (int i = 0; i < BNH / 64; ++i)
-            tma_load_3d_2sm(sb + (size_t)i * nsplit * GEMM_BK * 128, &tma_b, bar, nb0 + i * 64, k0, 0);
+          for (int i = 0; i < BNH / C::ATOM; ++i)
+            tma_load_3d_2sm(sb + (size_t)i * nsplit * BK * C::ROWB, &tma_b, bar, nb0 + i * C::ATOM, k0, 0);
         }
       }
     }
@@ -177,9 +178,9 @@ gemm_bf16x3_2cta_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_
           tc_fence_after();
           const uint32_t sa = smem_u32(smem + (size_t)s * stage_bytes);
           const uint32_t sb = sa + a_bytes;
-          if (nsplit == 3) issue_kblock<3, BNH, A_MN, B_MN, true>(sa, sb, t_main, t_corr, idesc, acc_main, acc_corr);
-          else if (nsplit == 2) issue_kblock<2, BNH, A_MN, B_MN, true>(sa, sb, t_main, t_corr, idesc, acc_main, acc_corr);
-          else issue_kblock<1, BNH, A_MN, B_MN, true>(sa, sb, t_main, t_corr, idesc, acc_main, acc_corr);
+          if (nsplit == 3) issue_kblock<3, BNH, A_MN, B_MN, true, BK>(sa, sb, t_main, t_corr, idesc, acc_main, acc_corr);
+          else if (nsplit == 2) issue_kblock<2, BNH, A_MN, B_MN, true, BK>(sa, sb, t_main, t_corr, idesc, acc_main, acc_corr);
+          else issue_kblock<1, BNH, A_MN, B_MN, true, BK>(sa, sb, t_main, t_corr, idesc, acc_main, acc_corr);
           umma_commit_2sm(&empty_bar[s]);
         }
         umma_commit_2sm(&tmem_full_bar[buf]);

@@ -11,25 +11,26 @@
 
 namespace oob {
 
-template <int BN, bool TWO_CTA>
+template <int BN, bool TWO_CTA, int BK>
 __host__ __device__ constexpr int gemmp_stage_bytes(int nsplit) {
-  return nsplit * (GEMM_BM + (TWO_CTA ? BN / 2 : BN)) * GEMM_BK * 2;   // per CTA
+  return nsplit * (GEMM_BM + (TWO_CTA ? BN / 2 : BN)) * BK * 2;   // per CTA
 }
 
 // grid.x = number of CTAs (1-CTA) or 2 x number of pairs (2-CTA, cluster dims (2,1,1)); tiles are distributed
 // round-robin: unit u (CTA or pair) takes tiles u, u + units, u + 2*units, ...; tile t -> (t % tiles_m, t / tiles_m)
 // so that the units running concurrently share the same B panel (L2 reuse) and stream different A row blocks.
-template <int BN, bool A_MN, bool B_MN, bool TWO_CTA>
+template <int BN, bool A_MN, bool B_MN, bool TWO_CTA, int BK>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_bf16x3_persistent_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
                               const GemmParams p, const int num_stages) {
   static_assert(BN == 128, "epilogue holds BN fp32 running sums per thread; TMEM = 4 x BN columns");
   constexpr int BROWS = TWO_CTA ? BN / 2 : BN;        // B rows staged per CTA
   constexpr int TILE_M = TWO_CTA ? 2 * GEMM_BM : GEMM_BM;
+  using C = KCfg<BK>;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   const int nsplit = p.nsplit;
-  const int a_bytes = nsplit * GEMM_BM * GEMM_BK * 2;
-  const int b_bytes = nsplit * BROWS * GEMM_BK * 2;
+  const int a_bytes = nsplit * GEMM_BM * BK * 2;
+  const int b_bytes = nsplit * BROWS * BK * 2;
   const int stage_bytes = a_bytes + b_bytes;
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + (size_t)num_stages * stage_bytes);
@@ -48,8 +49,8 @@ gemm_bf16x3_persistent_kernel(const __grid_constant__ CUtensorMap tma_a, const _
   const int tiles_m = (p.M + TILE_M - 1) / TILE_M;
   const int tiles_n = (p.N + BN - 1) / BN;
   const int num_tiles = tiles_m * tiles_n;
-  const int num_kb = (p.K + GEMM_BK - 1) / GEMM_BK;
-  const int chunk_kb = p.chunk_kb > 0 ? p.chunk_kb : GEMM_CHUNK_KB;
+  const int num_kb = (p.K + BK - 1) / BK;
+  const int chunk_kb = p.chunk_kb > 0 ? p.chunk_kb : GEMM_CHUNK_ELEMS / BK;
   const int num_chunks = (num_kb + chunk_kb - 1) / chunk_kb;
   constexpr uint32_t TMEM_COLS = 512;
   constexpr uint32_t kEpiArrivals = TWO_CTA ? 8 : 4;
@@ -90,32 +91,32 @@ gemm_bf16x3_persistent_kernel(const __grid_constant__ CUtensorMap tma_a, const _
           if (g >= num_stages) mbar_wait(&empty_bar[s], ((g / num_stages) - 1) & 1);
           uint8_t* sa = smem + (size_t)s * stage_bytes;
           uint8_t* sb = sa + a_bytes;
-          const int k0 = kb * GEMM_BK;
+          const int k0 = kb * BK;
           if constexpr (TWO_CTA) {
             if (leader) mbar_arrive_expect_tx(&full_bar[s], 2 * stage_bytes);
             const uint32_t bar = mapa_u32(smem_u32(&full_bar[s]), 0);
             if constexpr (!A_MN) tma_load_3d_2sm(sa, &tma_a, bar, k0, m0, 0);
             else
 #pragma unroll
-              for (int i = 0; i < GEMM_BM / 64; ++i)
-                tma_load_3d_2sm(sa + (size_t)i * nsplit * GEMM_BK * 128, &tma_a, bar, m0 + i * 64, k0, 0);
+              for (int i = 0; i < GEMM_BM / C::ATOM; ++i)
+                tma_load_3d_2sm(sa + (size_t)i * nsplit * BK * C::ROWB, &tma_a, bar, m0 + i * C::ATOM, k0, 0);
             if constexpr (!B_MN) tma_load_3d_2sm(sb, &tma_b, bar, k0, nb0, 0);
             else
 #pragma unroll
-              for (int i = 0; i < BROWS / 64; ++i)
-                tma_load_3d_2sm(sb + (size_t)i * nsplit * GEMM_BK * 128, &tma_b, bar, nb0 + i * 64, k0, 0);
+              for (int i = 0; i < BROWS / C::ATOM; ++i)
+                tma_load_3d_2sm(sb + (size_t)i * nsplit * BK * C::ROWB, &tma_b, bar, nb0 + i * C::ATOM, k0, 0);
           } else {
             mbar_arrive_expect_tx(&full_bar[s], stage_bytes);
             if constexpr (!A_MN) tma_load_3d(sa, &tma_a, &full_bar[s], k0, m0, 0);
             else
 #pragma unroll
-              for (int i = 0; i < GEMM_BM / 64; ++i)
-                tma_load_3d(sa + (size_t)i * nsplit * GEMM_BK * 128, &tma_a, &full_bar[s], m0 + i * 64, k0, 0);
+              for (int i = 0; i < GEMM_BM / C::ATOM; ++i)
+                tma_load_3d(sa + (size_t)i * nsplit * BK * C::ROWB, &tma_a, &full_bar[s], m0 + i * C::ATOM, k0, 0);
             if constexpr (!B_MN) tma_load_3d(sb, &tma_b, &full_bar[s], k0, nb0, 0);
             else
 #pragma unroll
-              for (int i = 0; i < BROWS / 64; ++i)
-                tma_load_3d(sb + (size_t)i * nsplit * GEMM_BK * 128, &tma_b, &full_bar[s], nb0 + i * 64, k0, 0);
+              for (int i = 0; i < BROWS / C::ATOM; ++i)
+                tma_load_3d(sb + (size_t)i * nsplit * BK * C::ROWB, &tma_b, &full_bar[s], nb0 + i * C::ATOM, k0, 0);
           }
         }
       }
@@ -151,9 +152,9 @@ gemm_bf16x3_persistent_kernel(const __grid_constant__ CUtensorMap tma_a, const _
             tc_fence_after();
             const uint32_t sa = smem_u32(smem + (size_t)s * stage_bytes);
             const uint32_t sb = sa + a_bytes;
-            if (nsplit == 3) issue_kblock<3, BROWS, A_MN, B_MN, TWO_CTA>(sa, sb, t_main, t_corr, idesc, acc_main, acc_corr);
-            else if (nsplit == 2) issue_kblock<2, BROWS, A_MN, B_MN, TWO_CTA>(sa, sb, t_main, t_corr, idesc, acc_main, acc_corr);
-            else issue_kblock<1, BROWS, A_MN, B_MN, TWO_CTA>(sa, sb, t_main, t_corr, idesc, acc_main, acc_corr);
+            if (nsplit == 3) issue_kblock<3, BROWS, A_MN, B_MN, TWO_CTA, BK>(sa, sb, t_main, t_corr, idesc, acc_main, acc_corr);
+            else if (nsplit == 2) issue_kblock<2, BROWS, A_MN, B_MN, TWO_CTA, BK>(sa, sb, t_main, t_corr, idesc, acc_main, acc_corr);
+            else issue_kblock<1, BROWS, A_MN, B_MN, TWO_CTA, BK>(sa, sb, t_main, t_corr, idesc, acc_main, acc_corr);
             if constexpr (TWO_CTA) umma_commit_2sm(&empty_bar[s]);
             else umma_commit(&empty_bar[s]);
           }
