@@ -48,7 +48,7 @@ struct GemmParams {
   int nsplit;   // planes used from each operand (1..3)
   GemmEpilogue epi;
   int chunk_kb; // promotion chunk in k-blocks (0 = default GEMM_CHUNK_KB)
-  int debug;    // diagnostics only (tools/gemm_sweep.py): 1 = skip the output stores
+  int debug;    // diagnostics (tools/gemm_sweep.py, persistent kernel): 1 skip output stores, 2 skip TMA, 4 skip MMAs
 };
 
 constexpr int GEMM_BM = 128;

@@ -131,10 +131,11 @@ gemm_bf16x3_2cta_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_
 
   if (warp == 0) {
     // ===================== TMA producer (both CTAs) =====================
-    if (lane == 0) {
+    {
       for (int kb = 0; kb < num_kb; ++kb) {
         const int s = kb % num_stages;
         if (kb >= num_stages) mbar_wait(&empty_bar[s], ((kb / num_stages) - 1) & 1);
+        if (!elect_one()) continue;
         uint8_t* sa = smem + (size_t)s * stage_bytes;
         uint8_t* sb = sa + a_bytes;
         if (leader) mbar_arrive_expect_tx(&full_bar[s], 2 * stage_bytes);
@@ -158,7 +159,7 @@ gemm_bf16x3_2cta_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_
     }
   } else if (warp == 1) {
     // ===================== MMA issuer (leader CTA only) =====================
-    if (leader && lane == 0) {
+    if (leader) {   // convergent warp, one elected lane issues (see gemm_sm100_persistent.cuh)
       constexpr uint32_t idesc = make_idesc_bf16(2 * GEMM_BM, BN, A_MN ? 1 : 0, B_MN ? 1 : 0);
       int kb = 0;
       uint32_t acc_corr = 0u;
@@ -178,12 +179,16 @@ gemm_bf16x3_2cta_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_
           tc_fence_after();
           const uint32_t sa = smem_u32(smem + (size_t)s * stage_bytes);
           const uint32_t sb = sa + a_bytes;
-          if (nsplit == 3) issue_kblock<3, BNH, A_MN, B_MN, true, BK>(sa, sb, t_main, t_corr, idesc, acc_main, acc_corr);
-          else if (nsplit == 2) issue_kblock<2, BNH, A_MN, B_MN, true, BK>(sa, sb, t_main, t_corr, idesc, acc_main, acc_corr);
-          else issue_kblock<1, BNH, A_MN, B_MN, true, BK>(sa, sb, t_main, t_corr, idesc, acc_main, acc_corr);
-          umma_commit_2sm(&empty_bar[s]);
+          if (elect_one()) {
+            if (nsplit == 3) issue_kblock<3, BNH, A_MN, B_MN, true, BK>(sa, sb, t_main, t_corr, idesc, acc_main, acc_corr);
+            else if (nsplit == 2) issue_kblock<2, BNH, A_MN, B_MN, true, BK>(sa, sb, t_main, t_corr, idesc, acc_main, acc_corr);
+            else issue_kblock<1, BNH, A_MN, B_MN, true, BK>(sa, sb, t_main, t_corr, idesc, acc_main, acc_corr);
+            umma_commit_2sm(&empty_bar[s]);
+          }
+          __syncwarp();
         }
-        umma_commit_2sm(&tmem_full_bar[buf]);
+        if (elect_one()) umma_commit_2sm(&tmem_full_bar[buf]);
+        __syncwarp();
       }
     }
   } else {

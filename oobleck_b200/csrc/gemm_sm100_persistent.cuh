@@ -81,8 +81,8 @@ gemm_bf16x3_persistent_kernel(const __grid_constant__ CUtensorMap tma_a, const _
 
   if (warp == 0) {
     // ===================== TMA producer =====================
-    if (lane == 0) {
-      int g = 0;   // k-blocks issued so far (ring position)
+    {
+      int g = 0;   // k-blocks issued so far (ring position); whole warp loops, one elected lane issues
       for (int t = unit; t < num_tiles; t += num_units) {
         const int m0 = (t % tiles_m) * TILE_M + (int)rank * GEMM_BM;
         const int nb0 = (t / tiles_m) * BN + (int)rank * BROWS;
@@ -92,6 +92,11 @@ gemm_bf16x3_persistent_kernel(const __grid_constant__ CUtensorMap tma_a, const _
           uint8_t* sa = smem + (size_t)s * stage_bytes;
           uint8_t* sb = sa + a_bytes;
           const int k0 = kb * BK;
+          if (!elect_one()) continue;
+          if (p.debug & 2) {   // diagnostics: no loads, the consumer runs on whatever is in smem
+            if (leader) mbar_arrive(&full_bar[s]);
+            continue;
+          }
           if constexpr (TWO_CTA) {
             if (leader) mbar_arrive_expect_tx(&full_bar[s], 2 * stage_bytes);
             const uint32_t bar = mapa_u32(smem_u32(&full_bar[s]), 0);
@@ -123,7 +128,10 @@ gemm_bf16x3_persistent_kernel(const __grid_constant__ CUtensorMap tma_a, const _
     }
   } else if (warp == 1) {
     // ===================== MMA issuer (leader CTA) =====================
-    if (leader && lane == 0) {
+    // The whole warp walks the loop (convergent control flow) and ONE elected lane issues: with a divergent
+    // `if (lane == 0)` around it the compiler wraps every uniform-datapath instruction (UTCHMMA, UTCBAR) in an
+    // ELECT/PLOP3/BRA.U.ANY retry loop, ~40 clk of issue per 64-clk MMA.
+    if (leader) {
       constexpr uint32_t idesc = make_idesc_bf16(TILE_M, BN, A_MN ? 1 : 0, B_MN ? 1 : 0);
       int g = 0;    // k-blocks consumed so far
       int gc = 0;   // chunks issued so far (main buffer = gc & 1)
@@ -152,14 +160,21 @@ gemm_bf16x3_persistent_kernel(const __grid_constant__ CUtensorMap tma_a, const _
             tc_fence_after();
             const uint32_t sa = smem_u32(smem + (size_t)s * stage_bytes);
             const uint32_t sb = sa + a_bytes;
-            if (nsplit == 3) issue_kblock<3, BROWS, A_MN, B_MN, TWO_CTA, BK>(sa, sb, t_main, t_corr, idesc, acc_main, acc_corr);
-            else if (nsplit == 2) issue_kblock<2, BROWS, A_MN, B_MN, TWO_CTA, BK>(sa, sb, t_main, t_corr, idesc, acc_main, acc_corr);
-            else issue_kblock<1, BROWS, A_MN, B_MN, TWO_CTA, BK>(sa, sb, t_main, t_corr, idesc, acc_main, acc_corr);
-            if constexpr (TWO_CTA) umma_commit_2sm(&empty_bar[s]);
-            else umma_commit(&empty_bar[s]);
+            if (elect_one()) {
+              if (p.debug & 4) { /* diagnostics: no MMAs */ }
+              else if (nsplit == 3) issue_kblock<3, BROWS, A_MN, B_MN, TWO_CTA, BK>(sa, sb, t_main, t_corr, idesc, acc_main, acc_corr);
+              else if (nsplit == 2) issue_kblock<2, BROWS, A_MN, B_MN, TWO_CTA, BK>(sa, sb, t_main, t_corr, idesc, acc_main, acc_corr);
+              else issue_kblock<1, BROWS, A_MN, B_MN, TWO_CTA, BK>(sa, sb, t_main, t_corr, idesc, acc_main, acc_corr);
+              if constexpr (TWO_CTA) umma_commit_2sm(&empty_bar[s]);
+              else umma_commit(&empty_bar[s]);
+            }
+            __syncwarp();
           }
-          if constexpr (TWO_CTA) umma_commit_2sm(&tmem_full_bar[buf]);
-          else umma_commit(&tmem_full_bar[buf]);
+          if (elect_one()) {
+            if constexpr (TWO_CTA) umma_commit_2sm(&tmem_full_bar[buf]);
+            else umma_commit(&tmem_full_bar[buf]);
+          }
+          __syncwarp();
         }
       }
     }
