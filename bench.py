@@ -250,6 +250,11 @@ def run_ours(args, cfg):
     L.call("oob_gemm_timing_end", C.byref(g_ms), C.byref(g_fl), C.byref(g_n))
     ms_e2e, losses = timed(args.steps, False, True)
 
+    last_loss = losses[-1] if losses else None
+    if world > 1:   # the loss lives on the last stage; rank 0 prints
+        t = torch.tensor([last_loss if last_loss is not None else float("-inf")], device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        last_loss = float(t.item())
     tokens_per_step = gb * T
     value = tokens_per_step * args.steps / (ms / 1e3)
     e2e = tokens_per_step * args.steps / (ms_e2e / 1e3)
@@ -271,7 +276,7 @@ def run_ours(args, cfg):
         "clocks": clocks,
         "gpu_launches": int(launches),
         "e2e": {"value": e2e, "unit": "tokens/s", "h2d_bytes_per_step": 2 * 8 * gb * T,
-                "d2h_bytes_per_step": 4 if is_last else 0, "loss": losses[-1] if losses else None},
+                "d2h_bytes_per_step": 4, "loss": last_loss},
         "model_flops_fraction_of_bf16_peak": value * fpt / (world * peaks["bf16_tflops"] * 1e12),
         "roofline": {
             "bound": "tensor", "kernel": "gemm_bf16x3_kernel (tcgen05, all GEMM launches of the last timed step)",

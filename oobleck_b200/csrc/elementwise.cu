@@ -216,15 +216,25 @@ layernorm_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ x, 
   }
 }
 
-// out[c] += sum_p partials[p][c]   (deterministic order)
-__global__ void colreduce_finalize_kernel(const float* __restrict__ partials, int nparts, int ncols,
-                                          float* __restrict__ out0, float* __restrict__ out1, int split) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= ncols) return;
+// out[c] += sum_p partials[p][c]   (fixed summation order -> deterministic).  Block (32 columns x 8 partial lanes):
+// lane y sums partials y, y+8, ... for its column, then the 8 lanes are folded through shared memory.
+__global__ void __launch_bounds__(256)
+colreduce_finalize_kernel(const float* __restrict__ partials, int nparts, int ncols, float* __restrict__ out0,
+                          float* __restrict__ out1, int split) {
+  __shared__ float sh[8][33];
+  const int c = blockIdx.x * 32 + threadIdx.x;
   float s = 0.f;
-  for (int p = 0; p < nparts; ++p) s += partials[(size_t)p * ncols + c];
-  if (c < split) out0[c] += s;
-  else out1[c - split] += s;
+  if (c < ncols)
+    for (int p = threadIdx.y; p < nparts; p += 8) s += partials[(size_t)p * ncols + c];
+  sh[threadIdx.y][threadIdx.x] = s;
+  __syncthreads();
+  if (threadIdx.y == 0 && c < ncols) {
+    float t = sh[0][threadIdx.x];
+#pragma unroll
+    for (int k = 1; k < 8; ++k) t += sh[k][threadIdx.x];
+    if (c < split) out0[c] += t;
+    else out1[c - split] += t;
+  }
 }
 
 int layernorm_bwd(const float* dy, const float* x, const float* mean, const float* rstd, const float* gamma,
@@ -237,7 +247,7 @@ int layernorm_bwd(const float* dy, const float* x, const float* mean, const floa
                                             partials, rows, E);
   OOB_CUDA_OK(cudaGetLastError());
   count_launch();
-  colreduce_finalize_kernel<<<(2 * E + 255) / 256, 256, 0, s>>>(partials, grid, 2 * E, dgamma, dbeta, E);
+  colreduce_finalize_kernel<<<(2 * E + 31) / 32, dim3(32, 8), 0, s>>>(partials, grid, 2 * E, dgamma, dbeta, E);
   OOB_CUDA_OK(cudaGetLastError());
   count_launch();
   return 0;
@@ -280,7 +290,7 @@ int colsum_accumulate(const float* a, long lda, int rows, int cols, float* out, 
   colsum_partial_kernel<<<grid, block, 0, s>>>(a, lda, rows, cols, partials);
   OOB_CUDA_OK(cudaGetLastError());
   count_launch();
-  colreduce_finalize_kernel<<<(cols + 255) / 256, 256, 0, s>>>(partials, gy, cols, out, out, cols);
+  colreduce_finalize_kernel<<<(cols + 31) / 32, dim3(32, 8), 0, s>>>(partials, gy, cols, out, out, cols);
   OOB_CUDA_OK(cudaGetLastError());
   count_launch();
   return 0;

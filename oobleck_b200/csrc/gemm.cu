@@ -74,45 +74,6 @@ int gemm_timing_end(double* total_ms, double* total_flops, long* launches) {
   return 0;
 }
 
-template <int BN, bool A_MN, bool B_MN, int BK>
-static int launch2_t(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, cudaStream_t stream) {
-  static int max_smem = -1;
-  if (max_smem < 0) {
-    int dev = 0;
-    OOB_CUDA_OK(cudaGetDevice(&dev));
-    OOB_CUDA_OK(cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
-  }
-  static bool attr_set = false;
-  auto kern = gemm_bf16x3_2cta_kernel<BN, A_MN, B_MN, BK>;
-  if (!attr_set) {
-    OOB_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
-    attr_set = true;
-  }
-  const int stage = gemm2_stage_bytes<BN, BK>(p.nsplit);
-  const int overhead = 1024 + 256;
-  int stages = (max_smem - overhead) / stage;
-  if (stages > 10) stages = 10;
-  OOB_CHECK(stages >= 2, "2-CTA GEMM tile does not fit %d B of shared memory", max_smem);
-  cudaLaunchConfig_t cfg{};
-  cfg.gridDim = dim3(2 * ((p.M + 2 * GEMM_BM - 1) / (2 * GEMM_BM)), (p.N + BN - 1) / BN);
-  cfg.blockDim = dim3(GEMM_THREADS);
-  cfg.dynamicSmemBytes = (size_t)stages * stage + overhead;
-  cfg.stream = stream;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeClusterDimension;
-  attr[0].val.clusterDim.x = 2;
-  attr[0].val.clusterDim.y = 1;
-  attr[0].val.clusterDim.z = 1;
-  cfg.attrs = attr;
-  cfg.numAttrs = 1;
-  TimedLaunch tl{};
-  if (g_timing) { tl.a = get_event(); tl.b = get_event(); tl.flops = 2.0 * p.M * p.N * p.K; cudaEventRecord(tl.a, stream); }
-  OOB_CUDA_OK(cudaLaunchKernelEx(&cfg, kern, ta, tb, p, stages));
-  if (g_timing) { cudaEventRecord(tl.b, stream); g_timed.push_back(tl); }
-  count_launch();
-  return 0;
-}
-
 template <int BN, bool A_MN, bool B_MN, bool TWO_CTA, int BK>
 static int launchp_t(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, cudaStream_t stream) {
   static int max_smem = -1, num_sms = 0;
@@ -166,15 +127,11 @@ int gemm_launch(const PlaneMat& A, int a_mn, const PlaneMat& B, int b_mn, const 
   OOB_CHECK(p.nsplit >= 1 && p.nsplit <= 3, "nsplit must be 1..3");
   OOB_CHECK(p.M > 0 && p.N > 0 && p.K > 0, "empty GEMM %d x %d x %d", p.M, p.N, p.K);
   constexpr int BN = 128;
-  // kernel selection (measured on B200, profiles/): 2-CTA pair tiles everywhere; persistent scheduling once a unit
-  // gets more than ~2 tiles; BK = 32 (SWIZZLE_64B, twice the ring depth) for the multi-plane modes.  Env vars
-  // override for experiments.
+  // kernel selection (measured on B200, profiles/r01_gemm_sweep*.log): persistent 2-CTA pair tiles with BK = 64 win on
+  // every GPT-2 shape (1-CTA: -15 %, BK = 32 / SWIZZLE_64B: -12 %).  Env vars select the variants for experiments.
   static const int env_2cta = [] { const char* e = getenv("OOB_GEMM_2CTA"); return e ? atoi(e) : -1; }();
-  static const int env_persist = [] { const char* e = getenv("OOB_GEMM_PERSIST"); return e ? atoi(e) : -1; }();
   static const int env_bk = [] { const char* e = getenv("OOB_GEMM_BK"); return e ? atoi(e) : -1; }();
   const int use_2cta = env_2cta >= 0 ? env_2cta : 1;
-  const long pair_tiles = (long)((p.M + 2 * GEMM_BM - 1) / (2 * GEMM_BM)) * ((p.N + BN - 1) / BN);
-  const int use_persist = !use_2cta ? 1 : (env_persist >= 0 ? env_persist : (pair_tiles > 2 * 74 ? 1 : 0));
   const int bk = (env_bk == 32 || env_bk == 64) ? env_bk : 64;
   CUtensorMap ta, tb;
   int rc;
@@ -203,11 +160,8 @@ int gemm_launch(const PlaneMat& A, int a_mn, const PlaneMat& B, int b_mn, const 
     if (a_mn && !b_mn) return FN<BN, true, false, __VA_ARGS__>(ta, tb, p, stream);          \
     return FN<BN, true, true, __VA_ARGS__>(ta, tb, p, stream);                              \
   } while (0)
-  if (use_persist) {
-    if (use_2cta) { if (bk == 64) OOB_DISPATCH_MAJORS(launchp_t, true, 64); else OOB_DISPATCH_MAJORS(launchp_t, true, 32); }
-    if (bk == 64) OOB_DISPATCH_MAJORS(launchp_t, false, 64); else OOB_DISPATCH_MAJORS(launchp_t, false, 32);
-  }
-  if (bk == 64) OOB_DISPATCH_MAJORS(launch2_t, 64); else OOB_DISPATCH_MAJORS(launch2_t, 32);
+  if (use_2cta) { if (bk == 64) OOB_DISPATCH_MAJORS(launchp_t, true, 64); else OOB_DISPATCH_MAJORS(launchp_t, true, 32); }
+  if (bk == 64) OOB_DISPATCH_MAJORS(launchp_t, false, 64); else OOB_DISPATCH_MAJORS(launchp_t, false, 32);
 #undef OOB_DISPATCH_MAJORS
 }
 
