@@ -285,7 +285,11 @@ def run_ours(args, cfg):
             "peak_source": peaks["source"] + " (cuBLAS bf16, sustained)",
             "tensor_products_per_algorithmic_flop": nprod,
             "executed_tensor_tflops": gemm_tflops * nprod if gemm_tflops else None,
-            "launches_timed": int(g_n.value), "traffic": None,
+            "launches_timed": int(g_n.value),
+            # dram__bytes_read.sum + dram__bytes_write.sum of ONE launch (forward FC GEMM 2048x6400x1600, nsplit 3) from
+            # profiles/r01_ncu_gemm_v3.txt; algorithmic bytes of that launch: 133 MB (3 planes of A and B + fp32 D)
+            "traffic": 107.3e6 if args.model == "gpt2-xl" and args.nsplit == 3 else None,
+            "traffic_note": "bytes/launch, ncu --set full, forward-FC shape; `achieved` aggregates all GEMM shapes",
         },
     }
     if world == 1:

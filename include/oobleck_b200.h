@@ -72,12 +72,15 @@ int oob_layernorm_bwd(const float* dy, const float* x, const float* mean, const 
 /* out[n] += sum_m a[m,n]  (bias gradients) */
 int oob_colsum_accumulate(const float* a, long lda, int rows, int cols, float* out, float* partials, void* stream);
 
-/* ---- attention (HF GPT2Attention eager: causal softmax(QK^T/sqrt(d))V, no dropout) ----------------------- */
-int oob_attention_fwd(const float* qkv, float* out, void* out_planes, long plane_stride, int nplanes, float* lse,
-                      int batch, int seq, int n_head, int head_dim, void* stream);
-int oob_attention_bwd(const float* qkv, const float* out, const float* dout, const float* lse, float* delta,
-                      float* dqkv, void* dqkv_planes, long plane_stride, int nplanes, int batch, int seq, int n_head,
-                      int head_dim, void* stream);
+/* ---- attention (HF GPT2Attention eager: causal softmax(QK^T/sqrt(d))V, no dropout) -----------------------
+ * q|k|v and dO are consumed as split planes ([3][B*T][3E] / [3][B*T][E]: the QKV GEMM and the proj dgrad GEMM write
+ * them in their epilogues); out/dout fp32 are only read for delta = rowsum(dO * O). */
+int oob_attention_fwd(const void* qkv_planes, long qkv_plane_stride, float* out, void* out_planes, long plane_stride,
+                      int nplanes, float* lse, int batch, int seq, int n_head, int head_dim, void* stream);
+int oob_attention_bwd(const void* qkv_planes, long qkv_plane_stride, const float* out, const float* dout,
+                      const void* dout_planes, long dout_plane_stride, const float* lse, float* delta, float* dqkv,
+                      void* dqkv_planes, long plane_stride, int nplanes, int batch, int seq, int n_head, int head_dim,
+                      void* stream);
 
 /* ---- fx layer 0 (wte[ids] + wpe[pos]) and its backward --------------------------------------------------- */
 int oob_embedding_fwd(const long long* ids, const float* wte, const float* wpe, float* hidden, int rows, int seq,
@@ -120,7 +123,7 @@ typedef struct oob_layer_params {
 
 typedef struct oob_block_ctx {      /* saved activations of one micro-batch through one GPT2Block */
   void* ln1_planes;  float* ln1_mean; float* ln1_rstd;   /* [3][M][E], [M], [M] */
-  float* qkv;                                            /* [M,3E] */
+  void* qkv_planes;                                      /* [3][M][3E] q|k|v split planes */
   float* att; void* att_planes; float* lse;              /* [M,E], [3][M][E], [B,H,T] */
   float* x2;                                             /* [M,E] hidden after the attention residual */
   void* ln2_planes;  float* ln2_mean; float* ln2_rstd;
@@ -131,7 +134,7 @@ typedef struct oob_bwd_scratch {    /* per-stage backward temporaries, reused by
   float* dfc; void* dfc_planes;     /* [M,4E], [3][M][4E] */
   float* dln;                       /* [M,E] */
   float* dx2; void* dx2_planes;     /* [M,E], [3][M][E] */
-  float* datt;                      /* [M,E] */
+  float* datt; void* datt_planes;   /* [M,E], [3][M][E]  d(attention output) */
   float* delta;                     /* [B*H*T] */
   float* dqkv; void* dqkv_planes;   /* [M,3E], [3][M][3E] */
   float* partials;                  /* max(oob_ln_bwd_partials_floats(E), oob_colsum_partials_floats(4E)) floats */

@@ -2,143 +2,175 @@
 // softmax(where(causal, QK^T/sqrt(d), finfo.min)) V, fp32), flash-style: the T x T score matrix never
 // reaches HBM (the reference materialises mb*H*T^2 fp32 = 210 MB per GPT-2-XL block).
 //
-// Tensor-core path: warp-level mma.sync.m16n8k8 TF32 with the 3-term split (hi*hi + hi*lo + lo*hi) done in
-// registers, which reproduces fp32 products to ~2^-21 -- the fp32-parity counterpart of the split-bf16 tcgen05
-// GEMMs.  64 x 64 tiles, head_dim == 64, 4 warps x 16 rows.  Tiles are staged in shared memory with a row
-// stride of 68 floats, which makes both fragment access patterns below bank-conflict free.
+// Operands arrive as the same split-bf16 planes the GEMMs use (q|k|v planes straight from the QKV GEMM epilogue, dO
+// planes from the proj dgrad epilogue), so tiles are cp.async'ed into shared memory without any ALU work and fed to
+// mma.sync.m16n8k16 bf16 through ldmatrix.  Each fp32 product is rebuilt from the six plane products
+// (p0q0 p0q1 p1q0 p1q1 p0q2 p2q0) like in the GEMM; probabilities / dS are split into planes in registers.
+// (First version: TF32x3 with per-fragment splitting of fp32 smem tiles -- 3.3x more issue slots per MMA; see
+// profiles/README.md.)  64 x 64 tiles, head_dim 64, 4 warps x 16 rows; smem tiles are [plane][64][64] bf16 with the
+// 16-byte chunks of a row XOR-swizzled by (row & 7), which makes every ldmatrix phase conflict-free.
+// The HMMA accumulator truncates, so each tile product goes to a fresh accumulator that is folded with RN adds.
 //
 //   forward        grid (T/64, H, B): S = QK^T, online softmax, O = PV; writes O (fp32 + split planes) and LSE
 //   backward dK,dV grid (T/64 kv tiles, H, B): S^T = KQ^T, dV += P^T dO, dP^T = V dO^T, dK += dS^T Q
 //   backward dQ    grid (T/64 q tiles, H, B):  S = QK^T, dP = dO V^T, dQ += dS K
+#include <cuda_bf16.h>
+
 #include "kernels.h"
 
 namespace oob {
 
-constexpr int AT = 64;    // tile (queries or keys)
-constexpr int AD = 64;    // head dim
-constexpr int ALD = 68;   // smem row stride (floats)
+constexpr int AT = 64;                     // tile (queries or keys)
+constexpr int AD = 64;                     // head dim
+constexpr int APLANE = AT * AD * 2;        // bytes of one plane of a tile (8 KB)
+constexpr int ATILE = 3 * APLANE;          // bytes of a 3-plane tile (24 KB)
 
-__device__ __forceinline__ void split_tf32(float x, uint32_t& hi, uint32_t& lo) {
-  hi = __float_as_uint(x) & 0xffffe000u;
-  lo = __float_as_uint(x - __uint_as_float(hi)) & 0xffffe000u;
+__device__ __forceinline__ uint32_t tile_off(int plane, int row, int col) {  // col: element index, multiple of 8
+  return (uint32_t)(plane * APLANE + row * 128 + ((((col >> 3) ^ row) & 7) << 4));
 }
-__device__ __forceinline__ void mma_tf32(float (&c)[4], const uint32_t (&a)[4], const uint32_t (&b)[2]) {
+__device__ __forceinline__ void cp_async16(uint32_t saddr, const void* g) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(saddr), "l"(g) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() {
+  asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
+}
+// tile rows [row0, row0+64) x 64 columns of every plane: global planes layout [3][rows][ld] (plane stride ps elements)
+__device__ __forceinline__ void load_tile_async(uint32_t sbase, const bf16* g, long ld, long ps, int valid_rows) {
+  for (int i = threadIdx.x; i < 3 * AT * 8; i += blockDim.x) {
+    const int plane = i >> 9, r = (i >> 3) & 63, c = i & 7;
+    const uint32_t dst = sbase + tile_off(plane, r, c * 8);
+    if (r < valid_rows) cp_async16(dst, g + (long)plane * ps + (long)r * ld + c * 8);
+    else asm volatile("st.shared.v4.u32 [%0], {%1, %1, %1, %1};" ::"r"(dst), "r"(0u) : "memory");
+  }
+}
+
+__device__ __forceinline__ void ldsm_x4(uint32_t addr, uint32_t (&r)[4]) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr));
+}
+__device__ __forceinline__ void ldsm_x4_trans(uint32_t addr, uint32_t (&r)[4]) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr));
+}
+__device__ __forceinline__ void mma_bf16(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
   asm volatile(
-      "mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+      "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
       : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
-      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }
-// c += a * b to fp32 accuracy: lo*hi + hi*lo first, hi*hi last
-__device__ __forceinline__ void mma3(float (&c)[4], const uint32_t (&ah)[4], const uint32_t (&al)[4],
-                                     const uint32_t (&bh)[2], const uint32_t (&bl)[2]) {
-  mma_tf32(c, al, bh);
-  mma_tf32(c, ah, bl);
-  mma_tf32(c, ah, bh);
-}
-
-// A fragment (16 x 8) of a row-major smem tile: rows r0.., columns k0..
-__device__ __forceinline__ void load_a_smem(const float* tile, int r0, int k0, int g, int t, uint32_t (&ah)[4],
-                                            uint32_t (&al)[4]) {
-  split_tf32(tile[(r0 + g) * ALD + k0 + t], ah[0], al[0]);
-  split_tf32(tile[(r0 + g + 8) * ALD + k0 + t], ah[1], al[1]);
-  split_tf32(tile[(r0 + g) * ALD + k0 + t + 4], ah[2], al[2]);
-  split_tf32(tile[(r0 + g + 8) * ALD + k0 + t + 4], ah[3], al[3]);
-}
-// A fragment from an accumulator n-tile (C layout -> A layout with the contraction index permuted:
-// fragment column t <-> C column 2t, column t+4 <-> C column 2t+1; the B side uses the same permutation).
-__device__ __forceinline__ void load_a_acc(const float (&c)[4], uint32_t (&ah)[4], uint32_t (&al)[4]) {
-  split_tf32(c[0], ah[0], al[0]);
-  split_tf32(c[2], ah[1], al[1]);
-  split_tf32(c[1], ah[2], al[2]);
-  split_tf32(c[3], ah[3], al[3]);
-}
-// B fragment (8 x 8) where B[k][n] = tile[n0+n][k0+k]  ("transposed" operand, e.g. K in QK^T)
-__device__ __forceinline__ void load_b_nk(const float* tile, int n0, int k0, int g, int t, uint32_t (&bh)[2],
-                                          uint32_t (&bl)[2]) {
-  split_tf32(tile[(n0 + g) * ALD + k0 + t], bh[0], bl[0]);
-  split_tf32(tile[(n0 + g) * ALD + k0 + t + 4], bh[1], bl[1]);
-}
-// B fragment where B[k][n] = tile[k0+perm(k)][n0+n] with the permutation matching load_a_acc
-__device__ __forceinline__ void load_b_kn_perm(const float* tile, int k0, int n0, int g, int t, uint32_t (&bh)[2],
-                                               uint32_t (&bl)[2]) {
-  split_tf32(tile[(k0 + 2 * t) * ALD + n0 + g], bh[0], bl[0]);
-  split_tf32(tile[(k0 + 2 * t + 1) * ALD + n0 + g], bh[1], bl[1]);
+// c += a*b rebuilt from the six plane products, smallest first.  b[p] holds the fragments of two adjacent n-tiles:
+// {b0, b1 of tile 2jp, b0, b1 of tile 2jp+1}; jj selects the tile.
+__device__ __forceinline__ void mma6(float (&c)[4], const uint32_t (&a)[3][4], const uint32_t (&b)[3][4], int jj) {
+  mma_bf16(c, a[0], b[2][2 * jj], b[2][2 * jj + 1]);
+  mma_bf16(c, a[2], b[0][2 * jj], b[0][2 * jj + 1]);
+  mma_bf16(c, a[1], b[1][2 * jj], b[1][2 * jj + 1]);
+  mma_bf16(c, a[0], b[1][2 * jj], b[1][2 * jj + 1]);
+  mma_bf16(c, a[1], b[0][2 * jj], b[0][2 * jj + 1]);
+  mma_bf16(c, a[0], b[0][2 * jj], b[0][2 * jj + 1]);
 }
 
-// acc[16 x 64] (+)= A_tile[r0..r0+16, 0..64] * B^T where B rows are the tile's rows  (C = A . tile^T)
-__device__ __forceinline__ void mm_a_smem_b_nk(float (&acc)[8][4], const float* a_tile, int r0, const float* b_tile,
-                                               int g, int t) {
+// two fp32 values -> one packed bf16x2 per plane (low half = x)
+__device__ __forceinline__ void split_pack(float x, float y, uint32_t& p0, uint32_t& p1, uint32_t& p2) {
+  __nv_bfloat162 h0 = __floats2bfloat162_rn(x, y);
+  float2 f = __bfloat1622float2(h0);
+  float rx = x - f.x, ry = y - f.y;
+  __nv_bfloat162 h1 = __floats2bfloat162_rn(rx, ry);
+  f = __bfloat1622float2(h1);
+  rx -= f.x; ry -= f.y;
+  __nv_bfloat162 h2 = __floats2bfloat162_rn(rx, ry);
+  p0 = *reinterpret_cast<uint32_t*>(&h0);
+  p1 = *reinterpret_cast<uint32_t*>(&h1);
+  p2 = *reinterpret_cast<uint32_t*>(&h2);
+}
+
+// acc[16 x 64] += A[r0..r0+16, 0..64] . B^T   with A = rows of smem tile `sa`, B[k][n] = tile_b[n][k]
+__device__ __forceinline__ void mm_smem_nk(float (&acc)[8][4], uint32_t sa, int r0, uint32_t sb, int lane) {
+  // ldmatrix.x4 address lanes: A -> {rows 0-7 | 8-15} x {k 0-7 | 8-15};  B -> {n 0-7: k 0-7, k 8-15 | n 8-15: ...}
+  const int a_row = r0 + (lane & 15), a_col = (lane >> 4) * 8;
+  const int b_row = (lane & 7) + (lane >> 4) * 8, b_col = ((lane >> 3) & 1) * 8;
 #pragma unroll
-  for (int ks = 0; ks < 8; ++ks) {
-    uint32_t ah[4], al[4];
-    load_a_smem(a_tile, r0, ks * 8, g, t, ah, al);
+  for (int kk = 0; kk < 4; ++kk) {
+    uint32_t a[3][4];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      uint32_t bh[2], bl[2];
-      load_b_nk(b_tile, j * 8, ks * 8, g, t, bh, bl);
-      mma3(acc[j], ah, al, bh, bl);
+    for (int p = 0; p < 3; ++p) ldsm_x4(sa + tile_off(p, a_row, kk * 16 + a_col), a[p]);
+#pragma unroll
+    for (int jp = 0; jp < 4; ++jp) {
+      uint32_t b[3][4];
+#pragma unroll
+      for (int p = 0; p < 3; ++p) ldsm_x4(sb + tile_off(p, jp * 16 + b_row, kk * 16 + b_col), b[p]);
+      mma6(acc[2 * jp], a, b, 0);
+      mma6(acc[2 * jp + 1], a, b, 1);
     }
   }
 }
-// acc[16 x 64] += P[16 x 64] * tile[64 x 64], P given in accumulator layout
-__device__ __forceinline__ void mm_a_acc_b_kn(float (&acc)[8][4], const float (&p)[8][4], const float* b_tile, int g,
-                                              int t) {
+// acc[16 x 64] += P[16 x 64] . B   with P in accumulator layout (fp32), B[k][n] = tile_b[k][n]
+__device__ __forceinline__ void mm_regs_kn(float (&acc)[8][4], const float (&pm)[8][4], uint32_t sb, int lane) {
+  // transposed ldmatrix.x4: {k 0-7 | 8-15} x {n 0-7 | 8-15}
+  const int b_row = lane & 15, b_col = (lane >> 4) * 8;
 #pragma unroll
-  for (int ks = 0; ks < 8; ++ks) {
-    uint32_t ah[4], al[4];
-    load_a_acc(p[ks], ah, al);
+  for (int kk = 0; kk < 4; ++kk) {
+    uint32_t a[3][4];   // C tiles 2kk, 2kk+1 -> A fragment (rows g / g+8, k 2t.. / 8+2t..)
+    split_pack(pm[2 * kk][0], pm[2 * kk][1], a[0][0], a[1][0], a[2][0]);
+    split_pack(pm[2 * kk][2], pm[2 * kk][3], a[0][1], a[1][1], a[2][1]);
+    split_pack(pm[2 * kk + 1][0], pm[2 * kk + 1][1], a[0][2], a[1][2], a[2][2]);
+    split_pack(pm[2 * kk + 1][2], pm[2 * kk + 1][3], a[0][3], a[1][3], a[2][3]);
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      uint32_t bh[2], bl[2];
-      load_b_kn_perm(b_tile, ks * 8, j * 8, g, t, bh, bl);
-      mma3(acc[j], ah, al, bh, bl);
+    for (int jp = 0; jp < 4; ++jp) {
+      uint32_t b[3][4];
+#pragma unroll
+      for (int p = 0; p < 3; ++p) ldsm_x4_trans(sb + tile_off(p, kk * 16 + b_row, jp * 16 + b_col), b[p]);
+      mma6(acc[2 * jp], a, b, 0);
+      mma6(acc[2 * jp + 1], a, b, 1);
     }
   }
 }
 
-// cooperative load of a [64 x 64] fp32 tile (row stride ld_g in global) into smem, rows >= valid zero-filled
-__device__ __forceinline__ void load_tile(float* dst, const float* src, long ld_g, int valid_rows) {
-  for (int i = threadIdx.x; i < AT * (AD / 4); i += blockDim.x) {
-    const int r = i / (AD / 4), c = (i % (AD / 4)) * 4;
-    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (r < valid_rows) v = ldg_f4(src + (long)r * ld_g + c);
-    *reinterpret_cast<float4*>(dst + r * ALD + c) = v;
+__device__ __forceinline__ void zero_acc(float (&a)[8][4]) {
+#pragma unroll
+  for (int j = 0; j < 8; ++j) a[j][0] = a[j][1] = a[j][2] = a[j][3] = 0.f;
+}
+__device__ __forceinline__ void store_pair(float* f32, bf16* planes, long plane_stride, int nplanes, long off, float a,
+                                           float c) {
+  if (f32) *reinterpret_cast<float2*>(f32 + off) = make_float2(a, c);
+  if (planes) {
+    uint32_t p0, p1, p2;
+    split_pack(a, c, p0, p1, p2);
+    *reinterpret_cast<uint32_t*>(planes + off) = p0;
+    if (nplanes > 1) *reinterpret_cast<uint32_t*>(planes + plane_stride + off) = p1;
+    if (nplanes > 2) *reinterpret_cast<uint32_t*>(planes + 2 * plane_stride + off) = p2;
   }
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(128)
-attention_fwd_kernel(const float* __restrict__ qkv, float* __restrict__ out, bf16* __restrict__ planes,
+__global__ void __launch_bounds__(128, 3)
+attention_fwd_kernel(const bf16* __restrict__ qkv, long qkv_ps, float* __restrict__ out, bf16* __restrict__ planes,
                      long plane_stride, int nplanes, float* __restrict__ lse, int T, int H, float scale) {
-  extern __shared__ float sm[];
-  float* sQ = sm;                 // [64][68]
-  float* sK = sQ + AT * ALD;
-  float* sV = sK + AT * ALD;
+  extern __shared__ __align__(1024) uint8_t sm_raw[];
+  const uint32_t sQ = (smem_u32(sm_raw) + 1023u) & ~1023u, sK = sQ + ATILE, sV = sK + ATILE;
   const int E = H * AD;
+  const long ld = 3L * E;
   const int qt = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
   const int q0 = qt * AT;
-  const float* base = qkv + (long)b * T * 3 * E + h * AD;
-  load_tile(sQ, base + (long)q0 * 3 * E, 3 * E, min(AT, T - q0));
+  const bf16* base = qkv + (long)b * T * ld + h * AD;
+  load_tile_async(sQ, base + (long)q0 * ld, ld, qkv_ps, min(AT, T - q0));
 
   float o[8][4];
-#pragma unroll
-  for (int j = 0; j < 8; ++j) o[j][0] = o[j][1] = o[j][2] = o[j][3] = 0.f;
+  zero_acc(o);
   float mrow[2] = {-INFINITY, -INFINITY}, lrow[2] = {0.f, 0.f};
   const int r0 = warp * 16;
   const int qi0 = q0 + r0 + g, qi1 = qi0 + 8;
 
   for (int kt = 0; kt <= qt; ++kt) {
     const int k0 = kt * AT;
-    __syncthreads();  // previous tile fully consumed (also orders the sQ fill on the first trip)
-    load_tile(sK, base + E + (long)k0 * 3 * E, 3 * E, min(AT, T - k0));
-    load_tile(sV, base + 2 * E + (long)k0 * 3 * E, 3 * E, min(AT, T - k0));
+    __syncthreads();  // previous tile fully consumed
+    load_tile_async(sK, base + E + (long)k0 * ld, ld, qkv_ps, min(AT, T - k0));
+    load_tile_async(sV, base + 2 * E + (long)k0 * ld, ld, qkv_ps, min(AT, T - k0));
+    cp_async_wait_all();
     __syncthreads();
     float s[8][4];
-#pragma unroll
-    for (int j = 0; j < 8; ++j) s[j][0] = s[j][1] = s[j][2] = s[j][3] = 0.f;
-    mm_a_smem_b_nk(s, sQ, r0, sK, g, t);
-    // scale + causal mask + running max
+    zero_acc(s);
+    mm_smem_nk(s, sQ, r0, sK, lane);
     float mx[2] = {mrow[0], mrow[1]};
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
@@ -177,12 +209,9 @@ attention_fwd_kernel(const float* __restrict__ qkv, float* __restrict__ out, bf1
       lrow[r] = lrow[r] * corr[r] + psum[r];
       mrow[r] = mx[r];
     }
-    // P.V goes into a fresh accumulator and is folded with a round-to-nearest add: the HMMA accumulator
-    // truncates, so a long-running accumulation over all key tiles would drift (see gemm_sm100.cuh)
     float ot[8][4];
-#pragma unroll
-    for (int j = 0; j < 8; ++j) ot[j][0] = ot[j][1] = ot[j][2] = ot[j][3] = 0.f;
-    mm_a_acc_b_kn(ot, s, sV, g, t);
+    zero_acc(ot);
+    mm_regs_kn(ot, s, sV, lane);
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       o[j][0] = o[j][0] * corr[0] + ot[j][0]; o[j][1] = o[j][1] * corr[0] + ot[j][1];
@@ -190,7 +219,6 @@ attention_fwd_kernel(const float* __restrict__ qkv, float* __restrict__ out, bf1
     }
   }
 
-  // epilogue: O / l, LSE
   const float inv0 = 1.f / lrow[0], inv1 = 1.f / lrow[1];
   if (t == 0) {
     if (qi0 < T) lse[((long)b * H + h) * T + qi0] = mrow[0] + logf(lrow[0]);
@@ -202,20 +230,9 @@ attention_fwd_kernel(const float* __restrict__ qkv, float* __restrict__ out, bf1
     for (int r = 0; r < 2; ++r) {
       const int qi = r ? qi1 : qi0;
       if (qi >= T) continue;
-      const float a = o[j][2 * r] * (r ? inv1 : inv0), c = o[j][2 * r + 1] * (r ? inv1 : inv0);
+      const float inv = r ? inv1 : inv0;
       const long off = ((long)b * T + qi) * E + h * AD + j * 8 + 2 * t;
-      if (out) *reinterpret_cast<float2*>(out + off) = make_float2(a, c);
-      if (planes) {
-        bf16 x0, x1, x2, y0, y1, y2;
-        split3(a, x0, x1, x2);
-        split3(c, y0, y1, y2);
-        const bf16 xs[3] = {x0, x1, x2}, ys[3] = {y0, y1, y2};
-#pragma unroll
-        for (int p = 0; p < 3; ++p)
-          if (p < nplanes)
-            *reinterpret_cast<uint32_t*>(planes + p * plane_stride + off) =
-                (uint32_t)__bfloat16_as_ushort(xs[p]) | ((uint32_t)__bfloat16_as_ushort(ys[p]) << 16);
-      }
+      store_pair(out, planes, plane_stride, nplanes, off, o[j][2 * r] * inv, o[j][2 * r + 1] * inv);
     }
   }
 }
@@ -236,50 +253,43 @@ __global__ void attention_delta_kernel(const float* __restrict__ o, const float*
 // ---------------------------------------------------------------------------------------------------------------
 // dK, dV for one tile of 64 keys; everything is computed transposed so that keys are the MMA row index.
 __global__ void __launch_bounds__(128)
-attention_bwd_kv_kernel(const float* __restrict__ qkv, const float* __restrict__ dout, const float* __restrict__ lse,
-                        const float* __restrict__ delta, float* __restrict__ dqkv, bf16* __restrict__ planes,
-                        long plane_stride, int nplanes, int T, int H, float scale) {
-  extern __shared__ float sm[];
-  float* sK = sm;
-  float* sV = sK + AT * ALD;
-  float* sQ = sV + AT * ALD;
-  float* sdO = sQ + AT * ALD;
-  float* sLse = sdO + AT * ALD;  // [64]
-  float* sDel = sLse + AT;       // [64]
+attention_bwd_kv_kernel(const bf16* __restrict__ qkv, long qkv_ps, const bf16* __restrict__ dout, long do_ps,
+                        const float* __restrict__ lse, const float* __restrict__ delta, float* __restrict__ dqkv,
+                        bf16* __restrict__ planes, long plane_stride, int nplanes, int T, int H, float scale) {
+  extern __shared__ __align__(1024) uint8_t sm_raw[];
+  const uint32_t sK = (smem_u32(sm_raw) + 1023u) & ~1023u, sV = sK + ATILE, sQ = sV + ATILE, sdO = sQ + ATILE;
+  __shared__ float sLse[AT], sDel[AT];
   const int E = H * AD;
+  const long ld = 3L * E;
   const int kt = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
   const int k0 = kt * AT;
-  const float* base = qkv + (long)b * T * 3 * E + h * AD;
-  const float* dobase = dout + (long)b * T * E + h * AD;
-  load_tile(sK, base + E + (long)k0 * 3 * E, 3 * E, min(AT, T - k0));
-  load_tile(sV, base + 2 * E + (long)k0 * 3 * E, 3 * E, min(AT, T - k0));
+  const bf16* base = qkv + (long)b * T * ld + h * AD;
+  const bf16* dobase = dout + (long)b * T * E + h * AD;
+  load_tile_async(sK, base + E + (long)k0 * ld, ld, qkv_ps, min(AT, T - k0));
+  load_tile_async(sV, base + 2 * E + (long)k0 * ld, ld, qkv_ps, min(AT, T - k0));
   const int r0 = warp * 16;
   const int kj0 = k0 + r0 + g, kj1 = kj0 + 8;
 
   float dk[8][4], dv[8][4];
-#pragma unroll
-  for (int j = 0; j < 8; ++j) {
-    dk[j][0] = dk[j][1] = dk[j][2] = dk[j][3] = 0.f;
-    dv[j][0] = dv[j][1] = dv[j][2] = dv[j][3] = 0.f;
-  }
+  zero_acc(dk);
+  zero_acc(dv);
   const int nqt = (T + AT - 1) / AT;
   for (int qt = kt; qt < nqt; ++qt) {
     const int q0 = qt * AT;
     __syncthreads();
-    load_tile(sQ, base + (long)q0 * 3 * E, 3 * E, min(AT, T - q0));
-    load_tile(sdO, dobase + (long)q0 * E, E, min(AT, T - q0));
+    load_tile_async(sQ, base + (long)q0 * ld, ld, qkv_ps, min(AT, T - q0));
+    load_tile_async(sdO, dobase + (long)q0 * E, E, do_ps, min(AT, T - q0));
     if (threadIdx.x < AT) {
       const int qi = q0 + threadIdx.x;
       sLse[threadIdx.x] = qi < T ? lse[((long)b * H + h) * T + qi] : INFINITY;
       sDel[threadIdx.x] = qi < T ? delta[((long)b * H + h) * T + qi] : 0.f;
     }
+    cp_async_wait_all();
     __syncthreads();
-    // S^T = K Q^T  (rows: keys, cols: queries)
     float s[8][4];
-#pragma unroll
-    for (int j = 0; j < 8; ++j) s[j][0] = s[j][1] = s[j][2] = s[j][3] = 0.f;
-    mm_a_smem_b_nk(s, sK, r0, sQ, g, t);
+    zero_acc(s);
+    mm_smem_nk(s, sK, r0, sQ, lane);          // S^T = K Q^T  (rows: keys, cols: queries)
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
 #pragma unroll
@@ -292,31 +302,24 @@ attention_bwd_kv_kernel(const float* __restrict__ qkv, const float* __restrict__
         s[j][e] = pv;  // P^T
       }
     }
-    // dV += P^T dO   (fresh accumulator per tile + RN fold, see forward)
     float tmp[8][4];
-#pragma unroll
-    for (int j = 0; j < 8; ++j) tmp[j][0] = tmp[j][1] = tmp[j][2] = tmp[j][3] = 0.f;
-    mm_a_acc_b_kn(tmp, s, sdO, g, t);
+    zero_acc(tmp);
+    mm_regs_kn(tmp, s, sdO, lane);             // dV += P^T dO
 #pragma unroll
     for (int j = 0; j < 8; ++j) { dv[j][0] += tmp[j][0]; dv[j][1] += tmp[j][1]; dv[j][2] += tmp[j][2]; dv[j][3] += tmp[j][3]; }
-    // dP^T = V dO^T
     float dp[8][4];
-#pragma unroll
-    for (int j = 0; j < 8; ++j) dp[j][0] = dp[j][1] = dp[j][2] = dp[j][3] = 0.f;
-    mm_a_smem_b_nk(dp, sV, r0, sdO, g, t);
-    // dS^T = P^T * (dP^T - delta) * scale
+    zero_acc(dp);
+    mm_smem_nk(dp, sV, r0, sdO, lane);         // dP^T = V dO^T
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
 #pragma unroll
       for (int e = 0; e < 4; ++e) {
         const int ql = j * 8 + 2 * t + (e & 1);
-        dp[j][e] = s[j][e] * (dp[j][e] - sDel[ql]) * scale;
+        dp[j][e] = s[j][e] * (dp[j][e] - sDel[ql]) * scale;   // dS^T
       }
     }
-    // dK += dS^T Q
-#pragma unroll
-    for (int j = 0; j < 8; ++j) tmp[j][0] = tmp[j][1] = tmp[j][2] = tmp[j][3] = 0.f;
-    mm_a_acc_b_kn(tmp, dp, sQ, g, t);
+    zero_acc(tmp);
+    mm_regs_kn(tmp, dp, sQ, lane);             // dK += dS^T Q
 #pragma unroll
     for (int j = 0; j < 8; ++j) { dk[j][0] += tmp[j][0]; dk[j][1] += tmp[j][1]; dk[j][2] += tmp[j][2]; dk[j][3] += tmp[j][3]; }
   }
@@ -327,44 +330,27 @@ attention_bwd_kv_kernel(const float* __restrict__ qkv, const float* __restrict__
       const int kj = r ? kj1 : kj0;
       if (kj >= T) continue;
       const long rowoff = ((long)b * T + kj) * 3 * E + h * AD + j * 8 + 2 * t;
-      const float vals[2][2] = {{dk[j][2 * r], dk[j][2 * r + 1]}, {dv[j][2 * r], dv[j][2 * r + 1]}};
-#pragma unroll
-      for (int w = 0; w < 2; ++w) {  // 0: dK (column block E), 1: dV (column block 2E)
-        const long off = rowoff + (w + 1) * E;
-        if (dqkv) *reinterpret_cast<float2*>(dqkv + off) = make_float2(vals[w][0], vals[w][1]);
-        if (planes) {
-          bf16 x0, x1, x2, y0, y1, y2;
-          split3(vals[w][0], x0, x1, x2);
-          split3(vals[w][1], y0, y1, y2);
-          const bf16 xs[3] = {x0, x1, x2}, ys[3] = {y0, y1, y2};
-#pragma unroll
-          for (int p = 0; p < 3; ++p)
-            if (p < nplanes)
-              *reinterpret_cast<uint32_t*>(planes + p * plane_stride + off) =
-                  (uint32_t)__bfloat16_as_ushort(xs[p]) | ((uint32_t)__bfloat16_as_ushort(ys[p]) << 16);
-        }
-      }
+      store_pair(dqkv, planes, plane_stride, nplanes, rowoff + E, dk[j][2 * r], dk[j][2 * r + 1]);
+      store_pair(dqkv, planes, plane_stride, nplanes, rowoff + 2 * E, dv[j][2 * r], dv[j][2 * r + 1]);
     }
   }
 }
 
 // dQ for one tile of 64 queries
 __global__ void __launch_bounds__(128)
-attention_bwd_q_kernel(const float* __restrict__ qkv, const float* __restrict__ dout, const float* __restrict__ lse,
-                       const float* __restrict__ delta, float* __restrict__ dqkv, bf16* __restrict__ planes,
-                       long plane_stride, int nplanes, int T, int H, float scale) {
-  extern __shared__ float sm[];
-  float* sQ = sm;
-  float* sdO = sQ + AT * ALD;
-  float* sK = sdO + AT * ALD;
-  float* sV = sK + AT * ALD;
+attention_bwd_q_kernel(const bf16* __restrict__ qkv, long qkv_ps, const bf16* __restrict__ dout, long do_ps,
+                       const float* __restrict__ lse, const float* __restrict__ delta, float* __restrict__ dqkv,
+                       bf16* __restrict__ planes, long plane_stride, int nplanes, int T, int H, float scale) {
+  extern __shared__ __align__(1024) uint8_t sm_raw[];
+  const uint32_t sQ = (smem_u32(sm_raw) + 1023u) & ~1023u, sdO = sQ + ATILE, sK = sdO + ATILE, sV = sK + ATILE;
   const int E = H * AD;
+  const long ld = 3L * E;
   const int qt = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
   const int q0 = qt * AT;
-  const float* base = qkv + (long)b * T * 3 * E + h * AD;
-  load_tile(sQ, base + (long)q0 * 3 * E, 3 * E, min(AT, T - q0));
-  load_tile(sdO, dout + ((long)b * T + q0) * E + h * AD, E, min(AT, T - q0));
+  const bf16* base = qkv + (long)b * T * ld + h * AD;
+  load_tile_async(sQ, base + (long)q0 * ld, ld, qkv_ps, min(AT, T - q0));
+  load_tile_async(sdO, dout + ((long)b * T + q0) * E + h * AD, E, do_ps, min(AT, T - q0));
   const int r0 = warp * 16;
   const int qi0 = q0 + r0 + g, qi1 = qi0 + 8;
   float lse_r[2], del_r[2];
@@ -374,22 +360,19 @@ attention_bwd_q_kernel(const float* __restrict__ qkv, const float* __restrict__ 
   del_r[1] = qi1 < T ? delta[((long)b * H + h) * T + qi1] : 0.f;
 
   float dq[8][4];
-#pragma unroll
-  for (int j = 0; j < 8; ++j) dq[j][0] = dq[j][1] = dq[j][2] = dq[j][3] = 0.f;
+  zero_acc(dq);
   for (int kt = 0; kt <= qt; ++kt) {
     const int k0 = kt * AT;
     __syncthreads();
-    load_tile(sK, base + E + (long)k0 * 3 * E, 3 * E, min(AT, T - k0));
-    load_tile(sV, base + 2 * E + (long)k0 * 3 * E, 3 * E, min(AT, T - k0));
+    load_tile_async(sK, base + E + (long)k0 * ld, ld, qkv_ps, min(AT, T - k0));
+    load_tile_async(sV, base + 2 * E + (long)k0 * ld, ld, qkv_ps, min(AT, T - k0));
+    cp_async_wait_all();
     __syncthreads();
     float s[8][4], dp[8][4];
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      s[j][0] = s[j][1] = s[j][2] = s[j][3] = 0.f;
-      dp[j][0] = dp[j][1] = dp[j][2] = dp[j][3] = 0.f;
-    }
-    mm_a_smem_b_nk(s, sQ, r0, sK, g, t);     // S  = Q K^T
-    mm_a_smem_b_nk(dp, sdO, r0, sV, g, t);   // dP = dO V^T
+    zero_acc(s);
+    zero_acc(dp);
+    mm_smem_nk(s, sQ, r0, sK, lane);     // S  = Q K^T
+    mm_smem_nk(dp, sdO, r0, sV, lane);   // dP = dO V^T
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
 #pragma unroll
@@ -401,10 +384,8 @@ attention_bwd_q_kernel(const float* __restrict__ qkv, const float* __restrict__ 
         s[j][e] = pv * (dp[j][e] - del_r[e >> 1]) * scale;  // dS
       }
     }
-    // dQ += dS K   (dp is dead here: reuse it as the per-tile accumulator)
-#pragma unroll
-    for (int j = 0; j < 8; ++j) dp[j][0] = dp[j][1] = dp[j][2] = dp[j][3] = 0.f;
-    mm_a_acc_b_kn(dp, s, sK, g, t);
+    zero_acc(dp);                        // dp is dead: reuse it as the per-tile accumulator
+    mm_regs_kn(dp, s, sK, lane);         // dQ += dS K
 #pragma unroll
     for (int j = 0; j < 8; ++j) { dq[j][0] += dp[j][0]; dq[j][1] += dp[j][1]; dq[j][2] += dp[j][2]; dq[j][3] += dp[j][3]; }
   }
@@ -415,19 +396,7 @@ attention_bwd_q_kernel(const float* __restrict__ qkv, const float* __restrict__ 
       const int qi = r ? qi1 : qi0;
       if (qi >= T) continue;
       const long off = ((long)b * T + qi) * 3 * E + h * AD + j * 8 + 2 * t;
-      const float a = dq[j][2 * r], c = dq[j][2 * r + 1];
-      if (dqkv) *reinterpret_cast<float2*>(dqkv + off) = make_float2(a, c);
-      if (planes) {
-        bf16 x0, x1, x2, y0, y1, y2;
-        split3(a, x0, x1, x2);
-        split3(c, y0, y1, y2);
-        const bf16 xs[3] = {x0, x1, x2}, ys[3] = {y0, y1, y2};
-#pragma unroll
-        for (int p = 0; p < 3; ++p)
-          if (p < nplanes)
-            *reinterpret_cast<uint32_t*>(planes + p * plane_stride + off) =
-                (uint32_t)__bfloat16_as_ushort(xs[p]) | ((uint32_t)__bfloat16_as_ushort(ys[p]) << 16);
-      }
+      store_pair(dqkv, planes, plane_stride, nplanes, off, dq[j][2 * r], dq[j][2 * r + 1]);
     }
   }
 }
@@ -438,32 +407,37 @@ static int set_smem(const void* fn, size_t bytes) {
   return 0;
 }
 
-int attention_fwd(const float* qkv, float* out, bf16* out_planes, long plane_stride, int nplanes, float* lse, int B,
-                  int T, int H, int D, cudaStream_t s) {
+int attention_fwd(const bf16* qkv_planes, long qkv_plane_stride, float* out, bf16* out_planes, long plane_stride,
+                  int nplanes, float* lse, int B, int T, int H, int D, cudaStream_t s) {
   OOB_CHECK(D == AD, "attention: head_dim must be 64 (got %d)", D);
-  const size_t smem = (size_t)3 * AT * ALD * sizeof(float);
+  OOB_CHECK((reinterpret_cast<uintptr_t>(qkv_planes) & 15) == 0 && (qkv_plane_stride & 7) == 0,
+            "attention: qkv planes misaligned");
+  const size_t smem = (size_t)3 * ATILE + 1024;
   static bool once = false;
   if (!once) {
     if (set_smem((const void*)attention_fwd_kernel, smem)) return -1;
     once = true;
   }
   dim3 grid((T + AT - 1) / AT, H, B);
-  attention_fwd_kernel<<<grid, 128, smem, s>>>(qkv, out, out_planes, plane_stride, nplanes, lse, T, H,
-                                               1.0f / sqrtf((float)D));
+  attention_fwd_kernel<<<grid, 128, smem, s>>>(qkv_planes, qkv_plane_stride, out, out_planes, plane_stride, nplanes, lse,
+                                               T, H, 1.0f / sqrtf((float)D));
   OOB_CUDA_OK(cudaGetLastError());
   count_launch();
   return 0;
 }
 
-int attention_bwd(const float* qkv, const float* out, const float* dout, const float* lse, float* delta, float* dqkv,
+int attention_bwd(const bf16* qkv_planes, long qkv_plane_stride, const float* out, const float* dout,
+                  const bf16* dout_planes, long dout_plane_stride, const float* lse, float* delta, float* dqkv,
                   bf16* dqkv_planes, long plane_stride, int nplanes, int B, int T, int H, int D, cudaStream_t s) {
   OOB_CHECK(D == AD, "attention: head_dim must be 64 (got %d)", D);
-  const size_t smem_kv = (size_t)(4 * AT * ALD + 2 * AT) * sizeof(float);
-  const size_t smem_q = (size_t)4 * AT * ALD * sizeof(float);
+  OOB_CHECK((reinterpret_cast<uintptr_t>(qkv_planes) & 15) == 0 && (qkv_plane_stride & 7) == 0 &&
+                (reinterpret_cast<uintptr_t>(dout_planes) & 15) == 0 && (dout_plane_stride & 7) == 0,
+            "attention: operand planes misaligned");
+  const size_t smem = (size_t)4 * ATILE + 1024;
   static bool once = false;
   if (!once) {
-    if (set_smem((const void*)attention_bwd_kv_kernel, smem_kv)) return -1;
-    if (set_smem((const void*)attention_bwd_q_kernel, smem_q)) return -1;
+    if (set_smem((const void*)attention_bwd_kv_kernel, smem)) return -1;
+    if (set_smem((const void*)attention_bwd_q_kernel, smem)) return -1;
     once = true;
   }
   const int total = B * T * H;
@@ -472,12 +446,12 @@ int attention_bwd(const float* qkv, const float* out, const float* dout, const f
   count_launch();
   dim3 grid((T + AT - 1) / AT, H, B);
   const float scale = 1.0f / sqrtf((float)D);
-  attention_bwd_kv_kernel<<<grid, 128, smem_kv, s>>>(qkv, dout, lse, delta, dqkv, dqkv_planes, plane_stride, nplanes,
-                                                     T, H, scale);
+  attention_bwd_kv_kernel<<<grid, 128, smem, s>>>(qkv_planes, qkv_plane_stride, dout_planes, dout_plane_stride, lse, delta,
+                                                  dqkv, dqkv_planes, plane_stride, nplanes, T, H, scale);
   OOB_CUDA_OK(cudaGetLastError());
   count_launch();
-  attention_bwd_q_kernel<<<grid, 128, smem_q, s>>>(qkv, dout, lse, delta, dqkv, dqkv_planes, plane_stride, nplanes, T,
-                                                   H, scale);
+  attention_bwd_q_kernel<<<grid, 128, smem, s>>>(qkv_planes, qkv_plane_stride, dout_planes, dout_plane_stride, lse, delta,
+                                                 dqkv, dqkv_planes, plane_stride, nplanes, T, H, scale);
   OOB_CUDA_OK(cudaGetLastError());
   count_launch();
   return 0;

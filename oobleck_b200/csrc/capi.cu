@@ -72,16 +72,20 @@ int oob_colsum_accumulate(const float* a, long lda, int rows, int cols, float* o
   return colsum_accumulate(a, lda, rows, cols, out, partials, S(stream));
 }
 
-int oob_attention_fwd(const float* qkv, float* out, void* out_planes, long plane_stride, int nplanes, float* lse,
-                      int batch, int seq, int n_head, int head_dim, void* stream) {
-  return attention_fwd(qkv, out, reinterpret_cast<bf16*>(out_planes), plane_stride, nplanes, lse, batch, seq, n_head,
-                       head_dim, S(stream));
+int oob_attention_fwd(const void* qkv_planes, long qkv_plane_stride, float* out, void* out_planes, long plane_stride,
+                      int nplanes, float* lse, int batch, int seq, int n_head, int head_dim, void* stream) {
+  return attention_fwd(reinterpret_cast<const bf16*>(qkv_planes), qkv_plane_stride, out,
+                       reinterpret_cast<bf16*>(out_planes), plane_stride, nplanes, lse, batch, seq, n_head, head_dim,
+                       S(stream));
 }
-int oob_attention_bwd(const float* qkv, const float* out, const float* dout, const float* lse, float* delta,
-                      float* dqkv, void* dqkv_planes, long plane_stride, int nplanes, int batch, int seq, int n_head,
-                      int head_dim, void* stream) {
-  return attention_bwd(qkv, out, dout, lse, delta, dqkv, reinterpret_cast<bf16*>(dqkv_planes), plane_stride, nplanes,
-                       batch, seq, n_head, head_dim, S(stream));
+int oob_attention_bwd(const void* qkv_planes, long qkv_plane_stride, const float* out, const float* dout,
+                      const void* dout_planes, long dout_plane_stride, const float* lse, float* delta, float* dqkv,
+                      void* dqkv_planes, long plane_stride, int nplanes, int batch, int seq, int n_head, int head_dim,
+                      void* stream) {
+  return attention_bwd(reinterpret_cast<const bf16*>(qkv_planes), qkv_plane_stride, out, dout,
+                       reinterpret_cast<const bf16*>(dout_planes), dout_plane_stride, lse, delta, dqkv,
+                       reinterpret_cast<bf16*>(dqkv_planes), plane_stride, nplanes, batch, seq, n_head, head_dim,
+                       S(stream));
 }
 
 int oob_embedding_fwd(const long long* ids, const float* wte, const float* wpe, float* hidden, int rows, int seq,

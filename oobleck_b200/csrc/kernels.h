@@ -31,10 +31,11 @@ int cross_entropy(const float* logits, long ldl, const long long* labels, int B,
 int adamw_step(float* p, const float* g, float* m, float* v, bf16* planes, long plane_stride, int nplanes, long n,
                float lr, float beta1, float beta2, float eps, float wd, int step, cudaStream_t s);
 
-// attention.cu -- causal multi-head attention on packed qkv [B*T, 3E] (q | k | v, head h at columns h*D..)
-int attention_fwd(const float* qkv, float* out, bf16* out_planes, long plane_stride, int nplanes, float* lse, int B,
-                  int T, int H, int D, cudaStream_t s);
-int attention_bwd(const float* qkv, const float* out, const float* dout, const float* lse, float* delta, float* dqkv,
+// attention.cu -- causal multi-head attention on packed q|k|v split planes [3][B*T][3E] (head h at columns h*D..)
+int attention_fwd(const bf16* qkv_planes, long qkv_plane_stride, float* out, bf16* out_planes, long plane_stride,
+                  int nplanes, float* lse, int B, int T, int H, int D, cudaStream_t s);
+int attention_bwd(const bf16* qkv_planes, long qkv_plane_stride, const float* out, const float* dout,
+                  const bf16* dout_planes, long dout_plane_stride, const float* lse, float* delta, float* dqkv,
                   bf16* dqkv_planes, long plane_stride, int nplanes, int B, int T, int H, int D, cudaStream_t s);
 
 }  // namespace oob

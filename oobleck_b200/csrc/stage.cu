@@ -40,16 +40,16 @@ inline GemmEpilogue epi_none() {
   return e;
 }
 
-// D = A[M,K] . W[K,N] + bias (+resid), optional GELU planes
+// D = A[M,K] . W[K,N] + bias (+resid); optionally the split planes of the result (or of GELU(result))
 int linear_fwd(const PlaneMat& a, const oob_layer_params* p, long w_off, long b_off, int M, int N, int K, int nsplit,
-               float* d, const float* resid, bf16* gelu_planes, cudaStream_t st) {
+               float* d, const float* resid, bf16* planes_out, bool gelu, cudaStream_t st) {
   GemmParams gp{M, N, K, nsplit, epi_none()};
   gp.epi.d = d; gp.epi.ldd = N;
   gp.epi.bias = p->w + b_off;
   gp.epi.resid = resid; gp.epi.ldr = N;
-  if (gelu_planes) {
-    gp.epi.act = ACT_GELU;
-    gp.epi.planes = gelu_planes; gp.epi.ldp = N; gp.epi.plane_stride = (long)M * N; gp.epi.nplanes_out = 3;
+  if (planes_out) {
+    gp.epi.act = gelu ? ACT_GELU : ACT_NONE;
+    gp.epi.planes = planes_out; gp.epi.ldp = N; gp.epi.plane_stride = (long)M * N; gp.epi.nplanes_out = 3;
   }
   return gemm_launch(a, 0, weight_planes(p, w_off, K, N), 1, gp, st);
 }
@@ -92,18 +92,19 @@ int oob_block_forward(const oob_dims* d, const oob_layer_params* p, const float*
   int rc;
   if ((rc = layernorm_fwd(x, p->w + o.ln1_w, p->w + o.ln1_b, nullptr, (bf16*)c->ln1_planes, ME, 3, c->ln1_mean,
                           c->ln1_rstd, M, E, d->ln_eps, st))) return rc;
-  if ((rc = linear_fwd(act_planes(c->ln1_planes, M, E), p, o.attn_w, o.attn_b, M, 3 * E, E, ns, c->qkv, nullptr,
-                       nullptr, st))) return rc;
-  if ((rc = attention_fwd(c->qkv, c->att, (bf16*)c->att_planes, ME, 3, c->lse, d->batch, d->seq, d->n_head, 64, st)))
-    return rc;
-  if ((rc = linear_fwd(act_planes(c->att_planes, M, E), p, o.proj_w, o.proj_b, M, E, E, ns, c->x2, x, nullptr, st)))
-    return rc;
+  // q|k|v go straight to split planes: attention (forward and the recompute in backward) is their only consumer
+  if ((rc = linear_fwd(act_planes(c->ln1_planes, M, E), p, o.attn_w, o.attn_b, M, 3 * E, E, ns, nullptr, nullptr,
+                       (bf16*)c->qkv_planes, false, st))) return rc;
+  if ((rc = attention_fwd((const bf16*)c->qkv_planes, (long)M * 3 * E, c->att, (bf16*)c->att_planes, ME, 3, c->lse,
+                          d->batch, d->seq, d->n_head, 64, st))) return rc;
+  if ((rc = linear_fwd(act_planes(c->att_planes, M, E), p, o.proj_w, o.proj_b, M, E, E, ns, c->x2, x, nullptr, false,
+                       st))) return rc;
   if ((rc = layernorm_fwd(c->x2, p->w + o.ln2_w, p->w + o.ln2_b, nullptr, (bf16*)c->ln2_planes, ME, 3, c->ln2_mean,
                           c->ln2_rstd, M, E, d->ln_eps, st))) return rc;
   if ((rc = linear_fwd(act_planes(c->ln2_planes, M, E), p, o.fc_w, o.fc_b, M, 4 * E, E, ns, c->fc, nullptr,
-                       (bf16*)c->gelu_planes, st))) return rc;
+                       (bf16*)c->gelu_planes, true, st))) return rc;
   if ((rc = linear_fwd(act_planes(c->gelu_planes, M, 4 * E), p, o.proj2_w, o.proj2_b, M, E, 4 * E, ns, y, c->x2,
-                       nullptr, st))) return rc;
+                       nullptr, false, st))) return rc;
   return 0;
 }
 
@@ -131,11 +132,12 @@ int oob_block_backward(const oob_dims* d, const oob_layer_params* p, const float
                           ME, 3, p->g + o.ln2_w, p->g + o.ln2_b, s->partials, M, E, st))) return rc;
   // ---- attention ----
   const PlaneMat dx2p = act_planes(s->dx2_planes, M, E);
-  if ((rc = linear_dgrad(dx2p, p, o.proj_w, M, E, E, ns, s->datt, nullptr, nullptr, st))) return rc;
+  if ((rc = linear_dgrad(dx2p, p, o.proj_w, M, E, E, ns, s->datt, nullptr, (bf16*)s->datt_planes, st))) return rc;
   if ((rc = linear_wgrad(act_planes(c->att_planes, M, E), dx2p, p, o.proj_w, M, E, E, ns, st))) return rc;
   if ((rc = colsum_accumulate(s->dx2, E, M, E, p->g + o.proj_b, s->partials, st))) return rc;
-  if ((rc = attention_bwd(c->qkv, c->att, s->datt, c->lse, s->delta, s->dqkv, (bf16*)s->dqkv_planes, (long)M * 3 * E, 3,
-                          d->batch, d->seq, d->n_head, 64, st))) return rc;
+  if ((rc = attention_bwd((const bf16*)c->qkv_planes, (long)M * 3 * E, c->att, s->datt, (const bf16*)s->datt_planes, ME,
+                          c->lse, s->delta, s->dqkv, (bf16*)s->dqkv_planes, (long)M * 3 * E, 3, d->batch, d->seq,
+                          d->n_head, 64, st))) return rc;
   const PlaneMat dqkvp = act_planes(s->dqkv_planes, M, 3 * E);
   if ((rc = linear_dgrad(dqkvp, p, o.attn_w, M, 3 * E, E, ns, s->dln, nullptr, nullptr, st))) return rc;
   if ((rc = linear_wgrad(act_planes(c->ln1_planes, M, E), dqkvp, p, o.attn_w, M, 3 * E, E, ns, st))) return rc;

@@ -47,7 +47,7 @@ class StageWorkspace:
         self.t = {
             "dfc": torch.empty(M, 4 * E, **f32), "dfc_planes": torch.empty(3, M, 4 * E, **bf),
             "dln": torch.empty(M, E, **f32), "dx2": torch.empty(M, E, **f32), "dx2_planes": torch.empty(3, M, E, **bf),
-            "datt": torch.empty(M, E, **f32), "delta": torch.empty(microbatch * n_head * seq, **f32),
+            "datt": torch.empty(M, E, **f32), "datt_planes": torch.empty(3, M, E, **bf), "delta": torch.empty(microbatch * n_head * seq, **f32),
             "dqkv": torch.empty(M, 3 * E, **f32), "dqkv_planes": torch.empty(3, M, 3 * E, **bf),
             "partials": torch.empty(nparts, **f32),
         }
@@ -172,7 +172,7 @@ class Layer:
         for _ in range(self.num_pipe_buffers):
             if self.spec.kind == "block":
                 t = {"ln1_planes": torch.empty(3, M, E, **bf), "ln1_mean": torch.empty(M, **f32),
-                     "ln1_rstd": torch.empty(M, **f32), "qkv": torch.empty(M, 3 * E, **f32),
+                     "ln1_rstd": torch.empty(M, **f32), "qkv_planes": torch.empty(3, M, 3 * E, **bf),
                      "att": torch.empty(M, E, **f32), "att_planes": torch.empty(3, M, E, **bf),
                      "lse": torch.empty(self.mb * H * self.T, **f32), "x2": torch.empty(M, E, **f32),
                      "ln2_planes": torch.empty(3, M, E, **bf), "ln2_mean": torch.empty(M, **f32),

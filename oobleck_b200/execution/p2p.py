@@ -22,7 +22,9 @@ from .. import lib as L
 from .pipeline import DistTransport
 
 NSLOTS = 4
-_GENERATION = 0   # bumped when pipelines are rebuilt so that store keys never collide
+# how many links this process has created with each peer: both ends of a boundary create their n-th link at the same
+# logical time (initial build, then once per reconfiguration), so (pair, n) is a collision-free rendezvous key
+_LINK_SEQ: dict[tuple[int, int], int] = {}
 
 
 def _align(n: int, a: int = 256) -> int:
@@ -33,7 +35,6 @@ class _Link:
     """Mailbox pair with one neighbour: ``mine`` (peer writes payloads / flags / acks here) and ``peer``."""
 
     def __init__(self, my_rank: int, peer_rank: int, slot_bytes: int, tag: str):
-        global _GENERATION
         self.slot_bytes = slot_bytes
         self.mine = C.c_void_p()
         handle = (C.c_char * 64)()
@@ -77,8 +78,10 @@ class NvlinkRingTransport(DistTransport):
         if peer_rank not in self.links:
             slot = sum(_align(t.numel() * t.element_size()) for t in tensors)
             me = dist.get_rank()
-            lo, hi = min(me, peer_rank), max(me, peer_rank)
-            self.links[peer_rank] = _Link(me, peer_rank, self._slot_bytes(tensors, slot), f"g{_GENERATION}/{lo}-{hi}")
+            pair = (min(me, peer_rank), max(me, peer_rank))
+            seq = _LINK_SEQ.get(pair, 0)
+            _LINK_SEQ[pair] = seq + 1
+            self.links[peer_rank] = _Link(me, peer_rank, self._slot_bytes(tensors, slot), f"{pair[0]}-{pair[1]}/{seq}")
         return self.links[peer_rank]
 
     def _slot_bytes(self, tensors, computed: int) -> int:

@@ -44,13 +44,13 @@ class OobLayerParams(C.Structure):
 
 class OobBlockCtx(C.Structure):
     """``oob_block_ctx``."""
-    _fields_ = [(n, C.c_void_p) for n in ["ln1_planes", "ln1_mean", "ln1_rstd", "qkv", "att", "att_planes", "lse", "x2",
+    _fields_ = [(n, C.c_void_p) for n in ["ln1_planes", "ln1_mean", "ln1_rstd", "qkv_planes", "att", "att_planes", "lse", "x2",
                                           "ln2_planes", "ln2_mean", "ln2_rstd", "fc", "gelu_planes"]]
 
 
 class OobBwdScratch(C.Structure):
     """``oob_bwd_scratch``."""
-    _fields_ = [(n, C.c_void_p) for n in ["dfc", "dfc_planes", "dln", "dx2", "dx2_planes", "datt", "delta", "dqkv",
+    _fields_ = [(n, C.c_void_p) for n in ["dfc", "dfc_planes", "dln", "dx2", "dx2_planes", "datt", "datt_planes", "delta", "dqkv",
                                           "dqkv_planes", "partials"]]
 
 
@@ -75,8 +75,8 @@ _SIGNATURES = {
     "oob_layernorm_fwd": (_I, [_P, _P, _P, _P, _P, _L, _I, _P, _P, _I, _I, _F, _P]),
     "oob_layernorm_bwd": (_I, [_P, _P, _P, _P, _P, _P, _P, _P, _L, _I, _P, _P, _P, _I, _I, _P]),
     "oob_colsum_accumulate": (_I, [_P, _L, _I, _I, _P, _P, _P]),
-    "oob_attention_fwd": (_I, [_P, _P, _P, _L, _I, _P, _I, _I, _I, _I, _P]),
-    "oob_attention_bwd": (_I, [_P, _P, _P, _P, _P, _P, _P, _L, _I, _I, _I, _I, _I, _P]),
+    "oob_attention_fwd": (_I, [_P, _L, _P, _P, _L, _I, _P, _I, _I, _I, _I, _P]),
+    "oob_attention_bwd": (_I, [_P, _L, _P, _P, _P, _L, _P, _P, _P, _P, _L, _I, _I, _I, _I, _I, _P]),
     "oob_embedding_fwd": (_I, [_P, _P, _P, _P, _I, _I, _I, _P]),
     "oob_embedding_bwd": (_I, [_P, _P, _P, _P, _I, _I, _I, _P]),
     "oob_cross_entropy": (_I, [_P, _L, _P, _I, _I, _I, _P, _P, _P, _P, _L, _L, _I, _P]),

@@ -140,7 +140,8 @@ def test_attention_fwd_bwd(B, T, H):
     out = torch.empty(B * T, E, device=DEV)
     outp = ops.new_planes(B * T, E)
     lse = torch.empty(B, H, T, device=DEV)
-    L.call("oob_attention_fwd", P(qkv), P(out), P(outp), outp.stride(0), 3, P(lse), B, T, H, D, S())
+    qp = ops.split(qkv)
+    L.call("oob_attention_fwd", P(qp), qp.stride(0), P(out), P(outp), outp.stride(0), 3, P(lse), B, T, H, D, S())
     q64 = qkv.double().requires_grad_(True)
     ref = ref_attention(q64, B, T, H, D)
     assert rel_err(out, ref) < 5e-6
@@ -150,8 +151,9 @@ def test_attention_fwd_bwd(B, T, H):
     dqkv = torch.full((B * T, 3 * E), float("nan"), device=DEV)
     dqp = ops.new_planes(B * T, 3 * E)
     delta = torch.empty(B, H, T, device=DEV)
-    L.call("oob_attention_bwd", P(qkv), P(out), P(dout), P(lse), P(delta), P(dqkv), P(dqp), dqp.stride(0), 3, B, T, H,
-           D, S())
+    dop = ops.split(dout)
+    L.call("oob_attention_bwd", P(qp), qp.stride(0), P(out), P(dout), P(dop), dop.stride(0), P(lse), P(delta), P(dqkv),
+           P(dqp), dqp.stride(0), 3, B, T, H, D, S())
     assert rel_err(dqkv, q64.grad) < 1e-5
     assert rel_err(ops.planes_to_float(dqp), q64.grad) < 1e-5
 

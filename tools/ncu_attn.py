@@ -22,12 +22,16 @@ dqp = ops.new_planes(B * T, 3 * E)
 delta = torch.empty(B, H, T, device="cuda")
 
 
+qp, dop = ops.split(qkv), ops.split(dout)
+
+
 def fwd():
-    L.call("oob_attention_fwd", P(qkv), P(out), P(outp), outp.stride(0), 3, P(lse), B, T, H, D, S())
+    L.call("oob_attention_fwd", P(qp), qp.stride(0), P(out), P(outp), outp.stride(0), 3, P(lse), B, T, H, D, S())
 
 
 def bwd():
-    L.call("oob_attention_bwd", P(qkv), P(out), P(dout), P(lse), P(delta), P(dqkv), P(dqp), dqp.stride(0), 3, B, T, H, D, S())
+    L.call("oob_attention_bwd", P(qp), qp.stride(0), P(out), P(dout), P(dop), dop.stride(0), P(lse), P(delta), P(dqkv),
+           P(dqp), dqp.stride(0), 3, B, T, H, D, S())
 
 
 for fn, name, flops in [(fwd, "fwd", 4 * B * H * T * T * D / 2), (bwd, "bwd", 10 * B * H * T * T * D / 2)]:
