@@ -225,8 +225,13 @@ def run_ours(args, cfg):
         e0.record()
         for i in range(nsteps):
             if time_gemms and i == nsteps - 1:
+                # per-launch GEMM durations for the roofline: this one step keeps every kernel on the compute stream
+                # (no wgrad side stream), so a launch's event pair times that launch alone
+                L.call("oob_side_stream_enable", 0)
                 L.call("oob_gemm_timing_begin")
             engine._train_step()
+            if time_gemms and i == nsteps - 1:
+                L.call("oob_side_stream_enable", args.side_stream)
             if read_loss and is_last:
                 losses.append(float(engine._pipeline.execution.total_loss.item()))   # D2H of the step's result
         e1.record()
@@ -238,6 +243,7 @@ def run_ours(args, cfg):
             ms = float(t.item())
         return ms, losses
 
+    L.call("oob_side_stream_enable", args.side_stream)
     for _ in range(1):
         timed(args.warmup, True, False)          # W untimed warm-up steps
     sampler = ClockSampler(local_rank)
@@ -272,6 +278,7 @@ def run_ours(args, cfg):
         "config": {"workload": f"{args.model} 1F1B train step: {Lh + 2} stage layers over {world} stage(s), "
                                f"micro-batch {mb}, {gb // mb} micro-batches/step, T={T}, AdamW",
                    "global_batch": gb, "seq_len": T, "parallelism": f"pp{world}", "nsplit": args.nsplit,
+                   "wgrad_side_stream": bool(args.side_stream),
                    "l2": "working set per step (>6 GB of weights) far exceeds the 126 MB L2; no flush needed"},
         "clocks": clocks,
         "gpu_launches": int(launches),
@@ -286,6 +293,7 @@ def run_ours(args, cfg):
             "tensor_products_per_algorithmic_flop": nprod,
             "executed_tensor_tflops": gemm_tflops * nprod if gemm_tflops else None,
             "launches_timed": int(g_n.value),
+            "timing_note": "last timed step runs with the wgrad side stream off so each launch is timed alone",
             # dram__bytes_read.sum + dram__bytes_write.sum of ONE launch (forward FC GEMM 2048x6400x1600, nsplit 3) from
             # profiles/r01_ncu_gemm_v3.txt; algorithmic bytes of that launch: 133 MB (3 planes of A and B + fp32 D)
             "traffic": 107.3e6 if args.model == "gpt2-xl" and args.nsplit == 3 else None,
@@ -309,6 +317,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--model", default="gpt2-xl", choices=sorted(MODELS))
     ap.add_argument("--nsplit", type=int, default=3, choices=[1, 2, 3])
+    ap.add_argument("--side-stream", type=int, default=1, choices=[0, 1],
+                    help="0: weight-gradient kernels stay on the compute stream (A/B of the overlap)")
     args = ap.parse_args()
     cfg = MODELS[args.model]
     if args.impl == "reference":

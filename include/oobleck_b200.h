@@ -138,6 +138,13 @@ typedef struct oob_bwd_scratch {    /* per-stage backward temporaries, reused by
   float* delta;                     /* [B*H*T] */
   float* dqkv; void* dqkv_planes;   /* [M,3E], [3][M][3E] */
   float* partials;                  /* max(oob_ln_bwd_partials_floats(E), oob_colsum_partials_floats(4E)) floats */
+  float* partials_side;             /* oob_colsum_partials_floats(4E) floats, or NULL.  Non-NULL: weight/bias gradient
+                                       kernels of oob_block_backward run on the library's side stream, concurrently
+                                       with the dgrad chain on `stream` */
+  int defer_join;                   /* 0: `stream` waits for the side stream before oob_block_backward returns.
+                                       1: the caller alternates TWO scratch sets between consecutive calls and calls
+                                       oob_side_join() before parameter gradients / ctx buffers are touched again */
+  int reserved_;
 } oob_bwd_scratch;
 
 typedef struct oob_head_ctx {       /* ln_f + lm_head + loss for one micro-batch */
@@ -161,6 +168,10 @@ int oob_head_forward(const oob_dims* d, const oob_layer_params* p, const float* 
                      oob_head_ctx* ctx, float* total_loss, void* stream);
 int oob_head_backward(const oob_dims* d, const oob_layer_params* p, const float* x, const oob_head_ctx* ctx,
                       oob_bwd_scratch* s, float* dx, void* dx_planes, void* stream);
+/* `stream` waits for every weight-gradient kernel queued on the side stream so far (see oob_bwd_scratch) */
+int oob_side_join(void* stream);
+/* 0 = run everything on the caller's stream even when partials_side is set (profiling: clean per-kernel times) */
+int oob_side_stream_enable(int on);
 
 /* ==== inter-stage P2P over NVLink (csrc/p2p.cu) =================================================================
  * Replaces PipelineCommunication._send/_recv (pipeline.py:270-286) and everything built on them: one mailbox per

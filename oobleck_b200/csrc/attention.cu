@@ -149,7 +149,8 @@ attention_fwd_kernel(const bf16* __restrict__ qkv, long qkv_ps, float* __restric
   const uint32_t sQ = (smem_u32(sm_raw) + 1023u) & ~1023u, sK = sQ + ATILE, sV = sK + ATILE;
   const int E = H * AD;
   const long ld = 3L * E;
-  const int qt = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
+  // heaviest tiles (most keys under the causal mask) are dispatched first: grid = (H, B, tiles), z is the slowest index
+  const int qt = (int)(gridDim.z - 1 - blockIdx.z), h = blockIdx.x, b = blockIdx.y;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
   const int q0 = qt * AT;
   const bf16* base = qkv + (long)b * T * ld + h * AD;
@@ -261,7 +262,8 @@ attention_bwd_kv_kernel(const bf16* __restrict__ qkv, long qkv_ps, const bf16* _
   __shared__ float sLse[AT], sDel[AT];
   const int E = H * AD;
   const long ld = 3L * E;
-  const int kt = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
+  // key tile 0 sees every query tile: heaviest first (grid = (H, B, tiles), z is the slowest index)
+  const int kt = blockIdx.z, h = blockIdx.x, b = blockIdx.y;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
   const int k0 = kt * AT;
   const bf16* base = qkv + (long)b * T * ld + h * AD;
@@ -345,7 +347,8 @@ attention_bwd_q_kernel(const bf16* __restrict__ qkv, long qkv_ps, const bf16* __
   const uint32_t sQ = (smem_u32(sm_raw) + 1023u) & ~1023u, sdO = sQ + ATILE, sK = sdO + ATILE, sV = sK + ATILE;
   const int E = H * AD;
   const long ld = 3L * E;
-  const int qt = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
+  // heaviest tiles (most keys under the causal mask) are dispatched first: grid = (H, B, tiles), z is the slowest index
+  const int qt = (int)(gridDim.z - 1 - blockIdx.z), h = blockIdx.x, b = blockIdx.y;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
   const int q0 = qt * AT;
   const bf16* base = qkv + (long)b * T * ld + h * AD;
@@ -418,7 +421,7 @@ int attention_fwd(const bf16* qkv_planes, long qkv_plane_stride, float* out, bf1
     if (set_smem((const void*)attention_fwd_kernel, smem)) return -1;
     once = true;
   }
-  dim3 grid((T + AT - 1) / AT, H, B);
+  dim3 grid(H, B, (T + AT - 1) / AT);
   attention_fwd_kernel<<<grid, 128, smem, s>>>(qkv_planes, qkv_plane_stride, out, out_planes, plane_stride, nplanes, lse,
                                                T, H, 1.0f / sqrtf((float)D));
   OOB_CUDA_OK(cudaGetLastError());
@@ -444,7 +447,7 @@ int attention_bwd(const bf16* qkv_planes, long qkv_plane_stride, const float* ou
   attention_delta_kernel<<<(total + 7) / 8, 256, 0, s>>>(out, dout, delta, B, T, H);
   OOB_CUDA_OK(cudaGetLastError());
   count_launch();
-  dim3 grid((T + AT - 1) / AT, H, B);
+  dim3 grid(H, B, (T + AT - 1) / AT);
   const float scale = 1.0f / sqrtf((float)D);
   attention_bwd_kv_kernel<<<grid, 128, smem, s>>>(qkv_planes, qkv_plane_stride, dout_planes, dout_plane_stride, lse, delta,
                                                   dqkv, dqkv_planes, plane_stride, nplanes, T, H, scale);

@@ -15,6 +15,7 @@
 // No NCCL rendezvous per message, no host synchronisation: both kernels are ordinary stream work, so the copy
 // overlaps the 1F1B compute on the dedicated copy streams the host side gives them.
 #include "../../include/oobleck_b200.h"
+#include <cstdlib>
 #include <cstring>
 
 #include "kernels.h"
@@ -42,14 +43,29 @@ __device__ __forceinline__ void st_release_sys(unsigned* p, unsigned v) {
   asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
 
+// Watchdog: a spin that outlives this many ns (peer died before anyone called oob_p2p_abort, or a rendezvous bug)
+// sets the local abort word to 2 and gives up, so a lost neighbour can never wedge the GPU.  OOB_P2P_TIMEOUT_S.
+__device__ unsigned long long g_spin_timeout_ns = 120ull * 1000000000ull;
+
+__device__ __forceinline__ unsigned long long globaltimer_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+
 // wait until *word >= target (wrap-safe), or the local abort word is set
 __device__ __forceinline__ void spin_until(const unsigned* word, unsigned target, const unsigned* abort_word) {
   if (threadIdx.x == 0) {
     unsigned ns = 32;
+    const unsigned long long t0 = globaltimer_ns();
     while ((int)(ld_acquire_sys(word) - target) < 0) {
       if (ld_acquire_sys(abort_word)) break;
       __nanosleep(ns);
       if (ns < 1024) ns <<= 1;
+      else if (globaltimer_ns() - t0 > g_spin_timeout_ns) {
+        atomicExch(const_cast<unsigned*>(abort_word), 2u);
+        break;
+      }
     }
   }
   __syncthreads();
@@ -139,6 +155,17 @@ int oob_p2p_free(void* mailbox) {
   return 0;
 }
 
+static int apply_timeout_env() {
+  static bool done = false;
+  if (done) return 0;
+  done = true;
+  if (const char* e = getenv("OOB_P2P_TIMEOUT_S")) {
+    const unsigned long long ns = (unsigned long long)(atof(e) * 1e9);
+    if (ns > 0) OOB_CUDA_OK(cudaMemcpyToSymbol(g_spin_timeout_ns, &ns, sizeof(ns)));
+  }
+  return 0;
+}
+
 /* make every spinning kernel on this rank's mailbox give up (peer lost); callable from the listener thread */
 int oob_p2p_abort(void* mailbox, void* stream) {
   static const unsigned one = 1;
@@ -161,6 +188,7 @@ int oob_p2p_send(const void* src, long bytes, void* my_mailbox, void* peer_mailb
   int blocks = (int)((bytes / 16 + 256 * 4 - 1) / (256 * 4));
   blocks = blocks < 1 ? 1 : (blocks > 64 ? 64 : blocks);
   const int wait_ack = first && seq > (unsigned)nslots;
+  if (int rc = apply_timeout_env()) return rc;
   p2p_send_kernel<<<blocks, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
       reinterpret_cast<const char*>(src), dst, bytes, &mine->acks[slot], seq - (unsigned)nslots, wait_ack,
       last ? &peer->flags[slot] : nullptr, seq, &mine->counters[0], &mine->abort);
@@ -180,6 +208,7 @@ int oob_p2p_recv(void* dst, long bytes, void* my_mailbox, void* peer_mailbox, in
   const char* src = reinterpret_cast<const char*>(mine + 1) + (long)slot * slot_bytes + offset_in_slot;
   int blocks = (int)((bytes / 16 + 256 * 4 - 1) / (256 * 4));
   blocks = blocks < 1 ? 1 : (blocks > 64 ? 64 : blocks);
+  if (int rc = apply_timeout_env()) return rc;
   p2p_recv_kernel<<<blocks, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
       src, reinterpret_cast<char*>(dst), bytes, &mine->flags[slot], seq, first, last ? &peer->acks[slot] : nullptr,
       &mine->counters[1], &mine->abort);

@@ -3,6 +3,7 @@
 // reference's fx shards execute) and its autograd backward.
 #include "../../include/oobleck_b200.h"
 #include "kernels.h"
+#include <unordered_map>
 
 using namespace oob;
 
@@ -70,6 +71,52 @@ int linear_wgrad(const PlaneMat& a, const PlaneMat& dy, const oob_layer_params* 
   return gemm_launch(a, 1, dy, 1, gp, st);
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Side stream for weight gradients.  dgrad feeds the next kernel of the backward chain, wgrad (+ the bias column
+// sums) feeds nothing until the optimizer, and each persistent GEMM leaves SMs idle in its last wave (74 CTA pairs,
+// e.g. 104 tiles for an [M,1600] output = 2 waves at 70 %).  Launching the wgrad work on a second stream lets its
+// CTAs take the SMs a dgrad's short wave frees (and vice versa) -- CTA-granular work conservation by the hardware
+// scheduler, no change to any kernel.  Ordering is by events only:
+//   fork        main -> side before every side task (its inputs were produced on main)
+//   dyread      side -> main: the tasks reading this call's dy are done (the next call overwrites that buffer last)
+//   done[s]     side -> main: all side tasks of the call that used scratch `s` are done (next use of `s` waits)
+// Callers that set defer_join alternate two scratch sets and call oob_side_join() before anything else consumes
+// parameter gradients or recycles a ctx; without it every call joins before returning.
+struct SideState {
+  cudaStream_t side = nullptr;
+  cudaEvent_t fork = nullptr, dyread = nullptr, all = nullptr;
+  bool dyread_pending = false, any_pending = false;
+  std::unordered_map<const void*, cudaEvent_t> done;
+  int enabled = 1;
+};
+SideState g_side[16];
+
+SideState* side_state() {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 16) return nullptr;
+  SideState& ss = g_side[dev];
+  if (!ss.side) {
+    if (cudaStreamCreateWithFlags(&ss.side, cudaStreamNonBlocking) != cudaSuccess) return nullptr;
+    cudaEventCreateWithFlags(&ss.fork, cudaEventDisableTiming);
+    cudaEventCreateWithFlags(&ss.dyread, cudaEventDisableTiming);
+    cudaEventCreateWithFlags(&ss.all, cudaEventDisableTiming);
+  }
+  return &ss;
+}
+int side_fork(SideState* ss, cudaStream_t main) {
+  OOB_CUDA_OK(cudaEventRecord(ss->fork, main));
+  OOB_CUDA_OK(cudaStreamWaitEvent(ss->side, ss->fork, 0));
+  return 0;
+}
+int side_join_all(SideState* ss, cudaStream_t main) {
+  if (!ss || !ss->any_pending) return 0;
+  OOB_CUDA_OK(cudaEventRecord(ss->all, ss->side));
+  OOB_CUDA_OK(cudaStreamWaitEvent(main, ss->all, 0));
+  ss->any_pending = false;
+  ss->dyread_pending = false;
+  return 0;
+}
+
 int check_dims(const oob_dims* d) {
   OOB_CHECK(d->n_embd % 8 == 0, "n_embd must be a multiple of 8");
   OOB_CHECK(d->n_head > 0 && d->n_embd / d->n_head == 64 && d->n_embd % d->n_head == 0, "head_dim must be 64");
@@ -118,33 +165,77 @@ int oob_block_backward(const oob_dims* d, const oob_layer_params* p, const float
   const long ME = (long)M * E;
   const PlaneMat dyp = act_planes(dy_planes, M, E);
   int rc;
+  // weight-gradient work goes to the side stream when the caller provided its scratch (see SideState)
+  SideState* ss = s->partials_side ? side_state() : nullptr;
+  if (ss && !ss->enabled) {
+    if ((rc = side_join_all(ss, st))) return rc;
+    ss = nullptr;
+  }
+  cudaStream_t sw = ss ? ss->side : st;
+  float* wparts = ss ? s->partials_side : s->partials;
+  cudaEvent_t done_ev = nullptr;
+  if (ss) {
+    if (ss->dyread_pending) {   // the previous call's dy buffer may be this call's dx
+      OOB_CUDA_OK(cudaStreamWaitEvent(st, ss->dyread, 0));
+      ss->dyread_pending = false;
+    }
+    auto it = ss->done.find(s->dfc);
+    if (it == ss->done.end()) {
+      cudaEvent_t ev;
+      OOB_CUDA_OK(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+      it = ss->done.emplace((const void*)s->dfc, ev).first;
+    } else {
+      OOB_CUDA_OK(cudaStreamWaitEvent(st, it->second, 0));   // last user of this scratch has drained
+    }
+    done_ev = it->second;
+  }
+#define OOB_FORK() do { if (ss && (rc = side_fork(ss, st))) return rc; } while (0)
   // ---- MLP ----
+  OOB_FORK();   // dy is ready on main
+  if ((rc = linear_wgrad(act_planes(c->gelu_planes, M, 4 * E), dyp, p, o.proj2_w, M, E, 4 * E, ns, sw))) return rc;
+  if ((rc = colsum_accumulate(dy, E, M, E, p->g + o.proj2_b, wparts, sw))) return rc;
+  if (ss) { OOB_CUDA_OK(cudaEventRecord(ss->dyread, sw)); ss->dyread_pending = true; ss->any_pending = true; }
   // d(fc pre-activation) = (dy . Wp2^T) * gelu'(fc)
   if ((rc = linear_dgrad(dyp, p, o.proj2_w, M, E, 4 * E, ns, s->dfc, c->fc, (bf16*)s->dfc_planes, st))) return rc;
-  if ((rc = linear_wgrad(act_planes(c->gelu_planes, M, 4 * E), dyp, p, o.proj2_w, M, E, 4 * E, ns, st))) return rc;
-  if ((rc = colsum_accumulate(dy, E, M, E, p->g + o.proj2_b, s->partials, st))) return rc;
   const PlaneMat dfcp = act_planes(s->dfc_planes, M, 4 * E);
+  OOB_FORK();
+  if ((rc = linear_wgrad(act_planes(c->ln2_planes, M, E), dfcp, p, o.fc_w, M, 4 * E, E, ns, sw))) return rc;
+  if ((rc = colsum_accumulate(s->dfc, 4 * E, M, 4 * E, p->g + o.fc_b, wparts, sw))) return rc;
   if ((rc = linear_dgrad(dfcp, p, o.fc_w, M, 4 * E, E, ns, s->dln, nullptr, nullptr, st))) return rc;
-  if ((rc = linear_wgrad(act_planes(c->ln2_planes, M, E), dfcp, p, o.fc_w, M, 4 * E, E, ns, st))) return rc;
-  if ((rc = colsum_accumulate(s->dfc, 4 * E, M, 4 * E, p->g + o.fc_b, s->partials, st))) return rc;
   // dx2 = dy + LN2'(dln)
   if ((rc = layernorm_bwd(s->dln, c->x2, c->ln2_mean, c->ln2_rstd, p->w + o.ln2_w, dy, s->dx2, (bf16*)s->dx2_planes,
                           ME, 3, p->g + o.ln2_w, p->g + o.ln2_b, s->partials, M, E, st))) return rc;
   // ---- attention ----
   const PlaneMat dx2p = act_planes(s->dx2_planes, M, E);
+  OOB_FORK();
+  if ((rc = linear_wgrad(act_planes(c->att_planes, M, E), dx2p, p, o.proj_w, M, E, E, ns, sw))) return rc;
+  if ((rc = colsum_accumulate(s->dx2, E, M, E, p->g + o.proj_b, wparts, sw))) return rc;
   if ((rc = linear_dgrad(dx2p, p, o.proj_w, M, E, E, ns, s->datt, nullptr, (bf16*)s->datt_planes, st))) return rc;
-  if ((rc = linear_wgrad(act_planes(c->att_planes, M, E), dx2p, p, o.proj_w, M, E, E, ns, st))) return rc;
-  if ((rc = colsum_accumulate(s->dx2, E, M, E, p->g + o.proj_b, s->partials, st))) return rc;
   if ((rc = attention_bwd((const bf16*)c->qkv_planes, (long)M * 3 * E, c->att, s->datt, (const bf16*)s->datt_planes, ME,
                           c->lse, s->delta, s->dqkv, (bf16*)s->dqkv_planes, (long)M * 3 * E, 3, d->batch, d->seq,
                           d->n_head, 64, st))) return rc;
   const PlaneMat dqkvp = act_planes(s->dqkv_planes, M, 3 * E);
+  OOB_FORK();
+  if ((rc = linear_wgrad(act_planes(c->ln1_planes, M, E), dqkvp, p, o.attn_w, M, 3 * E, E, ns, sw))) return rc;
+  if ((rc = colsum_accumulate(s->dqkv, 3 * E, M, 3 * E, p->g + o.attn_b, wparts, sw))) return rc;
+  if (ss) OOB_CUDA_OK(cudaEventRecord(done_ev, sw));
   if ((rc = linear_dgrad(dqkvp, p, o.attn_w, M, 3 * E, E, ns, s->dln, nullptr, nullptr, st))) return rc;
-  if ((rc = linear_wgrad(act_planes(c->ln1_planes, M, E), dqkvp, p, o.attn_w, M, 3 * E, E, ns, st))) return rc;
-  if ((rc = colsum_accumulate(s->dqkv, 3 * E, M, 3 * E, p->g + o.attn_b, s->partials, st))) return rc;
   // dx = dx2 + LN1'(dln)
   if ((rc = layernorm_bwd(s->dln, x, c->ln1_mean, c->ln1_rstd, p->w + o.ln1_w, s->dx2, dx, (bf16*)dx_planes, ME, 3,
                           p->g + o.ln1_w, p->g + o.ln1_b, s->partials, M, E, st))) return rc;
+#undef OOB_FORK
+  if (ss && !s->defer_join) return side_join_all(ss, st);
+  return 0;
+}
+
+int oob_side_join(void* stream) {
+  return side_join_all(side_state(), reinterpret_cast<cudaStream_t>(stream));
+}
+
+int oob_side_stream_enable(int on) {
+  SideState* ss = side_state();
+  OOB_CHECK(ss != nullptr, "no CUDA device for the side stream");
+  ss->enabled = on ? 1 : 0;
   return 0;
 }
 

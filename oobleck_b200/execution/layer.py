@@ -44,14 +44,24 @@ class StageWorkspace:
         bf = dict(dtype=torch.bfloat16, device=device)
         lib = L.load()
         nparts = max(lib.oob_ln_bwd_partials_floats(E), lib.oob_colsum_partials_floats(4 * E))
-        self.t = {
-            "dfc": torch.empty(M, 4 * E, **f32), "dfc_planes": torch.empty(3, M, 4 * E, **bf),
-            "dln": torch.empty(M, E, **f32), "dx2": torch.empty(M, E, **f32), "dx2_planes": torch.empty(3, M, E, **bf),
-            "datt": torch.empty(M, E, **f32), "datt_planes": torch.empty(3, M, E, **bf), "delta": torch.empty(microbatch * n_head * seq, **f32),
-            "dqkv": torch.empty(M, 3 * E, **f32), "dqkv_planes": torch.empty(3, M, 3 * E, **bf),
-            "partials": torch.empty(nparts, **f32),
-        }
-        self.scratch = OobBwdScratch(**{k: v.data_ptr() for k, v in self.t.items()})
+        # Two scratch sets, alternated between consecutive layer backwards: the weight-gradient kernels of layer l run
+        # on the library's side stream while the main stream is already in layer l-1 (oob_bwd_scratch.defer_join).
+        self.sets, self.scratches = [], []
+        for _ in range(2):
+            t = {
+                "dfc": torch.empty(M, 4 * E, **f32), "dfc_planes": torch.empty(3, M, 4 * E, **bf),
+                "dln": torch.empty(M, E, **f32), "dx2": torch.empty(M, E, **f32),
+                "dx2_planes": torch.empty(3, M, E, **bf),
+                "datt": torch.empty(M, E, **f32), "datt_planes": torch.empty(3, M, E, **bf),
+                "delta": torch.empty(microbatch * n_head * seq, **f32),
+                "dqkv": torch.empty(M, 3 * E, **f32), "dqkv_planes": torch.empty(3, M, 3 * E, **bf),
+                "partials": torch.empty(nparts, **f32),
+                "partials_side": torch.empty(lib.oob_colsum_partials_floats(4 * E), **f32),
+            }
+            self.sets.append(t)
+            self.scratches.append(OobBwdScratch(defer_join=1, **{k: v.data_ptr() for k, v in t.items()}))
+        self.t, self.scratch = self.sets[0], self.scratches[0]
+        self._scratch_flip = 0
         self.dx = [torch.empty(M, E, **f32) for _ in range(2)]
         self.dx_planes = [torch.empty(3, M, E, **bf) for _ in range(2)]
         self.recv_planes = torch.empty(3, M, E, **bf)  # planes of a gradient received from the next stage
@@ -60,6 +70,14 @@ class StageWorkspace:
     def next_dx(self):
         self.flip ^= 1
         return self.dx[self.flip], self.dx_planes[self.flip]
+
+    def next_scratch(self) -> OobBwdScratch:
+        self._scratch_flip ^= 1
+        return self.scratches[self._scratch_flip]
+
+    def join(self) -> None:
+        """Main stream waits for the side stream's weight-gradient kernels (end of a backward pass)."""
+        L.call("oob_side_join", _stream())
 
 
 @dataclass
@@ -238,7 +256,7 @@ class Layer:
             hidden = inputs[0]
             dx, dxp = ws.next_dx()
             L.call("oob_head_backward", C.byref(self.dims), C.byref(p), C.c_void_p(hidden.data_ptr()),
-                   C.byref(self.ctx[buffer_id]), C.byref(ws.scratch), C.c_void_p(dx.data_ptr()),
+                   C.byref(self.ctx[buffer_id]), C.byref(ws.next_scratch()), C.c_void_p(dx.data_ptr()),
                    C.c_void_p(dxp.data_ptr()), _stream())
             return HiddenGrad(dx, dxp)
         assert grad is not None
@@ -255,7 +273,7 @@ class Layer:
                 dx, dxp = ws.next_dx()
             L.call("oob_block_backward", C.byref(self.dims), C.byref(p), C.c_void_p(hidden.data_ptr()),
                    C.byref(self.ctx[buffer_id]), C.c_void_p(grad.grad.data_ptr()), C.c_void_p(grad.planes.data_ptr()),
-                   C.byref(ws.scratch), C.c_void_p(dx.data_ptr()), C.c_void_p(dxp.data_ptr()), _stream())
+                   C.byref(ws.next_scratch()), C.c_void_p(dx.data_ptr()), C.c_void_p(dxp.data_ptr()), _stream())
             return HiddenGrad(dx, dxp)
         # embedding
         input_ids = inputs[0]

@@ -134,6 +134,9 @@ class PipelineExecution:
             grad = HiddenGrad(grad_tensors[0])
         for layer in reversed(self._layers):
             grad = layer.backward(buffer_id, grad)
+        ws = getattr(self._layers[0], "workspace", None)
+        if ws is not None and hasattr(ws, "join"):
+            ws.join()     # weight-gradient kernels run on a side stream; the ctx slot is recycled after this pass
         if grad is not None:
             # gradient w.r.t. the stage input: parked on the input tensor like autograd would (send_gradients reads
             # ``buffer.grad``, :395-401).  Copied out of the stage's ping-pong buffer because the transfer is async.

@@ -51,7 +51,8 @@ class OobBlockCtx(C.Structure):
 class OobBwdScratch(C.Structure):
     """``oob_bwd_scratch``."""
     _fields_ = [(n, C.c_void_p) for n in ["dfc", "dfc_planes", "dln", "dx2", "dx2_planes", "datt", "datt_planes", "delta", "dqkv",
-                                          "dqkv_planes", "partials"]]
+                                          "dqkv_planes", "partials", "partials_side"]] + \
+               [("defer_join", C.c_int), ("reserved_", C.c_int)]
 
 
 class OobHeadCtx(C.Structure):
@@ -87,6 +88,8 @@ _SIGNATURES = {
     "oob_head_forward": (_I, [C.POINTER(OobDims), C.POINTER(OobLayerParams), _P, _P, C.POINTER(OobHeadCtx), _P, _P]),
     "oob_head_backward": (_I, [C.POINTER(OobDims), C.POINTER(OobLayerParams), _P, C.POINTER(OobHeadCtx),
                                C.POINTER(OobBwdScratch), _P, _P, _P]),
+    "oob_side_join": (_I, [_P]),
+    "oob_side_stream_enable": (_I, [_I]),
     "oob_p2p_header_bytes": (C.c_long, []),
     "oob_p2p_alloc": (_I, [_L, C.POINTER(C.c_void_p), _P]),
     "oob_p2p_open": (_I, [_P, C.POINTER(C.c_void_p)]),
