@@ -10,8 +10,11 @@
  *   - every function returns 0 on success, <0 on error; oob_last_error() returns the message (thread local)
  *   - all data pointers are CUDA device pointers owned by the caller (torch tensors' data_ptr()); `stream` is a
  *     cudaStream_t passed as void*; nothing synchronises the device or allocates device memory
- *   - "planes" are the split-bf16 representation of an fp32 matrix: [nplanes][rows][ld] bf16 with
- *     x == p0 + p1 + p2 to 24 bits.  They are what the tcgen05 GEMMs consume; see DESIGN.md "Data layout".
+ *   - "planes" are the split 16-bit representation of an fp32 matrix, what the tcgen05 GEMMs consume
+ *     (DESIGN.md "Numerics"): [nplanes][rows][ld] 2-byte elements.  Planes 0-2 are bf16 with x == p0 + p1 + p2 to
+ *     24 bits (any range: gradients, everything in backward).  A 5-plane buffer additionally carries, as planes 3-4,
+ *     the fp16 pair x ~= h0 + 2^-11 h1 (22 bits, bounded range: weights and forward activations), which needs half
+ *     the tensor-core products; producers write all five when asked for nplanes = 5.
  */
 #ifndef OOBLECK_B200_H_
 #define OOBLECK_B200_H_
@@ -26,18 +29,20 @@ const char* oob_last_error(void);
  * tcgen05 GEMM launch between begin/end (events are recorded on the launching stream; end synchronises them) */
 long oob_launch_count(void);
 int oob_gemm_timing_begin(void);
-int oob_gemm_timing_end(double* total_ms, double* total_flops, long* launches);
+/* total_flops: algorithmic 2MNK; executed_flops: 2MNK x tensor-core products issued per MAC (1, 3 or 6) */
+int oob_gemm_timing_end(double* total_ms, double* total_flops, double* executed_flops, long* launches);
 /* sizes of the scratch buffers the reductions below need, in floats */
 long oob_ln_bwd_partials_floats(int n_embd);
 long oob_colsum_partials_floats(int cols);
 
 /* ---- split planes --------------------------------------------------------------------------------------- */
 typedef struct oob_planes {
-  const void* base;   /* bf16 [nplanes][rows][ld] */
+  const void* base;   /* [nplanes][rows][ld] 2-byte elements; first plane of the format named below */
   long rows, cols;    /* stored matrix shape */
   long ld;            /* row stride in elements, multiple of 8 */
   long plane_stride;  /* elements between planes, multiple of 8 */
   int nplanes;
+  int format;         /* 0: bf16 planes p0 p1 p2;  1: fp16 planes h0 h1 (base points at plane 3 of a 5-plane buffer) */
 } oob_planes;
 
 /* fp32 -> planes (flat); used for freshly initialised / received parameters (layer.py:26-37 init_tensors) */
@@ -46,7 +51,8 @@ int oob_split_planes(const float* x, void* planes, long n, long plane_stride, in
 /* ---- GEMM: replaces torch.addmm / F.linear inside HF Conv1D + lm_head and their autograd backward --------
  * D[M,N] = alpha * A.B (+bias) (+resid) (+D if accumulate), optional GELU / dGELU, fp32 and/or planes output.
  * a_mn_major = 0: A stored [M,K];  1: A stored [K,M].   b_mn_major = 0: B stored [N,K];  1: B stored [K,N].
- * nsplit = 1|2|3 planes per operand (3 = fp32-grade, the parity mode). */
+ * nsplit = 1|2|3 planes per operand: fp32-grade is 3 for bf16 planes (6 products) and 2 for fp16 planes (3 products).
+ * Both operands must have the same format unless nsplit = 1. */
 typedef struct oob_gemm_epilogue {
   float* d; long ldd;
   const float* bias;
@@ -54,7 +60,7 @@ typedef struct oob_gemm_epilogue {
   int accumulate;
   int act;                 /* 0 none, 1 GELU(new): d=pre-activation, planes=gelu;  2 dGELU: value*=gelu'(aux) */
   const float* aux; long ldaux;
-  void* planes; long ldp; long plane_stride; int nplanes_out;
+  void* planes; long ldp; long plane_stride; int nplanes_out;   /* 1..3, or 5 (bf16 x 3 + fp16 x 2) */
   float alpha;
 } oob_gemm_epilogue;
 
@@ -109,11 +115,13 @@ typedef struct oob_dims {
   int n_embd, n_head;      /* head_dim = n_embd / n_head must be 64 */
   int vocab, vocab_padded; /* vocab_padded: row stride of logits buffers, multiple of 64 */
   float ln_eps;
-  int nsplit;              /* planes per GEMM operand: 3 = fp32-grade (parity), 2, 1 */
+  int nsplit;              /* bf16 planes per GEMM operand: 3 = fp32-grade (parity), 2, 1 */
+  int fwd_fp16;            /* 1 (needs nsplit = 3): forward GEMMs read the fp16 x 2 planes -- every activation / weight
+                              plane buffer marked [5] below must then have 5 planes; 0: 3-plane buffers, bf16 only */
 } oob_dims;
 
 /* parameters of one stage layer: flat fp32 vector in HF ``layer.parameters()`` order (what FSDP's FlatParamHandle
- * flattens, layer.py:96-111), its split planes [3][plane_stride] and the flat fp32 gradient (accumulated). */
+ * flattens, layer.py:96-111), its split planes [3 or 5][plane_stride] and the flat fp32 gradient (accumulated). */
 typedef struct oob_layer_params {
   const float* w;
   const void* w_planes;
@@ -122,12 +130,12 @@ typedef struct oob_layer_params {
 } oob_layer_params;
 
 typedef struct oob_block_ctx {      /* saved activations of one micro-batch through one GPT2Block */
-  void* ln1_planes;  float* ln1_mean; float* ln1_rstd;   /* [3][M][E], [M], [M] */
+  void* ln1_planes;  float* ln1_mean; float* ln1_rstd;   /* [3|5][M][E], [M], [M] */
   void* qkv_planes;                                      /* [3][M][3E] q|k|v split planes */
-  float* att; void* att_planes; float* lse;              /* [M,E], [3][M][E], [B,H,T] */
+  float* att; void* att_planes; float* lse;              /* [M,E], [3|5][M][E], [B,H,T] */
   float* x2;                                             /* [M,E] hidden after the attention residual */
-  void* ln2_planes;  float* ln2_mean; float* ln2_rstd;
-  float* fc; void* gelu_planes;                          /* [M,4E] pre-activation, [3][M][4E] */
+  void* ln2_planes;  float* ln2_mean; float* ln2_rstd;   /* [3|5][M][E] */
+  float* fc; void* gelu_planes;                          /* [M,4E] pre-activation, [3|5][M][4E] */
 } oob_block_ctx;
 
 typedef struct oob_bwd_scratch {    /* per-stage backward temporaries, reused by every layer / micro-batch */
@@ -148,7 +156,7 @@ typedef struct oob_bwd_scratch {    /* per-stage backward temporaries, reused by
 } oob_bwd_scratch;
 
 typedef struct oob_head_ctx {       /* ln_f + lm_head + loss for one micro-batch */
-  void* lnf_planes; float* mean; float* rstd;            /* [3][M][E], [M], [M] */
+  void* lnf_planes; float* mean; float* rstd;            /* [3|5][M][E], [M], [M] */
   float* logits;                                         /* [M, vocab_padded] */
   void* dlogits_planes;                                  /* [3][M][vocab_padded] */
   float* row_loss;                                       /* [M] */

@@ -138,6 +138,13 @@ __device__ __forceinline__ void store_pair(float* f32, bf16* planes, long plane_
     *reinterpret_cast<uint32_t*>(planes + off) = p0;
     if (nplanes > 1) *reinterpret_cast<uint32_t*>(planes + plane_stride + off) = p1;
     if (nplanes > 2) *reinterpret_cast<uint32_t*>(planes + 2 * plane_stride + off) = p2;
+    if (nplanes == 5) {   // fp16 x 2 planes for the forward proj GEMM
+      uint16_t a0, a1, c0, c1;
+      split_h2(a, a0, a1);
+      split_h2(c, c0, c1);
+      *reinterpret_cast<uint32_t*>(planes + 3 * plane_stride + off) = (uint32_t)a0 | ((uint32_t)c0 << 16);
+      *reinterpret_cast<uint32_t*>(planes + 4 * plane_stride + off) = (uint32_t)a1 | ((uint32_t)c1 << 16);
+    }
   }
 }
 

@@ -22,7 +22,8 @@ using namespace oob;
 
 static inline cudaStream_t S(void* s) { return reinterpret_cast<cudaStream_t>(s); }
 static inline PlaneMat PM(const oob_planes* p) {
-  return PlaneMat{reinterpret_cast<const bf16*>(p->base), p->rows, p->cols, p->ld, p->plane_stride, p->nplanes};
+  return PlaneMat{reinterpret_cast<const bf16*>(p->base), p->rows, p->cols, p->ld, p->plane_stride, p->nplanes,
+                  p->format};
 }
 
 extern "C" {
@@ -30,8 +31,8 @@ extern "C" {
 int oob_version(void) { return 100; }
 long oob_launch_count(void) { return g_launches.load(); }
 int oob_gemm_timing_begin(void) { return gemm_timing_begin(); }
-int oob_gemm_timing_end(double* total_ms, double* total_flops, long* launches) {
-  return gemm_timing_end(total_ms, total_flops, launches);
+int oob_gemm_timing_end(double* total_ms, double* total_flops, double* executed_flops, long* launches) {
+  return gemm_timing_end(total_ms, total_flops, executed_flops, launches);
 }
 const char* oob_last_error(void) { return g_err; }
 long oob_ln_bwd_partials_floats(int n_embd) { return (long)LN_BWD_MAX_GRID * 2 * n_embd; }

@@ -46,15 +46,51 @@ __device__ __forceinline__ void split3(float x, bf16& p0, bf16& p1, bf16& p2) {
   p2 = __float2bfloat16_rn(r);
 }
 
+// Second operand format: TWO fp16 planes, x ~= h0 + 2^-11 * h1 with h0 = fp16(x), h1 = fp16((x - h0) * 2^11).
+// 22 significand bits (fp16 carries 11 per plane; the residual is pre-scaled so it never falls into fp16 subnormals
+// before x itself is below ~2^-14), so the three products h0g0 + 2^-11 (h0g1 + h1g0) are fp32-grade at half the
+// tensor work of the six bf16 products.  fp16 has a 5-bit exponent: only tensors with a bounded range use it
+// (weights, LayerNorm / GELU / attention outputs -- the forward operands); gradients stay in bf16 x 3.
+// Conversions saturate (no inf) so an outlier degrades precision instead of poisoning the GEMM.
+constexpr float H1_SCALE = 2048.f;
+constexpr float H1_INV_SCALE = 1.f / 2048.f;
+__device__ __forceinline__ uint16_t f2h_sat(float x) {
+  uint16_t h;
+  asm("cvt.rn.satfinite.f16.f32 %0, %1;" : "=h"(h) : "f"(x));
+  return h;
+}
+__device__ __forceinline__ float h2f(uint16_t h) {
+  float f;
+  asm("cvt.f32.f16 %0, %1;" : "=f"(f) : "h"(h));
+  return f;
+}
+__device__ __forceinline__ void split_h2(float x, uint16_t& h0, uint16_t& h1) {
+  h0 = f2h_sat(x);
+  h1 = f2h_sat((x - h2f(h0)) * H1_SCALE);
+}
+// raw 16-bit patterns of all five planes of a "5-plane" buffer: [bf16 p0 p1 p2 | fp16 h0 h1]
+__device__ __forceinline__ void split5(float x, uint16_t& q0, uint16_t& q1, uint16_t& q2, uint16_t& q3, uint16_t& q4) {
+  bf16 a, b, c;
+  split3(x, a, b, c);
+  q0 = __bfloat16_as_ushort(a); q1 = __bfloat16_as_ushort(b); q2 = __bfloat16_as_ushort(c);
+  split_h2(x, q3, q4);
+}
+
+// tanh(u) = 1 - 2 / (1 + e^{2u}) on the SFU (ex2 + rcp, ~2 ulp each; saturates correctly at +-inf).  The libm
+// tanhf is ~40 instructions with a branch; the GEMM epilogues evaluate it for every FC element and their code has
+// to stay small enough for the instruction cache (profiles/README.md, epilogue section).
+__device__ __forceinline__ float tanh_fast(float u) {
+  return 1.0f - __fdividef(2.0f, 1.0f + __expf(2.0f * u));
+}
 __device__ __forceinline__ float gelu_new_f(float x) {
   const float k0 = 0.7978845608028654f, k1 = 0.044715f;
   float u = k0 * (x + k1 * x * x * x);
-  return 0.5f * x * (1.0f + tanhf(u));
+  return 0.5f * x * (1.0f + tanh_fast(u));
 }
 __device__ __forceinline__ float gelu_new_grad_f(float x) {
   const float k0 = 0.7978845608028654f, k1 = 0.044715f;
   float u = k0 * (x + k1 * x * x * x);
-  float t = tanhf(u);
+  float t = tanh_fast(u);
   return 0.5f * (1.0f + t) + 0.5f * x * (1.0f - t * t) * k0 * (1.0f + 3.0f * k1 * x * x);
 }
 
@@ -182,17 +218,20 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t lbo_
   d |= swizzle << 61;
   return d;
 }
-// Instruction descriptor for kind::f16 with bf16 inputs and fp32 accumulation (cute::UMMA::InstrDescriptor)
-__host__ __device__ constexpr uint32_t make_idesc_bf16(int M, int N, int a_mn_major, int b_mn_major) {
+// Instruction descriptor for kind::f16 with fp32 accumulation (cute::UMMA::InstrDescriptor); operand formats:
+// 1 = BF16, 0 = F16 (independent fields for A and B)
+__host__ __device__ constexpr uint32_t make_idesc_f16kind(int M, int N, int a_mn_major, int b_mn_major,
+                                                          int a_bf16 = 1, int b_bf16 = 1) {
   return (1u << 4)                       // c_format  = F32
-         | (1u << 7)                     // a_format  = BF16
-         | (1u << 10)                    // b_format  = BF16
+         | ((uint32_t)a_bf16 << 7)       // a_format
+         | ((uint32_t)b_bf16 << 10)      // b_format
          | ((uint32_t)a_mn_major << 15)  // a_major   (0 = K-major, 1 = MN-major)
          | ((uint32_t)b_mn_major << 16)  // b_major
          | ((uint32_t)(N >> 3) << 17)    // n_dim
          | ((uint32_t)(M >> 4) << 24);   // m_dim
 }
 
+__device__ __forceinline__ void prefetch_l1(const void* p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
 // 128-bit streaming global accesses
 __device__ __forceinline__ float4 ldg_f4(const float* p) { return *reinterpret_cast<const float4*>(p); }
 __device__ __forceinline__ void stg_f4(float* p, float4 v) { *reinterpret_cast<float4*>(p) = v; }

@@ -19,15 +19,17 @@ __global__ void split_kernel(const float* __restrict__ x, bf16* __restrict__ pla
     } else {
       for (int j = 0; j < 4; ++j) v[j] = (i + j < n) ? x[i + j] : 0.f;
     }
-    bf16 q[3][4];
+    uint16_t q[5][4];
 #pragma unroll
-    for (int j = 0; j < 4; ++j) split3(v[j], q[0][j], q[1][j], q[2][j]);
-    for (int p = 0; p < nplanes; ++p) {
-      bf16* dst = planes + p * plane_stride + i;
+    for (int j = 0; j < 4; ++j) split5(v[j], q[0][j], q[1][j], q[2][j], q[3][j], q[4][j]);
+#pragma unroll
+    for (int p = 0; p < 5; ++p) {
+      if (p >= nplanes) break;
+      uint16_t* dst = reinterpret_cast<uint16_t*>(planes) + p * plane_stride + i;
       if (i + 4 <= n) {
         uint2 w;
-        w.x = (uint32_t)__bfloat16_as_ushort(q[p][0]) | ((uint32_t)__bfloat16_as_ushort(q[p][1]) << 16);
-        w.y = (uint32_t)__bfloat16_as_ushort(q[p][2]) | ((uint32_t)__bfloat16_as_ushort(q[p][3]) << 16);
+        w.x = (uint32_t)q[p][0] | ((uint32_t)q[p][1] << 16);
+        w.y = (uint32_t)q[p][2] | ((uint32_t)q[p][3] << 16);
         *reinterpret_cast<uint2*>(dst) = w;
       } else {
         for (int j = 0; j < 4 && i + j < n; ++j) dst[j] = q[p][j];
@@ -97,15 +99,15 @@ layernorm_fwd_kernel(const float* __restrict__ x, const float* __restrict__ gamm
                     (v[i].w - mu) * rs * g.w + b.w};
       if (y) stg_f4(y + (long)row * E + c * 4, make_float4(o[0], o[1], o[2], o[3]));
       if (planes) {
-        bf16 pq[3][4];
+        uint16_t pq[5][4];
 #pragma unroll
-        for (int j = 0; j < 4; ++j) split3(o[j], pq[0][j], pq[1][j], pq[2][j]);
+        for (int j = 0; j < 4; ++j) split5(o[j], pq[0][j], pq[1][j], pq[2][j], pq[3][j], pq[4][j]);
 #pragma unroll
-        for (int p = 0; p < 3; ++p) {
+        for (int p = 0; p < 5; ++p) {
           if (p < nplanes) {
             uint2 w;
-            w.x = (uint32_t)__bfloat16_as_ushort(pq[p][0]) | ((uint32_t)__bfloat16_as_ushort(pq[p][1]) << 16);
-            w.y = (uint32_t)__bfloat16_as_ushort(pq[p][2]) | ((uint32_t)__bfloat16_as_ushort(pq[p][3]) << 16);
+            w.x = (uint32_t)pq[p][0] | ((uint32_t)pq[p][1] << 16);
+            w.y = (uint32_t)pq[p][2] | ((uint32_t)pq[p][3] << 16);
             *reinterpret_cast<uint2*>(planes + p * plane_stride + (long)row * E + c * 4) = w;
           }
         }
@@ -496,15 +498,17 @@ __global__ void adamw_kernel(float* __restrict__ p, const float* __restrict__ g,
       for (int j = 0; j < 4 && i + j < n; ++j) { p[i + j] = pv[j]; m[i + j] = mv[j]; v[i + j] = vv[j]; }
     }
     if (planes) {
-      bf16 q[3][4];
+      uint16_t q[5][4];
 #pragma unroll
-      for (int j = 0; j < 4; ++j) split3(pv[j], q[0][j], q[1][j], q[2][j]);
-      for (int pl = 0; pl < nplanes; ++pl) {
-        bf16* dst = planes + pl * plane_stride + i;
+      for (int j = 0; j < 4; ++j) split5(pv[j], q[0][j], q[1][j], q[2][j], q[3][j], q[4][j]);
+#pragma unroll
+      for (int pl = 0; pl < 5; ++pl) {
+        if (pl >= nplanes) break;
+        uint16_t* dst = reinterpret_cast<uint16_t*>(planes) + pl * plane_stride + i;
         if (full) {
           uint2 w;
-          w.x = (uint32_t)__bfloat16_as_ushort(q[pl][0]) | ((uint32_t)__bfloat16_as_ushort(q[pl][1]) << 16);
-          w.y = (uint32_t)__bfloat16_as_ushort(q[pl][2]) | ((uint32_t)__bfloat16_as_ushort(q[pl][3]) << 16);
+          w.x = (uint32_t)q[pl][0] | ((uint32_t)q[pl][1] << 16);
+          w.y = (uint32_t)q[pl][2] | ((uint32_t)q[pl][3] << 16);
           *reinterpret_cast<uint2*>(dst) = w;
         } else {
           for (int j = 0; j < 4 && i + j < n; ++j) dst[j] = q[pl][j];

@@ -48,7 +48,7 @@ static int make_map(CUtensorMap* m, const PlaneMat& a, int box_rows, int box_pla
 }
 
 // ---- optional CUDA-event timing of every launch (roofline measurement) ----------------------------------------
-struct TimedLaunch { cudaEvent_t a, b; double flops; };
+struct TimedLaunch { cudaEvent_t a, b; double flops; double executed; };
 static bool g_timing = false;
 static std::vector<TimedLaunch> g_timed;
 static std::vector<cudaEvent_t> g_event_pool;
@@ -57,25 +57,26 @@ static cudaEvent_t get_event() {
   cudaEvent_t e; cudaEventCreate(&e); return e;
 }
 int gemm_timing_begin() { g_timed.clear(); g_timing = true; return 0; }
-int gemm_timing_end(double* total_ms, double* total_flops, long* launches) {
+int gemm_timing_end(double* total_ms, double* total_flops, double* executed_flops, long* launches) {
   g_timing = false;
-  double ms = 0, fl = 0;
+  double ms = 0, fl = 0, ex = 0;
   for (auto& t : g_timed) {
     OOB_CUDA_OK(cudaEventSynchronize(t.b));
     float x = 0;
     OOB_CUDA_OK(cudaEventElapsedTime(&x, t.a, t.b));
-    ms += x; fl += t.flops;
+    ms += x; fl += t.flops; ex += t.executed;
     g_event_pool.push_back(t.a); g_event_pool.push_back(t.b);
   }
   if (total_ms) *total_ms = ms;
   if (total_flops) *total_flops = fl;
+  if (executed_flops) *executed_flops = ex;
   if (launches) *launches = (long)g_timed.size();
   g_timed.clear();
   return 0;
 }
 
 template <int BN, bool A_MN, bool B_MN, bool TWO_CTA, int BK>
-static int launchp_t(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, cudaStream_t stream) {
+static int launchp_t(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p_in, cudaStream_t stream) {
   static int max_smem = -1, num_sms = 0;
   if (max_smem < 0) {
     int dev = 0;
@@ -89,8 +90,16 @@ static int launchp_t(const CUtensorMap& ta, const CUtensorMap& tb, const GemmPar
     OOB_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
     attr_set = true;
   }
+  GemmParams p = p_in;
   const int stage = gemmp_stage_bytes<BN, TWO_CTA, BK>(p.nsplit);
-  const int overhead = 1024 + 256;
+  // epilogue transposition tiles: 4 warps x 32 rows x slab fp32; 32-column slabs (full 128-B lines per store) unless
+  // they would cost a ring stage
+  int overhead = 1024 + 256 + 4 * 32 * 32 * 4;
+  p.slab = 32;
+  if ((max_smem - overhead) / stage < (max_smem - (overhead - 4 * 32 * 16 * 4)) / stage) {
+    overhead -= 4 * 32 * 16 * 4;
+    p.slab = 16;
+  }
   int stages = (max_smem - overhead) / stage;
   if (stages > 10) stages = 10;
   OOB_CHECK(stages >= 2, "persistent GEMM tile does not fit %d B of shared memory", max_smem);
@@ -111,7 +120,8 @@ static int launchp_t(const CUtensorMap& ta, const CUtensorMap& tb, const GemmPar
   cfg.attrs = attr;
   cfg.numAttrs = 1;
   TimedLaunch tl{};
-  if (g_timing) { tl.a = get_event(); tl.b = get_event(); tl.flops = 2.0 * p.M * p.N * p.K; cudaEventRecord(tl.a, stream); }
+  if (g_timing) { tl.a = get_event(); tl.b = get_event(); tl.flops = 2.0 * p.M * p.N * p.K;
+    tl.executed = tl.flops * (p.nsplit == 1 ? 1 : (p.nsplit == 2 ? 3 : 6)); cudaEventRecord(tl.a, stream); }
   OOB_CUDA_OK(cudaLaunchKernelEx(&cfg, kern, ta, tb, p, stages));
   if (g_timing) { cudaEventRecord(tl.b, stream); g_timed.push_back(tl); }
   count_launch();
@@ -126,6 +136,26 @@ int gemm_launch(const PlaneMat& A, int a_mn, const PlaneMat& B, int b_mn, const 
   p.debug = env_debug;
   OOB_CHECK(p.nsplit >= 1 && p.nsplit <= 3, "nsplit must be 1..3");
   OOB_CHECK(p.M > 0 && p.N > 0 && p.K > 0, "empty GEMM %d x %d x %d", p.M, p.N, p.K);
+  // operand formats: bf16 x (1..3) planes, or fp16 x (1..2) planes with the second plane pre-scaled by 2^11.  A and B
+  // formats are independent fields of the instruction descriptor, but the two correction products of a mixed pair
+  // would need different weights, so mixed operands are single-plane only.
+  p.a_bf16 = A.fp16 ? 0 : 1;
+  p.b_bf16 = B.fp16 ? 0 : 1;
+  p.corr_scale = 1.0f;
+  if (A.fp16 || B.fp16) {
+    OOB_CHECK(p.nsplit <= 2, "fp16 planes come in pairs: nsplit must be 1 or 2");
+    OOB_CHECK(A.fp16 == B.fp16 || p.nsplit == 1, "mixed fp16 / bf16 operands are supported for nsplit = 1 only");
+    if (p.nsplit == 2) p.corr_scale = 1.0f / 2048.0f;
+  }
+  OOB_CHECK(A.nplanes >= p.nsplit && B.nplanes >= p.nsplit, "operands carry fewer planes than nsplit");
+  {
+    GemmEpilogue& e = p.epi;
+    auto ok16 = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15) == 0; };
+    e.vec4 = (!e.d || (ok16(e.d) && (e.ldd & 3) == 0)) && (!e.bias || ok16(e.bias)) &&
+             (!e.resid || (ok16(e.resid) && (e.ldr & 3) == 0)) && (!e.aux || (ok16(e.aux) && (e.ldaux & 3) == 0)) &&
+             (!e.planes || ((reinterpret_cast<uintptr_t>(e.planes) & 7) == 0 && (e.ldp & 3) == 0 &&
+                            (e.plane_stride & 3) == 0));
+  }
   constexpr int BN = 128;
   // kernel selection (measured on B200, profiles/r01_gemm_sweep*.log): persistent 2-CTA pair tiles with BK = 64 win on
   // every GPT-2 shape (1-CTA: -15 %, BK = 32 / SWIZZLE_64B: -12 %).  Env vars select the variants for experiments.

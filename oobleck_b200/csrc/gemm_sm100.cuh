@@ -39,14 +39,18 @@ struct GemmEpilogue {
   bf16* planes;         // split output [nplanes_out][M][ldp] or null
   long ldp;
   long plane_stride;
-  int nplanes_out;
+  int nplanes_out;      // 1..3 bf16 planes; 5 = three bf16 planes followed by the two fp16 planes (common.cuh)
   float alpha;          // value = alpha * acc (before bias etc.)
+  int vec4;             // set by gemm_launch: every pointer / stride above allows 16-B (fp32) and 8-B (plane) accesses
 };
 
 struct GemmParams {
   int M, N, K;
   int nsplit;   // planes used from each operand (1..3)
   GemmEpilogue epi;
+  int a_bf16, b_bf16;   // operand element formats (1 = bf16 planes, 0 = fp16 planes); set by gemm_launch
+  float corr_scale;     // weight of the correction accumulator (2^-11 for fp16 x 2 planes, else 1); gemm_launch
+  int slab;     // epilogue transposition slab: 32 columns when the smem budget allows, else 16; set by the launcher
   int chunk_kb; // promotion chunk in k-blocks (0 = default GEMM_CHUNK_KB)
   int debug;    // diagnostics (tools/gemm_sweep.py, persistent kernel): 1 skip output stores, 2 skip TMA, 4 skip MMAs
 };
@@ -118,80 +122,162 @@ __device__ __forceinline__ void umma_any<false>(uint32_t td, uint64_t da, uint64
   umma_bf16(td, da, db, idesc, acc);
 }
 
-// Fused epilogue for 32 consecutive columns of one output row held in registers.
-__device__ __forceinline__ void epilogue_store32(float (&x)[32], const GemmEpilogue& e, int row, int col0, int N) {
-  const bool full = (col0 + 32 <= N);
+// Fused epilogue for a slab of SLAB consecutive columns of the warp's 32 output rows.
+//
+// After tcgen05.ld each thread holds ONE row (TMEM lane) -- storing from that layout makes every warp store touch 32
+// different 128-B lines with 16 B each (measured: the forward-FC epilogue, 14 B/element, ran at ~1 TB/s and took
+// longer than the whole 3-product main loop; profiles/r01_gemm_sweep8_fp16.log).  So the slab is first transposed
+// through a small XOR-swizzled shared-memory tile (conflict-free both ways): afterwards SLAB/4 adjacent lanes own 4
+// consecutive columns each of the same row, and every global access of the epilogue -- bias / residual / dGELU aux /
+// accumulate loads, fp32 stores, plane stores -- is a run of full 32-B sectors (128-B lines for SLAB = 32).
+template <int SLAB>
+__device__ __forceinline__ uint32_t slab_swz(int row) {
+  return SLAB == 32 ? (uint32_t)(row & 7) : (uint32_t)((row >> 1) & 3);
+}
+
+__device__ __forceinline__ uint32_t pack_bf16x2(bf16 lo, bf16 hi) {
+  return (uint32_t)__bfloat16_as_ushort(lo) | ((uint32_t)__bfloat16_as_ushort(hi) << 16);
+}
+
+// Second half of a slab: reads the transposed tile back and does all global traffic.  Deliberately NOT inlined and not
+// unrolled: it is called once per slab from the (necessarily unrolled, the accumulators are registers) slab loop, and
+// the first version that inlined it grew the kernel to 123k SASS instructions -- instruction-fetch bound, every GEMM
+// 60 % slower (profiles/r01_gemm_sweep9_coalesced_epilogue.log).
+template <int SLAB>
+__device__ __noinline__ void epilogue_rows(const float* stage, const GemmEpilogue& ep, int row0, int col0, int M, int N,
+                                           int lane) {
+  constexpr int C = SLAB / 4;     // 16-B chunks per row
+  constexpr int RPI = 32 / C;     // rows covered by one warp-wide access
+  // The descriptor lives in param space behind a generic reference: copy what the loop needs into registers once, or
+  // every field is re-loaded after every global store (possible aliasing) and the loop becomes one dependent chain.
+  float* const d = ep.d;
+  const float* const bias = ep.bias;
+  const float* const resid = ep.resid;
+  const float* const aux = ep.aux;
+  uint16_t* const planes = reinterpret_cast<uint16_t*>(ep.planes);
+  const long ldd = ep.ldd, ldr = ep.ldr, ldaux = ep.ldaux, ldp = ep.ldp, pstride = ep.plane_stride;
+  const int accumulate = ep.accumulate, act = ep.act, nplanes_out = ep.nplanes_out;
+  const float alpha = ep.alpha;
+
+  const int cl = lane % C, rl = lane / C;
+  const int gcol = col0 + 4 * cl;
+  if (gcol >= N) return;
+  const bool vec = ep.vec4 && (gcol + 4 <= N);
+  if (!vec) {   // ragged / unaligned edge: plain per-element code, correctness only
+#pragma unroll 1
+    for (int q = 0; q < C; ++q) {
+      const int rr = q * RPI + rl;
+      const long grow = row0 + rr;
+      if (grow >= M) break;
+      const float* src = stage + rr * SLAB + 4 * (cl ^ slab_swz<SLAB>(rr));
+#pragma unroll 1
+      for (int j = 0; j < 4; ++j) {
+        if (gcol + j >= N) break;
+        float y = src[j] * alpha;
+        if (bias) y += bias[gcol + j];
+        if (resid) y += resid[grow * ldr + gcol + j];
+        if (accumulate) y += d[grow * ldd + gcol + j];
+        if (act == ACT_DGELU) y *= gelu_new_grad_f(aux[grow * ldaux + gcol + j]);
+        if (d) d[grow * ldd + gcol + j] = y;
+        if (planes) {
+          if (act == ACT_GELU) y = gelu_new_f(y);
+          uint16_t w[5];
+          split5(y, w[0], w[1], w[2], w[3], w[4]);
 #pragma unroll
-  for (int j = 0; j < 32; ++j) x[j] *= e.alpha;
-  if (e.bias) {
-#pragma unroll
-    for (int j = 0; j < 32; ++j)
-      if (full || col0 + j < N) x[j] += __ldg(e.bias + col0 + j);
-  }
-  if (e.resid) {
-    const float* r = e.resid + (long)row * e.ldr + col0;
-#pragma unroll
-    for (int j = 0; j < 32; ++j)
-      if (full || col0 + j < N) x[j] += r[j];
-  }
-  if (e.accumulate) {
-    const float* dprev = e.d + (long)row * e.ldd + col0;
-#pragma unroll
-    for (int j = 0; j < 32; ++j)
-      if (full || col0 + j < N) x[j] += dprev[j];
-  }
-  if (e.act == ACT_DGELU) {
-    const float* a = e.aux + (long)row * e.ldaux + col0;
-#pragma unroll
-    for (int j = 0; j < 32; ++j)
-      if (full || col0 + j < N) x[j] *= gelu_new_grad_f(a[j]);
-  }
-  if (e.d) {
-    float* dp = e.d + (long)row * e.ldd + col0;
-    if (full && ((reinterpret_cast<uintptr_t>(dp) & 15) == 0)) {
-#pragma unroll
-      for (int j = 0; j < 32; j += 4) stg_f4(dp + j, make_float4(x[j], x[j + 1], x[j + 2], x[j + 3]));
-    } else {
-#pragma unroll
-      for (int j = 0; j < 32; ++j)
-        if (col0 + j < N) dp[j] = x[j];
-    }
-  }
-  if (e.planes) {
-    if (e.act == ACT_GELU) {
-#pragma unroll
-      for (int j = 0; j < 32; ++j) x[j] = gelu_new_f(x[j]);
-    }
-    // pack the split planes two bf16 per 32-bit word so the stores stay in registers
-    uint32_t w[3][16];
-#pragma unroll
-    for (int j = 0; j < 32; j += 2) {
-      bf16 a0, a1, a2, b0, b1, b2;
-      split3(x[j], a0, a1, a2);
-      split3(x[j + 1], b0, b1, b2);
-      w[0][j >> 1] = (uint32_t)__bfloat16_as_ushort(a0) | ((uint32_t)__bfloat16_as_ushort(b0) << 16);
-      w[1][j >> 1] = (uint32_t)__bfloat16_as_ushort(a1) | ((uint32_t)__bfloat16_as_ushort(b1) << 16);
-      w[2][j >> 1] = (uint32_t)__bfloat16_as_ushort(a2) | ((uint32_t)__bfloat16_as_ushort(b2) << 16);
-    }
-    bf16* pp = e.planes + (long)row * e.ldp + col0;
-    const bool vec = full && ((reinterpret_cast<uintptr_t>(pp) & 15) == 0) && ((e.plane_stride & 7) == 0);
-#pragma unroll
-    for (int pl = 0; pl < 3; ++pl) {
-      if (pl < e.nplanes_out) {
-        bf16* dst = pp + (long)pl * e.plane_stride;
-        if (vec) {
-#pragma unroll
-          for (int j = 0; j < 16; j += 4)
-            *reinterpret_cast<uint4*>(dst + 2 * j) = make_uint4(w[pl][j], w[pl][j + 1], w[pl][j + 2], w[pl][j + 3]);
-        } else {
-#pragma unroll
-          for (int j = 0; j < 32; ++j)
-            if (col0 + j < N)
-              dst[j] = __ushort_as_bfloat16((unsigned short)((w[pl][j >> 1] >> ((j & 1) * 16)) & 0xFFFF));
+          for (int pl = 0; pl < 5; ++pl)
+            if (pl < nplanes_out) planes[pl * pstride + grow * ldp + gcol + j] = w[pl];
         }
       }
     }
+    return;
   }
+  float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (bias) b = ldg_f4(bias + gcol);
+  const bool has_r = resid != nullptr, has_acc = accumulate != 0, has_aux = act == ACT_DGELU;
+  // software pipeline, depth 1: the global loads of row-chunk q+1 are in flight while q is computed and stored (one
+  // epilogue warp per scheduler: nobody else hides the latency).  The loop body is NOT unrolled -- the whole function
+  // must stay resident in the instruction cache next to the MMA-issue and producer loops.
+  float4 r_n = make_float4(0.f, 0.f, 0.f, 0.f), a_n = r_n, acc_n = r_n;
+  if (has_r || has_acc || has_aux) {   // burst of L1 prefetches for every row-chunk of this slab: one exposed latency
+#pragma unroll 1
+    for (int q = 0; q < C; ++q) {
+      const long grow = row0 + q * RPI + rl;
+      if (grow >= M) break;
+      if (has_r) prefetch_l1(resid + grow * ldr + gcol);
+      if (has_acc) prefetch_l1(d + grow * ldd + gcol);
+      if (has_aux) prefetch_l1(aux + grow * ldaux + gcol);
+    }
+  }
+  {
+    const long grow = row0 + rl;
+    if (grow < M) {
+      if (has_r) r_n = ldg_f4(resid + grow * ldr + gcol);
+      if (has_acc) acc_n = ldg_f4(d + grow * ldd + gcol);
+      if (has_aux) a_n = ldg_f4(aux + grow * ldaux + gcol);
+    }
+  }
+#pragma unroll 1
+  for (int q = 0; q < C; ++q) {
+    const int rr = q * RPI + rl;
+    const long grow = row0 + rr;
+    if (grow >= M) break;
+    const float4 v = reinterpret_cast<const float4*>(stage + rr * SLAB)[cl ^ slab_swz<SLAB>(rr)];
+    const float4 r = r_n, a = a_n, acc = acc_n;
+    if (q + 1 < C && grow + RPI < M) {
+      const long gn = grow + RPI;
+      if (has_r) r_n = ldg_f4(resid + gn * ldr + gcol);
+      if (has_acc) acc_n = ldg_f4(d + gn * ldd + gcol);
+      if (has_aux) a_n = ldg_f4(aux + gn * ldaux + gcol);
+    }
+    float y[4] = {v.x * alpha + b.x + r.x + acc.x, v.y * alpha + b.y + r.y + acc.y, v.z * alpha + b.z + r.z + acc.z,
+                  v.w * alpha + b.w + r.w + acc.w};
+    if (has_aux) {
+      y[0] *= gelu_new_grad_f(a.x); y[1] *= gelu_new_grad_f(a.y); y[2] *= gelu_new_grad_f(a.z); y[3] *= gelu_new_grad_f(a.w);
+    }
+    if (d) stg_f4(d + grow * ldd + gcol, make_float4(y[0], y[1], y[2], y[3]));
+    if (planes) {
+      if (act == ACT_GELU) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) y[j] = gelu_new_f(y[j]);
+      }
+      uint16_t* pp = planes + grow * ldp + gcol;
+      if (nplanes_out <= 3 || nplanes_out == 5) {
+        bf16 p0[4], p1[4], p2[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) split3(y[j], p0[j], p1[j], p2[j]);
+        *reinterpret_cast<uint2*>(pp) = make_uint2(pack_bf16x2(p0[0], p0[1]), pack_bf16x2(p0[2], p0[3]));
+        if (nplanes_out > 1)
+          *reinterpret_cast<uint2*>(pp + pstride) = make_uint2(pack_bf16x2(p1[0], p1[1]), pack_bf16x2(p1[2], p1[3]));
+        if (nplanes_out > 2)
+          *reinterpret_cast<uint2*>(pp + 2 * pstride) = make_uint2(pack_bf16x2(p2[0], p2[1]), pack_bf16x2(p2[2], p2[3]));
+      }
+      if (nplanes_out == 5) {
+        uint16_t h0[4], h1[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) split_h2(y[j], h0[j], h1[j]);
+        *reinterpret_cast<uint2*>(pp + 3 * pstride) =
+            make_uint2((uint32_t)h0[0] | ((uint32_t)h0[1] << 16), (uint32_t)h0[2] | ((uint32_t)h0[3] << 16));
+        *reinterpret_cast<uint2*>(pp + 4 * pstride) =
+            make_uint2((uint32_t)h1[0] | ((uint32_t)h1[1] << 16), (uint32_t)h1[2] | ((uint32_t)h1[3] << 16));
+      }
+    }
+  }
+}
+
+// First half: each thread drops its row's SLAB accumulator values into the swizzled tile.
+template <int SLAB>
+__device__ __forceinline__ void epilogue_slab(const float* x, float* stage, const GemmEpilogue& e, int row0, int col0,
+                                              int M, int N, int lane) {
+  constexpr int C = SLAB / 4;
+  {
+    float4* dst = reinterpret_cast<float4*>(stage + lane * SLAB);
+    const uint32_t sw = slab_swz<SLAB>(lane);
+#pragma unroll
+    for (int k = 0; k < C; ++k) dst[k ^ sw] = make_float4(x[4 * k], x[4 * k + 1], x[4 * k + 2], x[4 * k + 3]);
+  }
+  __syncwarp();
+  epilogue_rows<SLAB>(stage, e, row0, col0, M, N, lane);
+  __syncwarp();
 }
 
 // Accumulation scheme.  The tensor core's fp32 accumulator TRUNCATES on every accumulate (measured on B200: the
@@ -216,6 +302,7 @@ struct PlaneMat {
   long ld;            // row stride in elements (multiple of 8)
   long plane_stride;  // elements between planes (multiple of 8)
   int nplanes;
+  int fp16 = 0;       // 0: bf16 planes (x = p0+p1+p2), 1: fp16 planes (x = h0 + 2^-11 h1), common.cuh
 };
 
 // D = A.B with A given as [M,K] (a_mn_major=0) or [K,M] (a_mn_major=1); B as [N,K] (0) or [K,N] (1).
@@ -224,6 +311,6 @@ int gemm_launch(const PlaneMat& A, int a_mn_major, const PlaneMat& B, int b_mn_m
 
 // CUDA-event instrumentation of GEMM launches (bench.py roofline): see oob_gemm_timing_begin/end
 int gemm_timing_begin();
-int gemm_timing_end(double* total_ms, double* total_flops, long* launches);
+int gemm_timing_end(double* total_ms, double* total_flops, double* executed_flops, long* launches);
 
 }  // namespace oob

@@ -22,7 +22,7 @@ __host__ __device__ constexpr int gemmp_stage_bytes(int nsplit) {
 template <int BN, bool A_MN, bool B_MN, bool TWO_CTA, int BK>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_bf16x3_persistent_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
-                              const GemmParams p, const int num_stages) {
+                              const __grid_constant__ GemmParams p, const int num_stages) {
   static_assert(BN == 128, "epilogue holds BN fp32 running sums per thread; TMEM = 4 x BN columns");
   constexpr int BROWS = TWO_CTA ? BN / 2 : BN;        // B rows staged per CTA
   constexpr int TILE_M = TWO_CTA ? 2 * GEMM_BM : GEMM_BM;
@@ -33,7 +33,9 @@ gemm_bf16x3_persistent_kernel(const __grid_constant__ CUtensorMap tma_a, const _
   const int b_bytes = nsplit * BROWS * BK * 2;
   const int stage_bytes = a_bytes + b_bytes;
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + (size_t)num_stages * stage_bytes);
+  // after the ring: one transposition tile per epilogue warp (32 rows x p.slab fp32), then the barriers
+  float* stage_out = reinterpret_cast<float*>(smem + (size_t)num_stages * stage_bytes);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(stage_out + 4 * 32 * p.slab);
   uint64_t* empty_bar = full_bar + num_stages;
   uint64_t* tmem_full_bar = empty_bar + num_stages;   // [2] chunk accumulator ready
   uint64_t* tmem_empty_bar = tmem_full_bar + 2;        // [2] chunk accumulator drained
@@ -132,7 +134,8 @@ gemm_bf16x3_persistent_kernel(const __grid_constant__ CUtensorMap tma_a, const _
     // `if (lane == 0)` around it the compiler wraps every uniform-datapath instruction (UTCHMMA, UTCBAR) in an
     // ELECT/PLOP3/BRA.U.ANY retry loop, ~40 clk of issue per 64-clk MMA.
     if (leader) {
-      constexpr uint32_t idesc = make_idesc_bf16(TILE_M, BN, A_MN ? 1 : 0, B_MN ? 1 : 0);
+      const uint32_t idesc = make_idesc_f16kind(TILE_M, BN, A_MN ? 1 : 0, B_MN ? 1 : 0, 0, 0) |
+                             ((uint32_t)p.a_bf16 << 7) | ((uint32_t)p.b_bf16 << 10);
       int g = 0;    // k-blocks consumed so far
       int gc = 0;   // chunks issued so far (main buffer = gc & 1)
       int ti = 0;   // tiles started so far (corr buffer = ti & 1)
@@ -208,7 +211,7 @@ gemm_bf16x3_persistent_kernel(const __grid_constant__ CUtensorMap tma_a, const _
             tmem_ld_32x32(t_lane + (uint32_t)((2 + cb) * BN + g * 32), v);
             tmem_ld_wait();
 #pragma unroll
-            for (int j = 0; j < 32; ++j) racc[g * 32 + j] += __uint_as_float(v[j]);
+            for (int j = 0; j < 32; ++j) racc[g * 32 + j] = fmaf(__uint_as_float(v[j]), p.corr_scale, racc[g * 32 + j]);
           }
         }
         tc_fence_before();
@@ -224,16 +227,17 @@ gemm_bf16x3_persistent_kernel(const __grid_constant__ CUtensorMap tma_a, const _
         }
       }
       // fused output for this tile; the tensor pipe is already working on the next one
-      if (row < p.M && !(p.debug & 1)) {
+      if (!(p.debug & 1)) {
+        float* my_stage = stage_out + (warp - 2) * 32 * p.slab;
+        const int row0 = m0 + quarter * 32;
+        if (p.slab == 32) {
 #pragma unroll
-        for (int g = 0; g < BN / 32; ++g) {
-          const int col0 = n0 + g * 32;
-          if (col0 < p.N) {
-            float x[32];
+          for (int g = 0; g < BN / 32; ++g)
+            if (n0 + g * 32 < p.N) epilogue_slab<32>(&racc[g * 32], my_stage, p.epi, row0, n0 + g * 32, p.M, p.N, lane);
+        } else {
 #pragma unroll
-            for (int j = 0; j < 32; ++j) x[j] = racc[g * 32 + j];
-            epilogue_store32(x, p.epi, row, col0, p.N);
-          }
+          for (int g = 0; g < BN / 16; ++g)
+            if (n0 + g * 16 < p.N) epilogue_slab<16>(&racc[g * 16], my_stage, p.epi, row0, n0 + g * 16, p.M, p.N, lane);
         }
       }
     }

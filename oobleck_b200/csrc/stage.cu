@@ -35,6 +35,14 @@ inline PlaneMat weight_planes(const oob_layer_params* p, long off, long rows, lo
 inline PlaneMat act_planes(const void* base, long rows, long cols) {
   return PlaneMat{reinterpret_cast<const bf16*>(base), rows, cols, cols, rows * cols, 3};
 }
+// the fp16 x 2 pair of a 5-plane buffer (planes 3, 4): forward-GEMM operands when oob_dims.fwd_fp16 is set
+inline PlaneMat weight_planes_h(const oob_layer_params* p, long off, long rows, long cols) {
+  return PlaneMat{reinterpret_cast<const bf16*>(p->w_planes) + 3 * p->plane_stride + off, rows, cols, cols,
+                  p->plane_stride, 2, 1};
+}
+inline PlaneMat act_planes_h(const void* base, long rows, long cols) {
+  return PlaneMat{reinterpret_cast<const bf16*>(base) + 3 * rows * cols, rows, cols, cols, rows * cols, 2, 1};
+}
 inline GemmEpilogue epi_none() {
   GemmEpilogue e{};
   e.alpha = 1.0f;
@@ -42,17 +50,21 @@ inline GemmEpilogue epi_none() {
 }
 
 // D = A[M,K] . W[K,N] + bias (+resid); optionally the split planes of the result (or of GELU(result))
-int linear_fwd(const PlaneMat& a, const oob_layer_params* p, long w_off, long b_off, int M, int N, int K, int nsplit,
-               float* d, const float* resid, bf16* planes_out, bool gelu, cudaStream_t st) {
-  GemmParams gp{M, N, K, nsplit, epi_none()};
+// `a_base` is the input's plane buffer: bf16 x 3, or 5 planes when fp16_ops (then the fp16 pair is the operand and the
+// weights' fp16 pair is used: 3 tensor-core products instead of 6)
+int linear_fwd(const void* a_base, bool fp16_ops, const oob_layer_params* p, long w_off, long b_off, int M, int N, int K,
+               int nsplit, float* d, const float* resid, bf16* planes_out, int nplanes_out, bool gelu,
+               cudaStream_t st) {
+  GemmParams gp{M, N, K, fp16_ops ? 2 : nsplit, epi_none()};
   gp.epi.d = d; gp.epi.ldd = N;
   gp.epi.bias = p->w + b_off;
   gp.epi.resid = resid; gp.epi.ldr = N;
   if (planes_out) {
     gp.epi.act = gelu ? ACT_GELU : ACT_NONE;
-    gp.epi.planes = planes_out; gp.epi.ldp = N; gp.epi.plane_stride = (long)M * N; gp.epi.nplanes_out = 3;
+    gp.epi.planes = planes_out; gp.epi.ldp = N; gp.epi.plane_stride = (long)M * N; gp.epi.nplanes_out = nplanes_out;
   }
-  return gemm_launch(a, 0, weight_planes(p, w_off, K, N), 1, gp, st);
+  if (fp16_ops) return gemm_launch(act_planes_h(a_base, M, K), 0, weight_planes_h(p, w_off, K, N), 1, gp, st);
+  return gemm_launch(act_planes(a_base, M, K), 0, weight_planes(p, w_off, K, N), 1, gp, st);
 }
 // dA[M,K] = dY[M,N] . W[K,N]^T  (optionally * gelu'(aux), planes out)
 int linear_dgrad(const PlaneMat& dy, const oob_layer_params* p, long w_off, int M, int N, int K, int nsplit, float* dA,
@@ -122,6 +134,7 @@ int check_dims(const oob_dims* d) {
   OOB_CHECK(d->n_head > 0 && d->n_embd / d->n_head == 64 && d->n_embd % d->n_head == 0, "head_dim must be 64");
   OOB_CHECK(d->nsplit >= 1 && d->nsplit <= 3, "nsplit must be 1..3");
   OOB_CHECK(d->batch > 0 && d->seq > 1, "bad micro-batch shape");
+  OOB_CHECK(!d->fwd_fp16 || d->nsplit == 3, "fwd_fp16 is the fp32-grade forward mode: it needs nsplit = 3");
   return 0;
 }
 
@@ -134,24 +147,26 @@ int oob_block_forward(const oob_dims* d, const oob_layer_params* p, const float*
   if (int rc = check_dims(d)) return rc;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   const int M = d->batch * d->seq, E = d->n_embd, ns = d->nsplit;
+  const bool h = d->fwd_fp16 != 0;
+  const int np = h ? 5 : 3;   // planes of every buffer that feeds a forward GEMM (and, as bf16 x 3, a wgrad)
   const BlockOffsets o(E);
   const long ME = (long)M * E;
   int rc;
-  if ((rc = layernorm_fwd(x, p->w + o.ln1_w, p->w + o.ln1_b, nullptr, (bf16*)c->ln1_planes, ME, 3, c->ln1_mean,
+  if ((rc = layernorm_fwd(x, p->w + o.ln1_w, p->w + o.ln1_b, nullptr, (bf16*)c->ln1_planes, ME, np, c->ln1_mean,
                           c->ln1_rstd, M, E, d->ln_eps, st))) return rc;
   // q|k|v go straight to split planes: attention (forward and the recompute in backward) is their only consumer
-  if ((rc = linear_fwd(act_planes(c->ln1_planes, M, E), p, o.attn_w, o.attn_b, M, 3 * E, E, ns, nullptr, nullptr,
-                       (bf16*)c->qkv_planes, false, st))) return rc;
-  if ((rc = attention_fwd((const bf16*)c->qkv_planes, (long)M * 3 * E, c->att, (bf16*)c->att_planes, ME, 3, c->lse,
+  if ((rc = linear_fwd(c->ln1_planes, h, p, o.attn_w, o.attn_b, M, 3 * E, E, ns, nullptr, nullptr,
+                       (bf16*)c->qkv_planes, 3, false, st))) return rc;
+  if ((rc = attention_fwd((const bf16*)c->qkv_planes, (long)M * 3 * E, c->att, (bf16*)c->att_planes, ME, np, c->lse,
                           d->batch, d->seq, d->n_head, 64, st))) return rc;
-  if ((rc = linear_fwd(act_planes(c->att_planes, M, E), p, o.proj_w, o.proj_b, M, E, E, ns, c->x2, x, nullptr, false,
-                       st))) return rc;
-  if ((rc = layernorm_fwd(c->x2, p->w + o.ln2_w, p->w + o.ln2_b, nullptr, (bf16*)c->ln2_planes, ME, 3, c->ln2_mean,
+  if ((rc = linear_fwd(c->att_planes, h, p, o.proj_w, o.proj_b, M, E, E, ns, c->x2, x, nullptr, 0, false, st)))
+    return rc;
+  if ((rc = layernorm_fwd(c->x2, p->w + o.ln2_w, p->w + o.ln2_b, nullptr, (bf16*)c->ln2_planes, ME, np, c->ln2_mean,
                           c->ln2_rstd, M, E, d->ln_eps, st))) return rc;
-  if ((rc = linear_fwd(act_planes(c->ln2_planes, M, E), p, o.fc_w, o.fc_b, M, 4 * E, E, ns, c->fc, nullptr,
-                       (bf16*)c->gelu_planes, true, st))) return rc;
-  if ((rc = linear_fwd(act_planes(c->gelu_planes, M, 4 * E), p, o.proj2_w, o.proj2_b, M, E, 4 * E, ns, y, c->x2,
-                       nullptr, false, st))) return rc;
+  if ((rc = linear_fwd(c->ln2_planes, h, p, o.fc_w, o.fc_b, M, 4 * E, E, ns, c->fc, nullptr, (bf16*)c->gelu_planes, np,
+                       true, st))) return rc;
+  if ((rc = linear_fwd(c->gelu_planes, h, p, o.proj2_w, o.proj2_b, M, E, 4 * E, ns, y, c->x2, nullptr, 0, false, st)))
+    return rc;
   return 0;
 }
 
@@ -248,11 +263,14 @@ int oob_head_forward(const oob_dims* d, const oob_layer_params* p, const float* 
   const long ME = (long)M * E;
   int rc;
   // flat layout: ln_f.weight [E], ln_f.bias [E], lm_head.weight [V,E]
-  if ((rc = layernorm_fwd(x, p->w, p->w + E, nullptr, (bf16*)c->lnf_planes, ME, 3, c->mean, c->rstd, M, E, d->ln_eps,
-                          st))) return rc;
-  GemmParams gp{M, V, E, ns, epi_none()};
+  const bool h = d->fwd_fp16 != 0;
+  if ((rc = layernorm_fwd(x, p->w, p->w + E, nullptr, (bf16*)c->lnf_planes, ME, h ? 5 : 3, c->mean, c->rstd, M, E,
+                          d->ln_eps, st))) return rc;
+  GemmParams gp{M, V, E, h ? 2 : ns, epi_none()};
   gp.epi.d = c->logits; gp.epi.ldd = Vp;
-  if ((rc = gemm_launch(act_planes(c->lnf_planes, M, E), 0, weight_planes(p, 2 * E, V, E), 0, gp, st))) return rc;
+  if (h) rc = gemm_launch(act_planes_h(c->lnf_planes, M, E), 0, weight_planes_h(p, 2 * E, V, E), 0, gp, st);
+  else rc = gemm_launch(act_planes(c->lnf_planes, M, E), 0, weight_planes(p, 2 * E, V, E), 0, gp, st);
+  if (rc) return rc;
   return cross_entropy(c->logits, Vp, labels, d->batch, d->seq, V, c->row_loss, c->loss, total_loss,
                        (bf16*)c->dlogits_planes, Vp, (long)M * Vp, 3, st);
 }

@@ -135,11 +135,16 @@ class Layer:
         self._param_handle = _ParamHandle(flat, process_group)
         self.exp_avg = torch.zeros(n, dtype=torch.float32, device=self.device)
         self.exp_avg_sq = torch.zeros(n, dtype=torch.float32, device=self.device)
-        self.planes = torch.empty(3, self.plane_stride, dtype=torch.bfloat16, device=self.device)
+        # forward GEMMs read fp16 x 2 planes (3 tensor-core products, fp32-grade for bounded-range operands); the
+        # bf16 x 3 planes stay for the backward GEMMs: 5-plane buffers (include/oobleck_b200.h)
+        self.fwd_fp16 = 1 if nsplit == 3 else 0
+        self.nplanes = 5 if (self.fwd_fp16 and layer.kind != "embedding") else 3
+        self.planes = torch.empty(self.nplanes, self.plane_stride, dtype=torch.bfloat16, device=self.device)
         self.refresh_planes()
 
         E, V = layer.n_embd, layer.vocab_size
-        self.dims = OobDims(self.mb, self.T, E, layer.n_head, V, (V + 63) // 64 * 64, layer.layer_norm_epsilon, nsplit)
+        self.dims = OobDims(self.mb, self.T, E, layer.n_head, V, (V + 63) // 64 * 64, layer.layer_norm_epsilon, nsplit,
+                            self.fwd_fp16)
         self._alloc_contexts()
 
     # -- parameters ------------------------------------------------------------------------------------------------
@@ -157,7 +162,7 @@ class Layer:
 
     def refresh_planes(self) -> None:
         L.call("oob_split_planes", C.c_void_p(self.flat_param.data_ptr()), C.c_void_p(self.planes.data_ptr()),
-               self.numel, self.plane_stride, 3, _stream())
+               self.numel, self.plane_stride, self.nplanes, _stream())
 
     def load_flat_(self, flat: torch.Tensor) -> None:
         """Install explicit weights (parity tests, reconfiguration copies)."""
@@ -189,18 +194,19 @@ class Layer:
         self.ctx_tensors, self.ctx, self.out, self.saved_in = [], [], [], [None] * self.num_pipe_buffers
         for _ in range(self.num_pipe_buffers):
             if self.spec.kind == "block":
-                t = {"ln1_planes": torch.empty(3, M, E, **bf), "ln1_mean": torch.empty(M, **f32),
+                np_ = 5 if self.fwd_fp16 else 3   # buffers that feed a forward GEMM also carry the fp16 pair
+                t = {"ln1_planes": torch.empty(np_, M, E, **bf), "ln1_mean": torch.empty(M, **f32),
                      "ln1_rstd": torch.empty(M, **f32), "qkv_planes": torch.empty(3, M, 3 * E, **bf),
-                     "att": torch.empty(M, E, **f32), "att_planes": torch.empty(3, M, E, **bf),
+                     "att": torch.empty(M, E, **f32), "att_planes": torch.empty(np_, M, E, **bf),
                      "lse": torch.empty(self.mb * H * self.T, **f32), "x2": torch.empty(M, E, **f32),
-                     "ln2_planes": torch.empty(3, M, E, **bf), "ln2_mean": torch.empty(M, **f32),
+                     "ln2_planes": torch.empty(np_, M, E, **bf), "ln2_mean": torch.empty(M, **f32),
                      "ln2_rstd": torch.empty(M, **f32), "fc": torch.empty(M, 4 * E, **f32),
-                     "gelu_planes": torch.empty(3, M, 4 * E, **bf)}
+                     "gelu_planes": torch.empty(np_, M, 4 * E, **bf)}
                 self.ctx.append(OobBlockCtx(**{k: v.data_ptr() for k, v in t.items()}))
                 self.out.append(torch.empty(self.mb, self.T, E, **f32).requires_grad_(True))
             elif self.spec.kind == "head":
                 Vp = self.dims.vocab_padded
-                t = {"lnf_planes": torch.empty(3, M, E, **bf), "mean": torch.empty(M, **f32),
+                t = {"lnf_planes": torch.empty(5 if self.fwd_fp16 else 3, M, E, **bf), "mean": torch.empty(M, **f32),
                      "rstd": torch.empty(M, **f32), "logits": torch.empty(M, Vp, **f32),
                      "dlogits_planes": torch.empty(3, M, Vp, **bf), "row_loss": torch.empty(M, **f32),
                      "loss": torch.zeros(1, **f32)}

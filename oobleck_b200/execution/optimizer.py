@@ -31,7 +31,7 @@ class FusedAdamW:
         for l in self.layers:
             L.call("oob_adamw_step", C.c_void_p(l.flat_param.data_ptr()), C.c_void_p(l.flat_grad.data_ptr()),
                    C.c_void_p(l.exp_avg.data_ptr()), C.c_void_p(l.exp_avg_sq.data_ptr()),
-                   C.c_void_p(l.planes.data_ptr()), l.plane_stride, 3, l.numel, float(g["lr"]), g["betas"][0],
+                   C.c_void_p(l.planes.data_ptr()), l.plane_stride, l.nplanes, l.numel, float(g["lr"]), g["betas"][0],
                    g["betas"][1], g["eps"], g["weight_decay"], self._step, stream)
             self.state[l.flat_param] = {"step": self._step, "exp_avg": l.exp_avg, "exp_avg_sq": l.exp_avg_sq}
 

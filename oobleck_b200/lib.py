@@ -18,9 +18,9 @@ class OobleckB200Error(RuntimeError):
 
 
 class Planes(C.Structure):
-    """``oob_planes``: split-bf16 matrix [nplanes][rows][ld]."""
+    """``oob_planes``: split 16-bit matrix [nplanes][rows][ld]; format 0 = bf16 planes, 1 = fp16 pair."""
     _fields_ = [("base", C.c_void_p), ("rows", C.c_long), ("cols", C.c_long), ("ld", C.c_long),
-                ("plane_stride", C.c_long), ("nplanes", C.c_int)]
+                ("plane_stride", C.c_long), ("nplanes", C.c_int), ("format", C.c_int)]
 
 
 class GemmEpilogue(C.Structure):
@@ -34,7 +34,7 @@ class GemmEpilogue(C.Structure):
 class OobDims(C.Structure):
     """``oob_dims``."""
     _fields_ = [("batch", C.c_int), ("seq", C.c_int), ("n_embd", C.c_int), ("n_head", C.c_int), ("vocab", C.c_int),
-                ("vocab_padded", C.c_int), ("ln_eps", C.c_float), ("nsplit", C.c_int)]
+                ("vocab_padded", C.c_int), ("ln_eps", C.c_float), ("nsplit", C.c_int), ("fwd_fp16", C.c_int)]
 
 
 class OobLayerParams(C.Structure):
@@ -68,7 +68,8 @@ _SIGNATURES = {
     "oob_last_error": (C.c_char_p, []),
     "oob_launch_count": (C.c_long, []),
     "oob_gemm_timing_begin": (_I, []),
-    "oob_gemm_timing_end": (_I, [C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_long)]),
+    "oob_gemm_timing_end": (_I, [C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_double),
+                                 C.POINTER(C.c_long)]),
     "oob_ln_bwd_partials_floats": (C.c_long, [_I]),
     "oob_colsum_partials_floats": (C.c_long, [_I]),
     "oob_split_planes": (_I, [_P, _P, _L, _L, _I, _P]),

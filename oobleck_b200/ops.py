@@ -24,10 +24,15 @@ def new_planes(rows: int, cols: int, nplanes: int = 3, device="cuda") -> torch.T
     return torch.empty((nplanes, rows, cols), dtype=torch.bfloat16, device=device)
 
 
-def planes_desc(p: torch.Tensor, rows=None, cols=None) -> L.Planes:
+def planes_desc(p: torch.Tensor, rows=None, cols=None, fp16: bool = False) -> L.Planes:
+    """``fp16``: describe the fp16 pair (planes 3, 4) of a 5-plane buffer instead of its bf16 planes."""
     assert p.dtype == torch.bfloat16 and p.dim() == 3 and p.stride(2) == 1
-    return L.Planes(p.data_ptr(), rows if rows is not None else p.shape[1], cols if cols is not None else p.shape[2],
-                    p.stride(1), p.stride(0), p.shape[0])
+    rows = rows if rows is not None else p.shape[1]
+    cols = cols if cols is not None else p.shape[2]
+    if fp16:
+        assert p.shape[0] == 5
+        return L.Planes(p[3:].data_ptr(), rows, cols, p.stride(1), p.stride(0), 2, 1)
+    return L.Planes(p.data_ptr(), rows, cols, p.stride(1), p.stride(0), min(p.shape[0], 3), 0)
 
 
 def split(x: torch.Tensor, out: torch.Tensor | None = None, nplanes: int = 3) -> torch.Tensor:
@@ -40,12 +45,16 @@ def split(x: torch.Tensor, out: torch.Tensor | None = None, nplanes: int = 3) ->
     return out
 
 
-def planes_to_float(p: torch.Tensor) -> torch.Tensor:
-    return p.float().sum(0)
+def planes_to_float(p: torch.Tensor, fp16: bool = False) -> torch.Tensor:
+    if fp16:   # planes 3, 4 hold fp16 bit patterns: x ~= h0 + 2^-11 h1
+        h = p[3:5].view(torch.float16).float()
+        return h[0] + h[1] / 2048.0
+    return p[:3].float().sum(0)
 
 
 def gemm(a: torch.Tensor, a_mn: bool, b: torch.Tensor, b_mn: bool, M: int, N: int, K: int, *, nsplit=NSPLIT_PARITY,
-         d=None, bias=None, resid=None, accumulate=False, act=L.ACT_NONE, aux=None, planes_out=None, alpha=1.0):
+         d=None, bias=None, resid=None, accumulate=False, act=L.ACT_NONE, aux=None, planes_out=None, alpha=1.0,
+         a_fp16=False, b_fp16=False):
     e = L.GemmEpilogue()
     e.d = 0 if d is None else d.data_ptr()
     e.ldd = 0 if d is None else d.stride(0)
@@ -61,5 +70,5 @@ def gemm(a: torch.Tensor, a_mn: bool, b: torch.Tensor, b_mn: bool, M: int, N: in
     e.plane_stride = 0 if planes_out is None else planes_out.stride(0)
     e.nplanes_out = 0 if planes_out is None else planes_out.shape[0]
     e.alpha = alpha
-    A, B = planes_desc(a), planes_desc(b)
+    A, B = planes_desc(a, fp16=a_fp16), planes_desc(b, fp16=b_fp16)
     L.call("oob_gemm", C.byref(A), int(a_mn), C.byref(B), int(b_mn), M, N, K, nsplit, C.byref(e), _stream())

@@ -128,11 +128,14 @@ def test_adamw_layer_step_matches_oracle():
         lr = 1e-3 * step
         L.call("oob_adamw_step", C.c_void_p(l.flat_param.data_ptr()), C.c_void_p(l.flat_grad.data_ptr()),
                C.c_void_p(l.exp_avg.data_ptr()), C.c_void_p(l.exp_avg_sq.data_ptr()), C.c_void_p(l.planes.data_ptr()),
-               l.plane_stride, 3, l.numel, lr, 0.9, 0.999, 1e-8, 0.01, step,
+               l.plane_stride, l.nplanes, l.numel, lr, 0.9, 0.999, 1e-8, 0.01, step,
                C.c_void_p(torch.cuda.current_stream().cuda_stream))
         oo.adamw_step_(p, g, m, v, step, lr)
         close(l.flat_param, p, f"param after step {step}", rtol=1e-6)
-    close(l.planes[:, :l.numel].float().sum(0), p, "planes track the parameters", rtol=1e-6)
+    close(l.planes[:3, :l.numel].float().sum(0), p, "bf16 planes track the parameters", rtol=1e-6)
+    if l.nplanes == 5:
+        h = l.planes[3:5, :l.numel].view(torch.float16).float()
+        close(h[0] + h[1] / 2048.0, p, "fp16 pair tracks the parameters", rtol=1e-6)
 
 
 def test_side_stream_wgrad_is_bit_identical():

@@ -23,6 +23,12 @@ sys.path.insert(0, ROOT)
 from bench import MODELS  # noqa: E402
 
 
+def log(rank, msg, t0=[None]):
+    if t0[0] is None:
+        t0[0] = time.perf_counter()
+    print(f"[rank {rank} +{time.perf_counter() - t0[0]:7.2f}s] {msg}", file=sys.stderr, flush=True)
+
+
 def worker(rank, world, port, model, q):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world),
                       LOCAL_RANK=str(rank))
@@ -44,12 +50,16 @@ def worker(rank, world, port, model, q):
     costs = layer_cost_model(eng._model, mb)
     half = world // 2
     eng._pipeline_templates = [balanced_template(costs, n) for n in range(1, half + 1)]
+    log(rank, "engine built")
     eng.initialize_distributed("nccl")
     eng.instantiate_pipelines(gb // mb, plan=[eng._pipeline_templates[-1]] * 2)
-    for _ in range(2):
+    log(rank, "pipelines instantiated")
+    for i in range(2):
         eng._train_step()
-    torch.cuda.synchronize()
+        torch.cuda.synchronize()
+        log(rank, f"train step {i} done")
     dist.barrier()
+    log(rank, "barrier passed; rank %d leaves now" % (world - 1))
     lost = world - 1
     if rank == lost:
         q.put((rank, None))
@@ -59,9 +69,11 @@ def worker(rank, world, port, model, q):
     eng._reconfiguration.on_reconfigure([lost])
     torch.cuda.synchronize()
     t1 = time.perf_counter()
+    log(rank, f"reconfigured in {t1 - t0:.3f}s: {[p._ranks for p in eng._reconfiguration._pipelines]}")
     eng._train_step()
     torch.cuda.synchronize()
     t2 = time.perf_counter()
+    log(rank, f"first post-reconfiguration step done at {t2 - t0:.3f}s")
     q.put((rank, {"rebuild_s": t1 - t0, "first_step_done_s": t2 - t0,
                   "new_ranks": [p._ranks for p in eng._reconfiguration._pipelines],
                   "my_layers": len(eng._pipeline.execution._layers)}))
@@ -81,7 +93,7 @@ def main():
     procs = [ctx.Process(target=worker, args=(r, a.gpus, port, a.model, q)) for r in range(a.gpus)]
     for p in procs:
         p.start()
-    res = dict(q.get(timeout=900) for _ in range(a.gpus))
+    res = dict(q.get(timeout=240) for _ in range(a.gpus))
     for p in procs:
         p.join(timeout=60)
     alive = {k: v for k, v in res.items() if v}
