@@ -178,6 +178,13 @@ def cpu_baseline_sample(cfg, budget_s: float = 20.0):
 
 
 # ---------------------------------------------------------------------------------------------------------------
+def _quiet_nccl():
+    # stdout carries exactly one JSON line: keep NCCL's "NCCL version ..." banner (printed to stdout at
+    # NCCL_DEBUG=VERSION and above) out of it
+    if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+        os.environ["NCCL_DEBUG"] = "WARN"
+
+
 def run_ours(args, cfg):
     import torch.distributed as dist
 
@@ -189,6 +196,7 @@ def run_ours(args, cfg):
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     assert world == args.gpus, f"launch with torchrun --nproc-per-node {args.gpus} (WORLD_SIZE={world})"
+    _quiet_nccl()
     torch.cuda.set_device(local_rank)
     L.load()
     ma = cfg["model_args"]

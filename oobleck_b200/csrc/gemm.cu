@@ -151,6 +151,8 @@ int gemm_launch(const PlaneMat& A, int a_mn, const PlaneMat& B, int b_mn, const 
   {
     GemmEpilogue& e = p.epi;
     auto ok16 = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15) == 0; };
+    static const int env_pf = [] { const char* v = getenv("OOB_EPI_PREFETCH"); return v ? atoi(v) : 1; }();
+    e.prefetch = env_pf;
     e.vec4 = (!e.d || (ok16(e.d) && (e.ldd & 3) == 0)) && (!e.bias || ok16(e.bias)) &&
              (!e.resid || (ok16(e.resid) && (e.ldr & 3) == 0)) && (!e.aux || (ok16(e.aux) && (e.ldaux & 3) == 0)) &&
              (!e.planes || ((reinterpret_cast<uintptr_t>(e.planes) & 7) == 0 && (e.ldp & 3) == 0 &&

@@ -42,6 +42,7 @@ struct GemmEpilogue {
   int nplanes_out;      // 1..3 bf16 planes; 5 = three bf16 planes followed by the two fp16 planes (common.cuh)
   float alpha;          // value = alpha * acc (before bias etc.)
   int vec4;             // set by gemm_launch: every pointer / stride above allows 16-B (fp32) and 8-B (plane) accesses
+  int prefetch;         // set by gemm_launch: L1-prefetch the residual / aux / accumulate rows of a slab in one burst
 };
 
 struct GemmParams {
@@ -198,7 +199,7 @@ __device__ __noinline__ void epilogue_rows(const float* stage, const GemmEpilogu
   // epilogue warp per scheduler: nobody else hides the latency).  The loop body is NOT unrolled -- the whole function
   // must stay resident in the instruction cache next to the MMA-issue and producer loops.
   float4 r_n = make_float4(0.f, 0.f, 0.f, 0.f), a_n = r_n, acc_n = r_n;
-  if (has_r || has_acc || has_aux) {   // burst of L1 prefetches for every row-chunk of this slab: one exposed latency
+  if (ep.prefetch && (has_r || has_acc || has_aux)) {   // burst of L1 prefetches for every row-chunk of this slab: one exposed latency
 #pragma unroll 1
     for (int q = 0; q < C; ++q) {
       const long grow = row0 + q * RPI + rl;
