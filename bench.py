@@ -197,6 +197,10 @@ def run_ours(args, cfg):
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     assert world == args.gpus, f"launch with torchrun --nproc-per-node {args.gpus} (WORLD_SIZE={world})"
     _quiet_nccl()
+    from oobleck_b200.execution import layer as _layer
+    if args.bwd_fp16 is not None:
+        _layer.DEFAULT_BWD_FP16 = bool(args.bwd_fp16)
+    bwd_fp16 = bool(_layer.DEFAULT_BWD_FP16) and args.nsplit == 3
     torch.cuda.set_device(local_rank)
     L.load()
     ma = cfg["model_args"]
@@ -281,13 +285,15 @@ def run_ours(args, cfg):
         "metric": "training_tokens_per_s", "value": value, "unit": "tokens/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None,
-        "dtype": ("f32 (fp16 x2 planes forward / bf16 x3 planes backward on tcgen05, fp32 accumulate + promotion)"
+        "dtype": (("f32 (fp16 x2 planes forward and backward (loss-scaled) on tcgen05, fp32 accumulate + promotion)"
+                   if bwd_fp16 else
+                   "f32 (fp16 x2 planes forward / bf16 x3 planes backward on tcgen05, fp32 accumulate + promotion)")
                   if args.nsplit == 3 else "split-bf16 x%d on tcgen05, fp32 accumulate" % args.nsplit),
         "data": "synthetic",
         "config": {"workload": f"{args.model} 1F1B train step: {Lh + 2} stage layers over {world} stage(s), "
                                f"micro-batch {mb}, {gb // mb} micro-batches/step, T={T}, AdamW",
                    "global_batch": gb, "seq_len": T, "parallelism": f"pp{world}", "nsplit": args.nsplit,
-                   "wgrad_side_stream": bool(args.side_stream),
+                   "wgrad_side_stream": bool(args.side_stream), "bwd_fp16": bwd_fp16,
                    "l2": "working set per step (>6 GB of weights) far exceeds the 126 MB L2; no flush needed"},
         "clocks": clocks,
         "gpu_launches": int(launches),
@@ -300,7 +306,7 @@ def run_ours(args, cfg):
             "frac": (gemm_tflops / peaks["bf16_tflops"]) if gemm_tflops else None,
             "peak_source": peaks["source"] + " (cuBLAS bf16, sustained)",
             "tensor_products_per_algorithmic_flop": (g_ex.value / g_fl.value) if g_fl.value else None,
-            "products_note": "forward GEMMs: fp16 x 2 planes = 3 products; backward: bf16 x 3 planes = 6",
+            "products_note": "GEMMs on fp16 x 2 planes issue 3 products per MAC, on bf16 x 3 planes 6",
             "executed_tensor_tflops": exec_tflops,
             "executed_frac_of_peak": (exec_tflops / peaks["bf16_tflops"]) if exec_tflops else None,
             "launches_timed": int(g_n.value),
@@ -328,6 +334,9 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--model", default="gpt2-xl", choices=sorted(MODELS))
     ap.add_argument("--nsplit", type=int, default=3, choices=[1, 2, 3])
+    ap.add_argument("--bwd-fp16", type=int, default=None, choices=[0, 1],
+                    help="backward GEMMs on loss-scaled fp16 pairs (3 products) instead of bf16 x 3 (6); default: the "
+                         "library default (oobleck_b200.execution.layer.DEFAULT_BWD_FP16)")
     ap.add_argument("--side-stream", type=int, default=1, choices=[0, 1],
                     help="0: weight-gradient kernels stay on the compute stream (A/B of the overlap)")
     args = ap.parse_args()

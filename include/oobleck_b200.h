@@ -19,6 +19,9 @@
 #ifndef OOBLECK_B200_H_
 #define OOBLECK_B200_H_
 
+/* `nplanes` codes understood by every plane producer: 1..3 bf16 planes; 5 = bf16 x 3 + fp16 pair; 22 = fp16 pair only */
+#define OOB_PLANES_FP16_PAIR 22
+
 #ifdef __cplusplus
 extern "C" {
 #endif
@@ -71,12 +74,14 @@ int oob_gemm(const oob_planes* a, int a_mn_major, const oob_planes* b, int b_mn_
 int oob_layernorm_fwd(const float* x, const float* gamma, const float* beta, float* y, void* y_planes,
                       long plane_stride, int nplanes, float* mean, float* rstd, int rows, int n_embd, float eps,
                       void* stream);
-/* dx = (dres ? dres : 0) + LN'(dy); dgamma/dbeta are ACCUMULATED (+=) */
+/* dx = (dres ? dres : 0) + LN'(dy); dgamma/dbeta are ACCUMULATED (+= param_grad_scale * ...): with a loss-scaled
+ * dy, param_grad_scale = 1 / loss_scale keeps parameter gradients unscaled while dx stays scaled */
 int oob_layernorm_bwd(const float* dy, const float* x, const float* mean, const float* rstd, const float* gamma,
                       const float* dres, float* dx, void* dx_planes, long plane_stride, int nplanes, float* dgamma,
-                      float* dbeta, float* partials, int rows, int n_embd, void* stream);
-/* out[n] += sum_m a[m,n]  (bias gradients) */
-int oob_colsum_accumulate(const float* a, long lda, int rows, int cols, float* out, float* partials, void* stream);
+                      float* dbeta, float* partials, int rows, int n_embd, float param_grad_scale, void* stream);
+/* out[n] += scale * sum_m a[m,n]  (bias gradients) */
+int oob_colsum_accumulate(const float* a, long lda, int rows, int cols, float* out, float* partials, float scale,
+                          void* stream);
 
 /* ---- attention (HF GPT2Attention eager: causal softmax(QK^T/sqrt(d))V, no dropout) -----------------------
  * q|k|v and dO are consumed as split planes ([3][B*T][3E] / [3][B*T][E]: the QKV GEMM and the proj dgrad GEMM write
@@ -92,12 +97,13 @@ int oob_attention_bwd(const void* qkv_planes, long qkv_plane_stride, const float
 int oob_embedding_fwd(const long long* ids, const float* wte, const float* wpe, float* hidden, int rows, int seq,
                       int n_embd, void* stream);
 int oob_embedding_bwd(const long long* ids, const float* dhidden, float* dwte, float* dwpe, int batch, int seq,
-                      int n_embd, void* stream);
+                      int n_embd, float scale /* 1 / loss scale of dhidden */, void* stream);
 
 /* ---- fx layer L+1 tail: shifted CrossEntropyLoss(mean) on logits[M, ldl], gradient into planes ----------- */
 int oob_cross_entropy(const float* logits, long ldl, const long long* labels, int batch, int seq, int vocab,
                       float* row_loss, float* loss, float* total_loss, void* dlogits_planes, long ldp,
-                      long plane_stride, int nplanes, void* stream);
+                      long plane_stride, int nplanes, float grad_scale /* loss scale applied to dlogits only */,
+                      void* stream);
 
 /* ---- optimizer: torch.optim.AdamW(fused=True).step() over one layer's flat parameter (pipeline.py:117-123) */
 int oob_adamw_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, void* planes,
@@ -118,6 +124,11 @@ typedef struct oob_dims {
   int nsplit;              /* bf16 planes per GEMM operand: 3 = fp32-grade (parity), 2, 1 */
   int fwd_fp16;            /* 1 (needs nsplit = 3): forward GEMMs read the fp16 x 2 planes -- every activation / weight
                               plane buffer marked [5] below must then have 5 planes; 0: 3-plane buffers, bf16 only */
+  int bwd_fp16;            /* 1 (needs fwd_fp16 = 1): backward GEMMs run on fp16 pairs too (3 products).  Gradients of
+                              activations are then carried multiplied by loss_scale (fp32 values AND their fp16-pair
+                              planes: dy / dx of the stage API, everything in oob_bwd_scratch except datt_planes);
+                              parameter gradients are unscaled where they are produced.  0: bf16 x 3 gradients */
+  float loss_scale;        /* power of two; oob_head_forward scales dlogits by it (bwd_fp16 = 1 only) */
 } oob_dims;
 
 /* parameters of one stage layer: flat fp32 vector in HF ``layer.parameters()`` order (what FSDP's FlatParamHandle

@@ -132,7 +132,13 @@ __device__ __forceinline__ void zero_acc(float (&a)[8][4]) {
 __device__ __forceinline__ void store_pair(float* f32, bf16* planes, long plane_stride, int nplanes, long off, float a,
                                            float c) {
   if (f32) *reinterpret_cast<float2*>(f32 + off) = make_float2(a, c);
-  if (planes) {
+  if (planes && nplanes == PLANES_H2) {   // loss-scaled gradient out: fp16 pair only
+    uint16_t a0, a1, c0, c1;
+    split_h2(a, a0, a1);
+    split_h2(c, c0, c1);
+    *reinterpret_cast<uint32_t*>(planes + off) = (uint32_t)a0 | ((uint32_t)c0 << 16);
+    *reinterpret_cast<uint32_t*>(planes + plane_stride + off) = (uint32_t)a1 | ((uint32_t)c1 << 16);
+  } else if (planes) {
     uint32_t p0, p1, p2;
     split_pack(a, c, p0, p1, p2);
     *reinterpret_cast<uint32_t*>(planes + off) = p0;

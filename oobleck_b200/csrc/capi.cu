@@ -65,12 +65,13 @@ int oob_layernorm_fwd(const float* x, const float* gamma, const float* beta, flo
 }
 int oob_layernorm_bwd(const float* dy, const float* x, const float* mean, const float* rstd, const float* gamma,
                       const float* dres, float* dx, void* dx_planes, long plane_stride, int nplanes, float* dgamma,
-                      float* dbeta, float* partials, int rows, int n_embd, void* stream) {
+                      float* dbeta, float* partials, int rows, int n_embd, float param_grad_scale, void* stream) {
   return layernorm_bwd(dy, x, mean, rstd, gamma, dres, dx, reinterpret_cast<bf16*>(dx_planes), plane_stride, nplanes,
-                       dgamma, dbeta, partials, rows, n_embd, S(stream));
+                       dgamma, dbeta, partials, rows, n_embd, param_grad_scale, S(stream));
 }
-int oob_colsum_accumulate(const float* a, long lda, int rows, int cols, float* out, float* partials, void* stream) {
-  return colsum_accumulate(a, lda, rows, cols, out, partials, S(stream));
+int oob_colsum_accumulate(const float* a, long lda, int rows, int cols, float* out, float* partials, float scale,
+                          void* stream) {
+  return colsum_accumulate(a, lda, rows, cols, out, partials, scale, S(stream));
 }
 
 int oob_attention_fwd(const void* qkv_planes, long qkv_plane_stride, float* out, void* out_planes, long plane_stride,
@@ -94,15 +95,15 @@ int oob_embedding_fwd(const long long* ids, const float* wte, const float* wpe, 
   return embedding_fwd(ids, wte, wpe, hidden, rows, seq, n_embd, S(stream));
 }
 int oob_embedding_bwd(const long long* ids, const float* dhidden, float* dwte, float* dwpe, int batch, int seq,
-                      int n_embd, void* stream) {
-  return embedding_bwd(ids, dhidden, dwte, dwpe, batch, seq, n_embd, S(stream));
+                      int n_embd, float scale, void* stream) {
+  return embedding_bwd(ids, dhidden, dwte, dwpe, batch, seq, n_embd, scale, S(stream));
 }
 
 int oob_cross_entropy(const float* logits, long ldl, const long long* labels, int batch, int seq, int vocab,
                       float* row_loss, float* loss, float* total_loss, void* dlogits_planes, long ldp,
-                      long plane_stride, int nplanes, void* stream) {
+                      long plane_stride, int nplanes, float grad_scale, void* stream) {
   return cross_entropy(logits, ldl, labels, batch, seq, vocab, row_loss, loss, total_loss,
-                       reinterpret_cast<bf16*>(dlogits_planes), ldp, plane_stride, nplanes, S(stream));
+                       reinterpret_cast<bf16*>(dlogits_planes), ldp, plane_stride, nplanes, grad_scale, S(stream));
 }
 
 int oob_adamw_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, void* planes,

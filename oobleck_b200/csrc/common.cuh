@@ -82,6 +82,15 @@ __device__ __forceinline__ void split5(float x, uint16_t& q0, uint16_t& q1, uint
 __device__ __forceinline__ float tanh_fast(float u) {
   return 1.0f - __fdividef(2.0f, 1.0f + __expf(2.0f * u));
 }
+// Plane-set codes accepted by every producer's `nplanes` argument:
+//   1..3        bf16 planes p0..  (x = p0 + p1 + p2)
+//   5           bf16 x 3 followed by the fp16 pair
+//   PLANES_H2   the fp16 pair only, at planes 0 and 1 (loss-scaled gradients, backward GEMM operands)
+constexpr int PLANES_H2 = 22;
+__host__ __device__ __forceinline__ int planes_count(int code) { return code == PLANES_H2 ? 2 : code; }
+// which of split5's five outputs goes to stored plane i
+__host__ __device__ __forceinline__ int planes_src(int code, int i) { return code == PLANES_H2 ? 3 + i : i; }
+
 __device__ __forceinline__ float gelu_new_f(float x) {
   const float k0 = 0.7978845608028654f, k1 = 0.044715f;
   float u = k0 * (x + k1 * x * x * x);

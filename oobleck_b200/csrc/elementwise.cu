@@ -22,17 +22,22 @@ __global__ void split_kernel(const float* __restrict__ x, bf16* __restrict__ pla
     uint16_t q[5][4];
 #pragma unroll
     for (int j = 0; j < 4; ++j) split5(v[j], q[0][j], q[1][j], q[2][j], q[3][j], q[4][j]);
+    const bool h2 = nplanes == PLANES_H2;
+    const int cnt = planes_count(nplanes);
 #pragma unroll
     for (int p = 0; p < 5; ++p) {
-      if (p >= nplanes) break;
+      if (p >= cnt) break;
       uint16_t* dst = reinterpret_cast<uint16_t*>(planes) + p * plane_stride + i;
+      uint16_t v4[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) v4[j] = (h2 && p < 2) ? q[3 + (p & 1)][j] : q[p][j];
       if (i + 4 <= n) {
         uint2 w;
-        w.x = (uint32_t)q[p][0] | ((uint32_t)q[p][1] << 16);
-        w.y = (uint32_t)q[p][2] | ((uint32_t)q[p][3] << 16);
+        w.x = (uint32_t)v4[0] | ((uint32_t)v4[1] << 16);
+        w.y = (uint32_t)v4[2] | ((uint32_t)v4[3] << 16);
         *reinterpret_cast<uint2*>(dst) = w;
       } else {
-        for (int j = 0; j < 4 && i + j < n; ++j) dst[j] = q[p][j];
+        for (int j = 0; j < 4 && i + j < n; ++j) dst[j] = v4[j];
       }
     }
   }
@@ -191,16 +196,26 @@ layernorm_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ x, 
         }
         if (dx) stg_f4(dx + (long)row * E + c * 4, make_float4(o[0], o[1], o[2], o[3]));
         if (planes) {
-          bf16 pq[3][4];
+          if (nplanes == PLANES_H2) {   // loss-scaled gradient: fp16 pair only
+            uint16_t h0[4], h1[4];
 #pragma unroll
-          for (int j = 0; j < 4; ++j) split3(o[j], pq[0][j], pq[1][j], pq[2][j]);
+            for (int j = 0; j < 4; ++j) split_h2(o[j], h0[j], h1[j]);
+            *reinterpret_cast<uint2*>(planes + (long)row * E + c * 4) =
+                make_uint2((uint32_t)h0[0] | ((uint32_t)h0[1] << 16), (uint32_t)h0[2] | ((uint32_t)h0[3] << 16));
+            *reinterpret_cast<uint2*>(planes + plane_stride + (long)row * E + c * 4) =
+                make_uint2((uint32_t)h1[0] | ((uint32_t)h1[1] << 16), (uint32_t)h1[2] | ((uint32_t)h1[3] << 16));
+          } else {
+            bf16 pq[3][4];
 #pragma unroll
-          for (int p = 0; p < 3; ++p) {
-            if (p < nplanes) {
-              uint2 w;
-              w.x = (uint32_t)__bfloat16_as_ushort(pq[p][0]) | ((uint32_t)__bfloat16_as_ushort(pq[p][1]) << 16);
-              w.y = (uint32_t)__bfloat16_as_ushort(pq[p][2]) | ((uint32_t)__bfloat16_as_ushort(pq[p][3]) << 16);
-              *reinterpret_cast<uint2*>(planes + p * plane_stride + (long)row * E + c * 4) = w;
+            for (int j = 0; j < 4; ++j) split3(o[j], pq[0][j], pq[1][j], pq[2][j]);
+#pragma unroll
+            for (int p = 0; p < 3; ++p) {
+              if (p < nplanes) {
+                uint2 w;
+                w.x = (uint32_t)__bfloat16_as_ushort(pq[p][0]) | ((uint32_t)__bfloat16_as_ushort(pq[p][1]) << 16);
+                w.y = (uint32_t)__bfloat16_as_ushort(pq[p][2]) | ((uint32_t)__bfloat16_as_ushort(pq[p][3]) << 16);
+                *reinterpret_cast<uint2*>(planes + p * plane_stride + (long)row * E + c * 4) = w;
+              }
             }
           }
         }
@@ -222,7 +237,7 @@ layernorm_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ x, 
 // lane y sums partials y, y+8, ... for its column, then the 8 lanes are folded through shared memory.
 __global__ void __launch_bounds__(256)
 colreduce_finalize_kernel(const float* __restrict__ partials, int nparts, int ncols, float* __restrict__ out0,
-                          float* __restrict__ out1, int split) {
+                          float* __restrict__ out1, int split, float scale) {
   __shared__ float sh[8][33];
   const int c = blockIdx.x * 32 + threadIdx.x;
   float s = 0.f;
@@ -234,14 +249,14 @@ colreduce_finalize_kernel(const float* __restrict__ partials, int nparts, int nc
     float t = sh[0][threadIdx.x];
 #pragma unroll
     for (int k = 1; k < 8; ++k) t += sh[k][threadIdx.x];
-    if (c < split) out0[c] += t;
-    else out1[c - split] += t;
+    if (c < split) out0[c] += t * scale;   // scale: 1 / loss scale of the incoming gradient (1 when unscaled)
+    else out1[c - split] += t * scale;
   }
 }
 
 int layernorm_bwd(const float* dy, const float* x, const float* mean, const float* rstd, const float* gamma,
                   const float* dres, float* dx, bf16* planes, long plane_stride, int nplanes, float* dgamma,
-                  float* dbeta, float* partials, int rows, int E, cudaStream_t s) {
+                  float* dbeta, float* partials, int rows, int E, float gscale, cudaStream_t s) {
   OOB_CHECK(E % 4 == 0 && E <= LNB_V * 256 * 4, "layernorm_bwd: E=%d unsupported", E);
   if (rows <= 0) return 0;
   int grid = rows < LN_BWD_MAX_GRID ? rows : LN_BWD_MAX_GRID;
@@ -249,7 +264,7 @@ int layernorm_bwd(const float* dy, const float* x, const float* mean, const floa
                                             partials, rows, E);
   OOB_CUDA_OK(cudaGetLastError());
   count_launch();
-  colreduce_finalize_kernel<<<(2 * E + 31) / 32, dim3(32, 8), 0, s>>>(partials, grid, 2 * E, dgamma, dbeta, E);
+  colreduce_finalize_kernel<<<(2 * E + 31) / 32, dim3(32, 8), 0, s>>>(partials, grid, 2 * E, dgamma, dbeta, E, gscale);
   OOB_CUDA_OK(cudaGetLastError());
   count_launch();
   return 0;
@@ -283,7 +298,8 @@ colsum_partial_kernel(const float* __restrict__ a, long lda, int rows, int cols,
   }
 }
 
-int colsum_accumulate(const float* a, long lda, int rows, int cols, float* out, float* partials, cudaStream_t s) {
+int colsum_accumulate(const float* a, long lda, int rows, int cols, float* out, float* partials, float scale,
+                      cudaStream_t s) {
   OOB_CHECK(cols % 4 == 0 && lda % 4 == 0, "colsum: cols must be a multiple of 4");
   if (rows <= 0) return 0;
   int gy = (rows + 63) / 64;
@@ -292,7 +308,7 @@ int colsum_accumulate(const float* a, long lda, int rows, int cols, float* out, 
   colsum_partial_kernel<<<grid, block, 0, s>>>(a, lda, rows, cols, partials);
   OOB_CUDA_OK(cudaGetLastError());
   count_launch();
-  colreduce_finalize_kernel<<<(cols + 31) / 32, dim3(32, 8), 0, s>>>(partials, gy, cols, out, out, cols);
+  colreduce_finalize_kernel<<<(cols + 31) / 32, dim3(32, 8), 0, s>>>(partials, gy, cols, out, out, cols, scale);
   OOB_CUDA_OK(cudaGetLastError());
   count_launch();
   return 0;
@@ -326,37 +342,41 @@ int embedding_fwd(const long long* ids, const float* wte, const float* wpe, floa
 
 // dwte[ids[m],:] += dx[m,:] (red.add, tokens may repeat);  dwpe[t,:] += sum_b dx[b*T+t,:]
 __global__ void embedding_bwd_wte_kernel(const long long* __restrict__ ids, const float* __restrict__ dx,
-                                         float* __restrict__ dwte, int rows, int E) {
+                                         float* __restrict__ dwte, int rows, int E, float scale) {
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (warp >= rows) return;
   float* d = dwte + ids[warp] * E;
   const float* g = dx + (long)warp * E;
   for (int c = lane * 4; c < E; c += 128) {
     const float4 v = ldg_f4(g + c);
-    atomicAdd(d + c, v.x); atomicAdd(d + c + 1, v.y); atomicAdd(d + c + 2, v.z); atomicAdd(d + c + 3, v.w);
+    atomicAdd(d + c, v.x * scale); atomicAdd(d + c + 1, v.y * scale); atomicAdd(d + c + 2, v.z * scale);
+    atomicAdd(d + c + 3, v.w * scale);
   }
 }
-__global__ void embedding_bwd_wpe_kernel(const float* __restrict__ dx, float* __restrict__ dwpe, int B, int T, int E) {
+__global__ void embedding_bwd_wpe_kernel(const float* __restrict__ dx, float* __restrict__ dwpe, int B, int T, int E,
+                                         float scale) {
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (warp >= T) return;
   for (int c = lane * 4; c < E; c += 128) {
-    float4 acc = ldg_f4(dwpe + (long)warp * E + c);
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
     for (int b = 0; b < B; ++b) {
       const float4 v = ldg_f4(dx + ((long)b * T + warp) * E + c);
       acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
     }
-    stg_f4(dwpe + (long)warp * E + c, acc);
+    const float4 old = ldg_f4(dwpe + (long)warp * E + c);
+    stg_f4(dwpe + (long)warp * E + c, make_float4(old.x + acc.x * scale, old.y + acc.y * scale, old.z + acc.z * scale,
+                                                  old.w + acc.w * scale));
   }
 }
 
-int embedding_bwd(const long long* ids, const float* dx, float* dwte, float* dwpe, int B, int T, int E,
+int embedding_bwd(const long long* ids, const float* dx, float* dwte, float* dwpe, int B, int T, int E, float scale,
                   cudaStream_t s) {
   const int rows = B * T;
   if (rows <= 0) return 0;
-  embedding_bwd_wte_kernel<<<(rows + 7) / 8, 256, 0, s>>>(ids, dx, dwte, rows, E);
+  embedding_bwd_wte_kernel<<<(rows + 7) / 8, 256, 0, s>>>(ids, dx, dwte, rows, E, scale);
   OOB_CUDA_OK(cudaGetLastError());
   count_launch();
-  embedding_bwd_wpe_kernel<<<(T + 7) / 8, 256, 0, s>>>(dx, dwpe, B, T, E);
+  embedding_bwd_wpe_kernel<<<(T + 7) / 8, 256, 0, s>>>(dx, dwpe, B, T, E, scale);
   OOB_CUDA_OK(cudaGetLastError());
   count_launch();
   return 0;
@@ -391,7 +411,7 @@ cross_entropy_kernel(const float* __restrict__ logits, long ldl, const long long
   if (!has_target) {
     if (threadIdx.x == 0) row_loss[row] = 0.f;
     if (dplanes) {
-      for (int p = 0; p < nplanes; ++p) {
+      for (int p = 0; p < planes_count(nplanes); ++p) {
         uint4* d = reinterpret_cast<uint4*>(dplanes + p * plane_stride + (long)row * ldp);
         for (int c = threadIdx.x; c < vpad / 8; c += blockDim.x) d[c] = make_uint4(0, 0, 0, 0);
       }
@@ -417,12 +437,20 @@ cross_entropy_kernel(const float* __restrict__ logits, long ldl, const long long
         g[j] = 0.f;
         if (cc < V) g[j] = (expf(lr[cc] - mx) * inv - (cc == target ? 1.f : 0.f)) * grad_scale;
       }
-      bf16 a[3], b[3];
-      split3(g[0], a[0], a[1], a[2]);
-      split3(g[1], b[0], b[1], b[2]);
-      for (int p = 0; p < nplanes; ++p) {
-        const uint32_t w = (uint32_t)__bfloat16_as_ushort(a[p]) | ((uint32_t)__bfloat16_as_ushort(b[p]) << 16);
-        *reinterpret_cast<uint32_t*>(dplanes + p * plane_stride + (long)row * ldp + c) = w;
+      if (nplanes == PLANES_H2) {
+        uint16_t a0, a1, b0, b1;
+        split_h2(g[0], a0, a1);
+        split_h2(g[1], b0, b1);
+        *reinterpret_cast<uint32_t*>(dplanes + (long)row * ldp + c) = (uint32_t)a0 | ((uint32_t)b0 << 16);
+        *reinterpret_cast<uint32_t*>(dplanes + plane_stride + (long)row * ldp + c) = (uint32_t)a1 | ((uint32_t)b1 << 16);
+      } else {
+        bf16 a[3], b[3];
+        split3(g[0], a[0], a[1], a[2]);
+        split3(g[1], b[0], b[1], b[2]);
+        for (int p = 0; p < nplanes; ++p) {
+          const uint32_t w = (uint32_t)__bfloat16_as_ushort(a[p]) | ((uint32_t)__bfloat16_as_ushort(b[p]) << 16);
+          *reinterpret_cast<uint32_t*>(dplanes + p * plane_stride + (long)row * ldp + c) = w;
+        }
       }
     }
   }
@@ -444,13 +472,13 @@ __global__ void __launch_bounds__(1024) loss_reduce_kernel(const float* __restri
 
 int cross_entropy(const float* logits, long ldl, const long long* labels, int B, int T, int V, float* row_loss,
                   float* loss, float* total_loss, bf16* dplanes, long ldp, long plane_stride, int nplanes,
-                  cudaStream_t s) {
+                  float grad_scale, cudaStream_t s) {
   const int rows = B * T;
   OOB_CHECK(T >= 2, "cross_entropy: sequence length must be >= 2");
   OOB_CHECK(dplanes == nullptr || (ldp % 8 == 0 && plane_stride % 8 == 0), "cross_entropy: plane strides must be multiples of 8");
   const float scale = 1.0f / (float)((long)B * (T - 1));
-  cross_entropy_kernel<<<rows, 512, 0, s>>>(logits, ldl, labels, T, V, scale, row_loss, dplanes, ldp, plane_stride,
-                                            nplanes);
+  cross_entropy_kernel<<<rows, 512, 0, s>>>(logits, ldl, labels, T, V, scale * grad_scale, row_loss, dplanes, ldp,
+                                            plane_stride, nplanes);
   OOB_CUDA_OK(cudaGetLastError());
   count_launch();
   loss_reduce_kernel<<<1, 1024, 0, s>>>(row_loss, rows, scale, loss, total_loss);

@@ -39,7 +39,7 @@ struct GemmEpilogue {
   bf16* planes;         // split output [nplanes_out][M][ldp] or null
   long ldp;
   long plane_stride;
-  int nplanes_out;      // 1..3 bf16 planes; 5 = three bf16 planes followed by the two fp16 planes (common.cuh)
+  int nplanes_out;      // plane-set code (common.cuh): 1..3 bf16 planes, 5 = bf16 x 3 + fp16 pair, PLANES_H2 = pair only
   float alpha;          // value = alpha * acc (before bias etc.)
   int vec4;             // set by gemm_launch: every pointer / stride above allows 16-B (fp32) and 8-B (plane) accesses
   int prefetch;         // set by gemm_launch: L1-prefetch the residual / aux / accumulate rows of a slab in one burst
@@ -186,7 +186,8 @@ __device__ __noinline__ void epilogue_rows(const float* stage, const GemmEpilogu
           split5(y, w[0], w[1], w[2], w[3], w[4]);
 #pragma unroll
           for (int pl = 0; pl < 5; ++pl)
-            if (pl < nplanes_out) planes[pl * pstride + grow * ldp + gcol + j] = w[pl];
+            if (pl < planes_count(nplanes_out))
+              planes[pl * pstride + grow * ldp + gcol + j] = (nplanes_out == PLANES_H2 && pl < 2) ? w[3 + (pl & 1)] : w[pl];
         }
       }
     }
@@ -252,13 +253,14 @@ __device__ __noinline__ void epilogue_rows(const float* stage, const GemmEpilogu
         if (nplanes_out > 2)
           *reinterpret_cast<uint2*>(pp + 2 * pstride) = make_uint2(pack_bf16x2(p2[0], p2[1]), pack_bf16x2(p2[2], p2[3]));
       }
-      if (nplanes_out == 5) {
+      if (nplanes_out == 5 || nplanes_out == PLANES_H2) {
         uint16_t h0[4], h1[4];
 #pragma unroll
         for (int j = 0; j < 4; ++j) split_h2(y[j], h0[j], h1[j]);
-        *reinterpret_cast<uint2*>(pp + 3 * pstride) =
+        uint16_t* ph = nplanes_out == 5 ? pp + 3 * pstride : pp;
+        *reinterpret_cast<uint2*>(ph) =
             make_uint2((uint32_t)h0[0] | ((uint32_t)h0[1] << 16), (uint32_t)h0[2] | ((uint32_t)h0[3] << 16));
-        *reinterpret_cast<uint2*>(pp + 4 * pstride) =
+        *reinterpret_cast<uint2*>(ph + pstride) =
             make_uint2((uint32_t)h1[0] | ((uint32_t)h1[1] << 16), (uint32_t)h1[2] | ((uint32_t)h1[3] << 16));
       }
     }

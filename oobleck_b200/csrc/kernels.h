@@ -15,18 +15,19 @@ int layernorm_fwd(const float* x, const float* gamma, const float* beta, float* 
 // partials: scratch of at least LN_BWD_MAX_GRID * 2 * E floats
 int layernorm_bwd(const float* dy, const float* x, const float* mean, const float* rstd, const float* gamma,
                   const float* dres, float* dx, bf16* planes, long plane_stride, int nplanes, float* dgamma,
-                  float* dbeta, float* partials, int rows, int E, cudaStream_t s);
+                  float* dbeta, float* partials, int rows, int E, float gscale, cudaStream_t s);
 // out[n] += sum_m a[m,n]; partials: scratch of at least COLSUM_MAX_PARTS * cols floats
-int colsum_accumulate(const float* a, long lda, int rows, int cols, float* out, float* partials, cudaStream_t s);
+int colsum_accumulate(const float* a, long lda, int rows, int cols, float* out, float* partials, float scale,
+                      cudaStream_t s);
 
 int embedding_fwd(const long long* ids, const float* wte, const float* wpe, float* out, int rows, int T, int E,
                   cudaStream_t s);
-int embedding_bwd(const long long* ids, const float* dx, float* dwte, float* dwpe, int B, int T, int E,
+int embedding_bwd(const long long* ids, const float* dx, float* dwte, float* dwpe, int B, int T, int E, float scale,
                   cudaStream_t s);
 
 int cross_entropy(const float* logits, long ldl, const long long* labels, int B, int T, int V, float* row_loss,
                   float* loss, float* total_loss, bf16* dplanes, long ldp, long plane_stride, int nplanes,
-                  cudaStream_t s);
+                  float grad_scale, cudaStream_t s);
 
 int adamw_step(float* p, const float* g, float* m, float* v, bf16* planes, long plane_stride, int nplanes, long n,
                float lr, float beta1, float beta2, float eps, float wd, int step, cudaStream_t s);

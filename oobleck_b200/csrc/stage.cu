@@ -43,6 +43,10 @@ inline PlaneMat weight_planes_h(const oob_layer_params* p, long off, long rows, 
 inline PlaneMat act_planes_h(const void* base, long rows, long cols) {
   return PlaneMat{reinterpret_cast<const bf16*>(base) + 3 * rows * cols, rows, cols, cols, rows * cols, 2, 1};
 }
+// a loss-scaled gradient stored as an fp16 pair at planes 0, 1 (bwd_fp16 mode)
+inline PlaneMat grad_planes_h(const void* base, long rows, long cols) {
+  return PlaneMat{reinterpret_cast<const bf16*>(base), rows, cols, cols, rows * cols, 2, 1};
+}
 inline GemmEpilogue epi_none() {
   GemmEpilogue e{};
   e.alpha = 1.0f;
@@ -67,20 +71,26 @@ int linear_fwd(const void* a_base, bool fp16_ops, const oob_layer_params* p, lon
   return gemm_launch(act_planes(a_base, M, K), 0, weight_planes(p, w_off, K, N), 1, gp, st);
 }
 // dA[M,K] = dY[M,N] . W[K,N]^T  (optionally * gelu'(aux), planes out)
+// dy.fp16 selects the operand family: fp16 pairs (3 products; weights' pair) or bf16 x 3 (6 products)
 int linear_dgrad(const PlaneMat& dy, const oob_layer_params* p, long w_off, int M, int N, int K, int nsplit, float* dA,
-                 const float* dgelu_aux, bf16* planes_out, cudaStream_t st) {
-  GemmParams gp{M, K, N, nsplit, epi_none()};
+                 const float* dgelu_aux, bf16* planes_out, int nplanes_out, cudaStream_t st) {
+  GemmParams gp{M, K, N, dy.fp16 ? 2 : nsplit, epi_none()};
   gp.epi.d = dA; gp.epi.ldd = K;
   if (dgelu_aux) { gp.epi.act = ACT_DGELU; gp.epi.aux = dgelu_aux; gp.epi.ldaux = K; }
-  if (planes_out) { gp.epi.planes = planes_out; gp.epi.ldp = K; gp.epi.plane_stride = (long)M * K; gp.epi.nplanes_out = 3; }
-  return gemm_launch(dy, 0, weight_planes(p, w_off, K, N), 0, gp, st);
+  if (planes_out) {
+    gp.epi.planes = planes_out; gp.epi.ldp = K; gp.epi.plane_stride = (long)M * K; gp.epi.nplanes_out = nplanes_out;
+  }
+  return gemm_launch(dy, 0, dy.fp16 ? weight_planes_h(p, w_off, K, N) : weight_planes(p, w_off, K, N), 0, gp, st);
 }
 // dW[K,N] += A[M,K]^T . dY[M,N]
-int linear_wgrad(const PlaneMat& a, const PlaneMat& dy, const oob_layer_params* p, long w_off, int M, int N, int K,
-                 int nsplit, cudaStream_t st) {
-  GemmParams gp{K, N, M, nsplit, epi_none()};
+// `a_base`: the saved activation's plane buffer; with an fp16-pair dy its fp16 pair (planes 3, 4) is the operand and
+// `unscale` (1 / loss scale) is applied to the product before it is accumulated
+int linear_wgrad(const void* a_base, const PlaneMat& dy, const oob_layer_params* p, long w_off, int M, int N, int K,
+                 int nsplit, float unscale, cudaStream_t st) {
+  GemmParams gp{K, N, M, dy.fp16 ? 2 : nsplit, epi_none()};
   gp.epi.d = p->g + w_off; gp.epi.ldd = N; gp.epi.accumulate = 1;
-  return gemm_launch(a, 1, dy, 1, gp, st);
+  gp.epi.alpha = unscale;
+  return gemm_launch(dy.fp16 ? act_planes_h(a_base, M, K) : act_planes(a_base, M, K), 1, dy, 1, gp, st);
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -135,6 +145,7 @@ int check_dims(const oob_dims* d) {
   OOB_CHECK(d->nsplit >= 1 && d->nsplit <= 3, "nsplit must be 1..3");
   OOB_CHECK(d->batch > 0 && d->seq > 1, "bad micro-batch shape");
   OOB_CHECK(!d->fwd_fp16 || d->nsplit == 3, "fwd_fp16 is the fp32-grade forward mode: it needs nsplit = 3");
+  OOB_CHECK(!d->bwd_fp16 || (d->fwd_fp16 && d->loss_scale > 0.f), "bwd_fp16 needs fwd_fp16 and a positive loss_scale");
   return 0;
 }
 
@@ -178,7 +189,15 @@ int oob_block_backward(const oob_dims* d, const oob_layer_params* p, const float
   const int M = d->batch * d->seq, E = d->n_embd, ns = d->nsplit;
   const BlockOffsets o(E);
   const long ME = (long)M * E;
-  const PlaneMat dyp = act_planes(dy_planes, M, E);
+  // bwd_fp16: activation gradients (dy, dx and the scratch) are multiplied by loss_scale and their planes are fp16
+  // pairs; `us` brings parameter gradients back to true scale where they are produced
+  const bool hb = d->bwd_fp16 != 0;
+  const float us = hb ? 1.0f / d->loss_scale : 1.0f;
+  const int gp_code = hb ? PLANES_H2 : 3;
+  auto gplanes = [&](const void* base, long rows, long cols) {
+    return hb ? grad_planes_h(base, rows, cols) : act_planes(base, rows, cols);
+  };
+  const PlaneMat dyp = gplanes(dy_planes, M, E);
   int rc;
   // weight-gradient work goes to the side stream when the caller provided its scratch (see SideState)
   SideState* ss = s->partials_side ? side_state() : nullptr;
@@ -207,37 +226,39 @@ int oob_block_backward(const oob_dims* d, const oob_layer_params* p, const float
 #define OOB_FORK() do { if (ss && (rc = side_fork(ss, st))) return rc; } while (0)
   // ---- MLP ----
   OOB_FORK();   // dy is ready on main
-  if ((rc = linear_wgrad(act_planes(c->gelu_planes, M, 4 * E), dyp, p, o.proj2_w, M, E, 4 * E, ns, sw))) return rc;
-  if ((rc = colsum_accumulate(dy, E, M, E, p->g + o.proj2_b, wparts, sw))) return rc;
+  if ((rc = linear_wgrad(c->gelu_planes, dyp, p, o.proj2_w, M, E, 4 * E, ns, us, sw))) return rc;
+  if ((rc = colsum_accumulate(dy, E, M, E, p->g + o.proj2_b, wparts, us, sw))) return rc;
   if (ss) { OOB_CUDA_OK(cudaEventRecord(ss->dyread, sw)); ss->dyread_pending = true; ss->any_pending = true; }
   // d(fc pre-activation) = (dy . Wp2^T) * gelu'(fc)
-  if ((rc = linear_dgrad(dyp, p, o.proj2_w, M, E, 4 * E, ns, s->dfc, c->fc, (bf16*)s->dfc_planes, st))) return rc;
-  const PlaneMat dfcp = act_planes(s->dfc_planes, M, 4 * E);
+  if ((rc = linear_dgrad(dyp, p, o.proj2_w, M, E, 4 * E, ns, s->dfc, c->fc, (bf16*)s->dfc_planes, gp_code, st)))
+    return rc;
+  const PlaneMat dfcp = gplanes(s->dfc_planes, M, 4 * E);
   OOB_FORK();
-  if ((rc = linear_wgrad(act_planes(c->ln2_planes, M, E), dfcp, p, o.fc_w, M, 4 * E, E, ns, sw))) return rc;
-  if ((rc = colsum_accumulate(s->dfc, 4 * E, M, 4 * E, p->g + o.fc_b, wparts, sw))) return rc;
-  if ((rc = linear_dgrad(dfcp, p, o.fc_w, M, 4 * E, E, ns, s->dln, nullptr, nullptr, st))) return rc;
+  if ((rc = linear_wgrad(c->ln2_planes, dfcp, p, o.fc_w, M, 4 * E, E, ns, us, sw))) return rc;
+  if ((rc = colsum_accumulate(s->dfc, 4 * E, M, 4 * E, p->g + o.fc_b, wparts, us, sw))) return rc;
+  if ((rc = linear_dgrad(dfcp, p, o.fc_w, M, 4 * E, E, ns, s->dln, nullptr, nullptr, 0, st))) return rc;
   // dx2 = dy + LN2'(dln)
   if ((rc = layernorm_bwd(s->dln, c->x2, c->ln2_mean, c->ln2_rstd, p->w + o.ln2_w, dy, s->dx2, (bf16*)s->dx2_planes,
-                          ME, 3, p->g + o.ln2_w, p->g + o.ln2_b, s->partials, M, E, st))) return rc;
+                          ME, gp_code, p->g + o.ln2_w, p->g + o.ln2_b, s->partials, M, E, us, st))) return rc;
   // ---- attention ----
-  const PlaneMat dx2p = act_planes(s->dx2_planes, M, E);
+  const PlaneMat dx2p = gplanes(s->dx2_planes, M, E);
   OOB_FORK();
-  if ((rc = linear_wgrad(act_planes(c->att_planes, M, E), dx2p, p, o.proj_w, M, E, E, ns, sw))) return rc;
-  if ((rc = colsum_accumulate(s->dx2, E, M, E, p->g + o.proj_b, wparts, sw))) return rc;
-  if ((rc = linear_dgrad(dx2p, p, o.proj_w, M, E, E, ns, s->datt, nullptr, (bf16*)s->datt_planes, st))) return rc;
+  if ((rc = linear_wgrad(c->att_planes, dx2p, p, o.proj_w, M, E, E, ns, us, sw))) return rc;
+  if ((rc = colsum_accumulate(s->dx2, E, M, E, p->g + o.proj_b, wparts, us, sw))) return rc;
+  // d(attention out) feeds the mma.sync attention backward, which still reads bf16 x 3 planes (any range)
+  if ((rc = linear_dgrad(dx2p, p, o.proj_w, M, E, E, ns, s->datt, nullptr, (bf16*)s->datt_planes, 3, st))) return rc;
   if ((rc = attention_bwd((const bf16*)c->qkv_planes, (long)M * 3 * E, c->att, s->datt, (const bf16*)s->datt_planes, ME,
-                          c->lse, s->delta, s->dqkv, (bf16*)s->dqkv_planes, (long)M * 3 * E, 3, d->batch, d->seq,
+                          c->lse, s->delta, s->dqkv, (bf16*)s->dqkv_planes, (long)M * 3 * E, gp_code, d->batch, d->seq,
                           d->n_head, 64, st))) return rc;
-  const PlaneMat dqkvp = act_planes(s->dqkv_planes, M, 3 * E);
+  const PlaneMat dqkvp = gplanes(s->dqkv_planes, M, 3 * E);
   OOB_FORK();
-  if ((rc = linear_wgrad(act_planes(c->ln1_planes, M, E), dqkvp, p, o.attn_w, M, 3 * E, E, ns, sw))) return rc;
-  if ((rc = colsum_accumulate(s->dqkv, 3 * E, M, 3 * E, p->g + o.attn_b, wparts, sw))) return rc;
+  if ((rc = linear_wgrad(c->ln1_planes, dqkvp, p, o.attn_w, M, 3 * E, E, ns, us, sw))) return rc;
+  if ((rc = colsum_accumulate(s->dqkv, 3 * E, M, 3 * E, p->g + o.attn_b, wparts, us, sw))) return rc;
   if (ss) OOB_CUDA_OK(cudaEventRecord(done_ev, sw));
-  if ((rc = linear_dgrad(dqkvp, p, o.attn_w, M, 3 * E, E, ns, s->dln, nullptr, nullptr, st))) return rc;
+  if ((rc = linear_dgrad(dqkvp, p, o.attn_w, M, 3 * E, E, ns, s->dln, nullptr, nullptr, 0, st))) return rc;
   // dx = dx2 + LN1'(dln)
-  if ((rc = layernorm_bwd(s->dln, x, c->ln1_mean, c->ln1_rstd, p->w + o.ln1_w, s->dx2, dx, (bf16*)dx_planes, ME, 3,
-                          p->g + o.ln1_w, p->g + o.ln1_b, s->partials, M, E, st))) return rc;
+  if ((rc = layernorm_bwd(s->dln, x, c->ln1_mean, c->ln1_rstd, p->w + o.ln1_w, s->dx2, dx, (bf16*)dx_planes, ME,
+                          gp_code, p->g + o.ln1_w, p->g + o.ln1_b, s->partials, M, E, us, st))) return rc;
 #undef OOB_FORK
   if (ss && !s->defer_join) return side_join_all(ss, st);
   return 0;
@@ -272,7 +293,8 @@ int oob_head_forward(const oob_dims* d, const oob_layer_params* p, const float* 
   else rc = gemm_launch(act_planes(c->lnf_planes, M, E), 0, weight_planes(p, 2 * E, V, E), 0, gp, st);
   if (rc) return rc;
   return cross_entropy(c->logits, Vp, labels, d->batch, d->seq, V, c->row_loss, c->loss, total_loss,
-                       (bf16*)c->dlogits_planes, Vp, (long)M * Vp, 3, st);
+                       (bf16*)c->dlogits_planes, Vp, (long)M * Vp, d->bwd_fp16 ? PLANES_H2 : 3,
+                       d->bwd_fp16 ? d->loss_scale : 1.0f, st);
 }
 
 int oob_head_backward(const oob_dims* d, const oob_layer_params* p, const float* x, const oob_head_ctx* c,
@@ -281,18 +303,22 @@ int oob_head_backward(const oob_dims* d, const oob_layer_params* p, const float*
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   const int M = d->batch * d->seq, E = d->n_embd, V = d->vocab, Vp = d->vocab_padded, ns = d->nsplit;
   const long ME = (long)M * E;
-  const PlaneMat dlog{reinterpret_cast<const bf16*>(c->dlogits_planes), M, Vp, Vp, (long)M * Vp, 3};
+  const bool hb = d->bwd_fp16 != 0;
+  const float us = hb ? 1.0f / d->loss_scale : 1.0f;
+  const PlaneMat dlog{reinterpret_cast<const bf16*>(c->dlogits_planes), M, Vp, Vp, (long)M * Vp, hb ? 2 : 3, hb ? 1 : 0};
   int rc;
   // d(ln_f out)[M,E] = dlogits[M,V] . Wlm[V,E]
-  GemmParams g1{M, E, V, ns, epi_none()};
+  GemmParams g1{M, E, V, hb ? 2 : ns, epi_none()};
   g1.epi.d = s->dln; g1.epi.ldd = E;
-  if ((rc = gemm_launch(dlog, 0, weight_planes(p, 2 * E, V, E), 1, g1, st))) return rc;
+  if ((rc = gemm_launch(dlog, 0, hb ? weight_planes_h(p, 2 * E, V, E) : weight_planes(p, 2 * E, V, E), 1, g1, st)))
+    return rc;
   // dWlm[V,E] += dlogits^T . lnf
-  GemmParams g2{V, E, M, ns, epi_none()};
-  g2.epi.d = p->g + 2 * E; g2.epi.ldd = E; g2.epi.accumulate = 1;
-  if ((rc = gemm_launch(dlog, 1, act_planes(c->lnf_planes, M, E), 1, g2, st))) return rc;
-  return layernorm_bwd(s->dln, x, c->mean, c->rstd, p->w, nullptr, dx, (bf16*)dx_planes, ME, 3, p->g, p->g + E,
-                       s->partials, M, E, st);
+  GemmParams g2{V, E, M, hb ? 2 : ns, epi_none()};
+  g2.epi.d = p->g + 2 * E; g2.epi.ldd = E; g2.epi.accumulate = 1; g2.epi.alpha = us;
+  if ((rc = gemm_launch(dlog, 1, hb ? act_planes_h(c->lnf_planes, M, E) : act_planes(c->lnf_planes, M, E), 1, g2, st)))
+    return rc;
+  return layernorm_bwd(s->dln, x, c->mean, c->rstd, p->w, nullptr, dx, (bf16*)dx_planes, ME, hb ? PLANES_H2 : 3, p->g,
+                       p->g + E, s->partials, M, E, us, st);
 }
 
 }  // extern "C"

@@ -15,6 +15,8 @@ one GPU per stage, which is the reference's ``NO_SHARD`` branch (layer.py:100-10
 from __future__ import annotations
 
 import ctypes as C
+import math
+import os
 from dataclasses import dataclass
 
 import torch
@@ -24,6 +26,11 @@ from ..module.model import StageLayerSpec
 
 
 from ..lib import OobBlockCtx, OobBwdScratch, OobDims, OobHeadCtx, OobLayerParams  # noqa: E402
+
+
+# default numerics of the backward GEMMs (see Layer.__init__); bench.py / tests flip it explicitly.  On: measured
+# +25 % tokens/s on GPT-2-XL with unchanged gradient parity (worst 3.3e-6 of max vs 2.4e-6, tests/test_stage_gpu.py)
+DEFAULT_BWD_FP16 = os.environ.get("OOB_BWD_FP16", "1") == "1"
 
 
 def _stream() -> C.c_void_p:
@@ -108,7 +115,8 @@ class Layer:
 
     def __init__(self, layer_id: int, layer: StageLayerSpec, process_group=None, pre_stream=None, post_stream=None, *,
                  microbatch_size: int, num_pipe_buffers: int, workspace: StageWorkspace | None = None,
-                 nsplit: int = 3, device: torch.device | None = None, seq_len: int | None = None):
+                 nsplit: int = 3, device: torch.device | None = None, seq_len: int | None = None,
+                 bwd_fp16: bool | None = None):
         L.load()  # fail loudly if the CUDA extension is missing
         if not torch.cuda.is_available():
             raise L.OobleckB200Error("oobleck_b200.Layer needs a CUDA device (there is no CPU path)")
@@ -138,13 +146,18 @@ class Layer:
         # forward GEMMs read fp16 x 2 planes (3 tensor-core products, fp32-grade for bounded-range operands); the
         # bf16 x 3 planes stay for the backward GEMMs: 5-plane buffers (include/oobleck_b200.h)
         self.fwd_fp16 = 1 if nsplit == 3 else 0
+        # backward GEMMs on loss-scaled fp16 pairs as well (3 products); activation gradients inside the stage -- and
+        # across stage boundaries, both sides are this engine -- are carried multiplied by ``loss_scale``
+        self.bwd_fp16 = 1 if (self.fwd_fp16 and (DEFAULT_BWD_FP16 if bwd_fp16 is None else bwd_fp16)) else 0
+        tokens = max(1, microbatch_size * ((seq_len or layer.n_positions) - 1))
+        self.loss_scale = float(16 * 2 ** int(math.floor(math.log2(tokens))))   # dlogits * loss_scale is O(16)
         self.nplanes = 5 if (self.fwd_fp16 and layer.kind != "embedding") else 3
         self.planes = torch.empty(self.nplanes, self.plane_stride, dtype=torch.bfloat16, device=self.device)
         self.refresh_planes()
 
         E, V = layer.n_embd, layer.vocab_size
         self.dims = OobDims(self.mb, self.T, E, layer.n_head, V, (V + 63) // 64 * 64, layer.layer_norm_epsilon, nsplit,
-                            self.fwd_fp16)
+                            self.fwd_fp16, self.bwd_fp16, self.loss_scale)
         self._alloc_contexts()
 
     # -- parameters ------------------------------------------------------------------------------------------------
@@ -272,7 +285,7 @@ class Layer:
             if grad.planes is None:  # arrived from the next stage as fp32 only: split it here
                 dy_planes = ws.recv_planes
                 L.call("oob_split_planes", C.c_void_p(grad.grad.data_ptr()), C.c_void_p(dy_planes.data_ptr()),
-                       grad.grad.numel(), dy_planes.stride(0), 3, _stream())
+                       grad.grad.numel(), dy_planes.stride(0), 22 if self.bwd_fp16 else 3, _stream())
                 grad = HiddenGrad(grad.grad, dy_planes)
             dx, dxp = ws.next_dx()
             if dx.data_ptr() == grad.grad.data_ptr():
@@ -286,7 +299,7 @@ class Layer:
         g = self.flat_grad
         L.call("oob_embedding_bwd", C.c_void_p(input_ids.data_ptr()), C.c_void_p(grad.grad.data_ptr()),
                C.c_void_p(g.data_ptr()), C.c_void_p(g.data_ptr() + self.spec.vocab_size * E * 4), self.mb, self.T, E,
-               _stream())
+               (1.0 / self.loss_scale) if self.bwd_fp16 else 1.0, _stream())
         return None
 
     # -- data parallel -----------------------------------------------------------------------------------------------

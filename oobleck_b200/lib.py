@@ -34,7 +34,8 @@ class GemmEpilogue(C.Structure):
 class OobDims(C.Structure):
     """``oob_dims``."""
     _fields_ = [("batch", C.c_int), ("seq", C.c_int), ("n_embd", C.c_int), ("n_head", C.c_int), ("vocab", C.c_int),
-                ("vocab_padded", C.c_int), ("ln_eps", C.c_float), ("nsplit", C.c_int), ("fwd_fp16", C.c_int)]
+                ("vocab_padded", C.c_int), ("ln_eps", C.c_float), ("nsplit", C.c_int), ("fwd_fp16", C.c_int),
+                ("bwd_fp16", C.c_int), ("loss_scale", C.c_float)]
 
 
 class OobLayerParams(C.Structure):
@@ -75,13 +76,13 @@ _SIGNATURES = {
     "oob_split_planes": (_I, [_P, _P, _L, _L, _I, _P]),
     "oob_gemm": (_I, [C.POINTER(Planes), _I, C.POINTER(Planes), _I, _I, _I, _I, _I, C.POINTER(GemmEpilogue), _P]),
     "oob_layernorm_fwd": (_I, [_P, _P, _P, _P, _P, _L, _I, _P, _P, _I, _I, _F, _P]),
-    "oob_layernorm_bwd": (_I, [_P, _P, _P, _P, _P, _P, _P, _P, _L, _I, _P, _P, _P, _I, _I, _P]),
-    "oob_colsum_accumulate": (_I, [_P, _L, _I, _I, _P, _P, _P]),
+    "oob_layernorm_bwd": (_I, [_P, _P, _P, _P, _P, _P, _P, _P, _L, _I, _P, _P, _P, _I, _I, _F, _P]),
+    "oob_colsum_accumulate": (_I, [_P, _L, _I, _I, _P, _P, _F, _P]),
     "oob_attention_fwd": (_I, [_P, _L, _P, _P, _L, _I, _P, _I, _I, _I, _I, _P]),
     "oob_attention_bwd": (_I, [_P, _L, _P, _P, _P, _L, _P, _P, _P, _P, _L, _I, _I, _I, _I, _I, _P]),
     "oob_embedding_fwd": (_I, [_P, _P, _P, _P, _I, _I, _I, _P]),
-    "oob_embedding_bwd": (_I, [_P, _P, _P, _P, _I, _I, _I, _P]),
-    "oob_cross_entropy": (_I, [_P, _L, _P, _I, _I, _I, _P, _P, _P, _P, _L, _L, _I, _P]),
+    "oob_embedding_bwd": (_I, [_P, _P, _P, _P, _I, _I, _I, _F, _P]),
+    "oob_cross_entropy": (_I, [_P, _L, _P, _I, _I, _I, _P, _P, _P, _P, _L, _L, _I, _F, _P]),
     "oob_adamw_step": (_I, [_P, _P, _P, _P, _P, _L, _I, _L, _F, _F, _F, _F, _F, _I, _P]),
     "oob_block_forward": (_I, [C.POINTER(OobDims), C.POINTER(OobLayerParams), _P, _P, C.POINTER(OobBlockCtx), _P]),
     "oob_block_backward": (_I, [C.POINTER(OobDims), C.POINTER(OobLayerParams), _P, C.POINTER(OobBlockCtx), _P, _P,

@@ -52,6 +52,15 @@ def planes_to_float(p: torch.Tensor, fp16: bool = False) -> torch.Tensor:
     return p[:3].float().sum(0)
 
 
+def pair_to_float(p: torch.Tensor) -> torch.Tensor:
+    """fp16 pair stored at planes 0, 1 (``OOB_PLANES_FP16_PAIR`` output of a gradient producer)."""
+    h = p[0:2].view(torch.float16).float()
+    return h[0] + h[1] / 2048.0
+
+
+PLANES_FP16_PAIR = 22   # include/oobleck_b200.h OOB_PLANES_FP16_PAIR
+
+
 def gemm(a: torch.Tensor, a_mn: bool, b: torch.Tensor, b_mn: bool, M: int, N: int, K: int, *, nsplit=NSPLIT_PARITY,
          d=None, bias=None, resid=None, accumulate=False, act=L.ACT_NONE, aux=None, planes_out=None, alpha=1.0,
          a_fp16=False, b_fp16=False):

@@ -162,18 +162,27 @@ def test_layernorm_fwd_bwd(E):
     dg, db = torch.ones(E, device=DEV), torch.ones(E, device=DEV)  # accumulate onto ones
     part = torch.empty(L.load().oob_ln_bwd_partials_floats(E), device=DEV)
     L.call("oob_layernorm_bwd", P(dy), P(x), P(mean), P(rstd), P(g), P(dres), P(dx), P(dxp), dxp.stride(0), 3, P(dg),
-           P(db), P(part), rows, E, S())
+           P(db), P(part), rows, E, 1.0, S())
     assert rel_err(dx, x64.grad + dres.double()) < 5e-6
     assert rel_err(ops.planes_to_float(dxp), x64.grad + dres.double()) < 5e-6
     assert rel_err(dg - 1, g64.grad) < 5e-6
     assert rel_err(db - 1, b64.grad) < 5e-6
+    # loss-scaled gradient in, fp16 pair out, parameter gradients unscaled
+    S_ = 4096.0
+    dg2, db2 = torch.zeros(E, device=DEV), torch.zeros(E, device=DEV)
+    dys, drs = dy * S_, dres * S_
+    L.call("oob_layernorm_bwd", P(dys), P(x), P(mean), P(rstd), P(g), P(drs), P(dx), P(dxp), dxp.stride(0),
+           ops.PLANES_FP16_PAIR, P(dg2), P(db2), P(part), rows, E, 1.0 / S_, S())
+    assert rel_err(dx / S_, x64.grad + dres.double()) < 5e-6
+    assert rel_err(ops.pair_to_float(dxp) / S_, x64.grad + dres.double()) < 5e-6
+    assert rel_err(dg2, g64.grad) < 5e-6 and rel_err(db2, b64.grad) < 5e-6
 
 
 def test_colsum():
     a = torch.randn(1000, 4800, device=DEV)
     out = torch.ones(4800, device=DEV)
     part = torch.empty(L.load().oob_colsum_partials_floats(4800), device=DEV)
-    L.call("oob_colsum_accumulate", P(a), a.stride(0), 1000, 4800, P(out), P(part), S())
+    L.call("oob_colsum_accumulate", P(a), a.stride(0), 1000, 4800, P(out), P(part), 1.0, S())
     assert rel_err(out - 1, a.double().sum(0)) < 2e-6
 
 
@@ -223,7 +232,7 @@ def test_embedding_fwd_bwd():
     assert torch.equal(h, ref)
     dh = torch.randn(B * T, E, device=DEV)
     dwte, dwpe = torch.zeros_like(wte), torch.zeros_like(wpe)
-    L.call("oob_embedding_bwd", P(ids), P(dh), P(dwte), P(dwpe), B, T, E, S())
+    L.call("oob_embedding_bwd", P(ids), P(dh), P(dwte), P(dwpe), B, T, E, 1.0, S())
     want_wte = torch.zeros_like(wte).double().index_add_(0, ids.view(-1), dh.double())
     assert rel_err(dwte, want_wte) < 2e-6
     assert rel_err(dwpe, dh.double().view(B, T, E).sum(0)) < 2e-6
@@ -238,13 +247,19 @@ def test_cross_entropy():
     loss, total = torch.zeros(1, device=DEV), torch.ones(1, device=DEV)
     dp = ops.new_planes(B * T, Vp)
     L.call("oob_cross_entropy", P(logits), Vp, P(labels), B, T, V, P(row_loss), P(loss), P(total), P(dp), Vp,
-           dp.stride(0), 3, S())
+           dp.stride(0), 3, 1.0, S())
     l64 = logits[:, :V].double().view(B, T, V).requires_grad_(True)
     ref = torch.nn.functional.cross_entropy(l64[:, :-1].reshape(-1, V), labels[:, 1:].reshape(-1))
     ref.backward()
     assert abs(loss.item() - ref.item()) < 1e-5 * abs(ref.item())
     assert abs(total.item() - 1 - ref.item()) < 1e-5 * abs(ref.item())
     got = ops.planes_to_float(dp)
+    assert rel_err(got[:, :V], l64.grad.view(B * T, V)) < 5e-6
+    assert (got[:, V:] == 0).all()
+    # loss-scaled fp16-pair gradient
+    L.call("oob_cross_entropy", P(logits), Vp, P(labels), B, T, V, P(row_loss), P(loss), P(total), P(dp), Vp,
+           dp.stride(0), ops.PLANES_FP16_PAIR, 1024.0, S())
+    got = ops.pair_to_float(dp) / 1024.0
     assert rel_err(got[:, :V], l64.grad.view(B * T, V)) < 5e-6
     assert (got[:, V:] == 0).all()
 

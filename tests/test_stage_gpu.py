@@ -23,7 +23,7 @@ def close(got, want, name, rtol=RTOL):
     return err
 
 
-def build(cfg, mb, nbuf=2, nsplit=3):
+def build(cfg, mb, nbuf=2, nsplit=3, bwd_fp16=False):
     d = og.GPT2Dims(**cfg)
     olayers = og.build_layers(d)
     og.init_layers_(olayers)
@@ -42,19 +42,21 @@ def build(cfg, mb, nbuf=2, nsplit=3):
     layers = []
     for i, spec in enumerate(model.layers):
         assert spec.num_params == sum(p.numel() for p in olayers[i].parameters())
-        l = Layer(i, spec, None, None, None, microbatch_size=mb, num_pipe_buffers=nbuf, workspace=ws, nsplit=nsplit)
+        l = Layer(i, spec, None, None, None, microbatch_size=mb, num_pipe_buffers=nbuf, workspace=ws, nsplit=nsplit,
+                  bwd_fp16=bwd_fp16)
         l.load_flat_(og.flat_params(olayers[i]))
         layers.append(l)
     return d, olayers, layers
 
 
+@pytest.mark.parametrize("bwd_fp16", [False, True])
 @pytest.mark.parametrize("cfg,mb", [
     (dict(n_embd=128, n_head=2, n_layer=2, n_positions=64, vocab_size=503), 2),
     (dict(n_embd=256, n_head=4, n_layer=3, n_positions=256, vocab_size=1000), 3),
     (dict(n_embd=768, n_head=12, n_layer=2, n_positions=1024, vocab_size=50257), 1),
 ])
-def test_stage_forward_backward_parity(cfg, mb):
-    d, olayers, layers = build(cfg, mb)
+def test_stage_forward_backward_parity(cfg, mb, bwd_fp16):
+    d, olayers, layers = build(cfg, mb, bwd_fp16=bwd_fp16)
     total = torch.zeros(1, device="cuda")
     ref_total = 0.0
     n_mb = 2
