@@ -85,10 +85,13 @@ int oob_colsum_accumulate(const float* a, long lda, int rows, int cols, float* o
 
 /* ---- attention (HF GPT2Attention eager: causal softmax(QK^T/sqrt(d))V, no dropout) -----------------------
  * q|k|v and dO are consumed as split planes ([3][B*T][3E] / [3][B*T][E]: the QKV GEMM and the proj dgrad GEMM write
- * them in their epilogues); out/dout fp32 are only read for delta = rowsum(dO * O). */
-int oob_attention_fwd(const void* qkv_planes, long qkv_plane_stride, float* out, void* out_planes, long plane_stride,
-                      int nplanes, float* lse, int batch, int seq, int n_head, int head_dim, void* stream);
-int oob_attention_bwd(const void* qkv_planes, long qkv_plane_stride, const float* out, const float* dout,
+ * them in their epilogues); out/dout fp32 are only read for delta = rowsum(dO * O).
+ * operand_fp16 = 1: q|k|v (and dO) are fp16 pairs [2][..] -- three tensor-core products per MAC instead of six; dO may
+ * then be loss-scaled (the kernel is linear in dO, dqkv comes out with the same scale). */
+int oob_attention_fwd(const void* qkv_planes, long qkv_plane_stride, int operand_fp16, float* out, void* out_planes,
+                      long plane_stride, int nplanes, float* lse, int batch, int seq, int n_head, int head_dim,
+                      void* stream);
+int oob_attention_bwd(const void* qkv_planes, long qkv_plane_stride, int operand_fp16, const float* out, const float* dout,
                       const void* dout_planes, long dout_plane_stride, const float* lse, float* delta, float* dqkv,
                       void* dqkv_planes, long plane_stride, int nplanes, int batch, int seq, int n_head, int head_dim,
                       void* stream);

@@ -74,17 +74,18 @@ int oob_colsum_accumulate(const float* a, long lda, int rows, int cols, float* o
   return colsum_accumulate(a, lda, rows, cols, out, partials, scale, S(stream));
 }
 
-int oob_attention_fwd(const void* qkv_planes, long qkv_plane_stride, float* out, void* out_planes, long plane_stride,
-                      int nplanes, float* lse, int batch, int seq, int n_head, int head_dim, void* stream) {
-  return attention_fwd(reinterpret_cast<const bf16*>(qkv_planes), qkv_plane_stride, out,
+int oob_attention_fwd(const void* qkv_planes, long qkv_plane_stride, int operand_fp16, float* out, void* out_planes,
+                      long plane_stride, int nplanes, float* lse, int batch, int seq, int n_head, int head_dim,
+                      void* stream) {
+  return attention_fwd(reinterpret_cast<const bf16*>(qkv_planes), qkv_plane_stride, operand_fp16, out,
                        reinterpret_cast<bf16*>(out_planes), plane_stride, nplanes, lse, batch, seq, n_head, head_dim,
                        S(stream));
 }
-int oob_attention_bwd(const void* qkv_planes, long qkv_plane_stride, const float* out, const float* dout,
+int oob_attention_bwd(const void* qkv_planes, long qkv_plane_stride, int operand_fp16, const float* out, const float* dout,
                       const void* dout_planes, long dout_plane_stride, const float* lse, float* delta, float* dqkv,
                       void* dqkv_planes, long plane_stride, int nplanes, int batch, int seq, int n_head, int head_dim,
                       void* stream) {
-  return attention_bwd(reinterpret_cast<const bf16*>(qkv_planes), qkv_plane_stride, out, dout,
+  return attention_bwd(reinterpret_cast<const bf16*>(qkv_planes), qkv_plane_stride, operand_fp16, out, dout,
                        reinterpret_cast<const bf16*>(dout_planes), dout_plane_stride, lse, delta, dqkv,
                        reinterpret_cast<bf16*>(dqkv_planes), plane_stride, nplanes, batch, seq, n_head, head_dim,
                        S(stream));

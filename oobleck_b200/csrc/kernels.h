@@ -33,9 +33,10 @@ int adamw_step(float* p, const float* g, float* m, float* v, bf16* planes, long 
                float lr, float beta1, float beta2, float eps, float wd, int step, cudaStream_t s);
 
 // attention.cu -- causal multi-head attention on packed q|k|v split planes [3][B*T][3E] (head h at columns h*D..)
-int attention_fwd(const bf16* qkv_planes, long qkv_plane_stride, float* out, bf16* out_planes, long plane_stride,
-                  int nplanes, float* lse, int B, int T, int H, int D, cudaStream_t s);
-int attention_bwd(const bf16* qkv_planes, long qkv_plane_stride, const float* out, const float* dout,
+// operand_fp16: q|k|v (and dO) planes are fp16 pairs (3 products per MAC) instead of bf16 x 3 (6)
+int attention_fwd(const bf16* qkv_planes, long qkv_plane_stride, int operand_fp16, float* out, bf16* out_planes,
+                  long plane_stride, int nplanes, float* lse, int B, int T, int H, int D, cudaStream_t s);
+int attention_bwd(const bf16* qkv_planes, long qkv_plane_stride, int operand_fp16, const float* out, const float* dout,
                   const bf16* dout_planes, long dout_plane_stride, const float* lse, float* delta, float* dqkv,
                   bf16* dqkv_planes, long plane_stride, int nplanes, int B, int T, int H, int D, cudaStream_t s);
 

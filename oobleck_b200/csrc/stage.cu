@@ -166,9 +166,11 @@ int oob_block_forward(const oob_dims* d, const oob_layer_params* p, const float*
   if ((rc = layernorm_fwd(x, p->w + o.ln1_w, p->w + o.ln1_b, nullptr, (bf16*)c->ln1_planes, ME, np, c->ln1_mean,
                           c->ln1_rstd, M, E, d->ln_eps, st))) return rc;
   // q|k|v go straight to split planes: attention (forward and the recompute in backward) is their only consumer
+  // (fp16 pairs when the backward runs on fp16 pairs too: the attention backward reads q|k|v and dO in ONE format)
+  const int ha = d->bwd_fp16 ? 1 : 0;
   if ((rc = linear_fwd(c->ln1_planes, h, p, o.attn_w, o.attn_b, M, 3 * E, E, ns, nullptr, nullptr,
-                       (bf16*)c->qkv_planes, 3, false, st))) return rc;
-  if ((rc = attention_fwd((const bf16*)c->qkv_planes, (long)M * 3 * E, c->att, (bf16*)c->att_planes, ME, np, c->lse,
+                       (bf16*)c->qkv_planes, ha ? PLANES_H2 : 3, false, st))) return rc;
+  if ((rc = attention_fwd((const bf16*)c->qkv_planes, (long)M * 3 * E, ha, c->att, (bf16*)c->att_planes, ME, np, c->lse,
                           d->batch, d->seq, d->n_head, 64, st))) return rc;
   if ((rc = linear_fwd(c->att_planes, h, p, o.proj_w, o.proj_b, M, E, E, ns, c->x2, x, nullptr, 0, false, st)))
     return rc;
@@ -245,9 +247,10 @@ int oob_block_backward(const oob_dims* d, const oob_layer_params* p, const float
   OOB_FORK();
   if ((rc = linear_wgrad(c->att_planes, dx2p, p, o.proj_w, M, E, E, ns, us, sw))) return rc;
   if ((rc = colsum_accumulate(s->dx2, E, M, E, p->g + o.proj_b, wparts, us, sw))) return rc;
-  // d(attention out) feeds the mma.sync attention backward, which still reads bf16 x 3 planes (any range)
-  if ((rc = linear_dgrad(dx2p, p, o.proj_w, M, E, E, ns, s->datt, nullptr, (bf16*)s->datt_planes, 3, st))) return rc;
-  if ((rc = attention_bwd((const bf16*)c->qkv_planes, (long)M * 3 * E, c->att, s->datt, (const bf16*)s->datt_planes, ME,
+  if ((rc = linear_dgrad(dx2p, p, o.proj_w, M, E, E, ns, s->datt, nullptr, (bf16*)s->datt_planes, gp_code, st)))
+    return rc;
+  if ((rc = attention_bwd((const bf16*)c->qkv_planes, (long)M * 3 * E, hb ? 1 : 0, c->att, s->datt,
+                          (const bf16*)s->datt_planes, ME,
                           c->lse, s->delta, s->dqkv, (bf16*)s->dqkv_planes, (long)M * 3 * E, gp_code, d->batch, d->seq,
                           d->n_head, 64, st))) return rc;
   const PlaneMat dqkvp = gplanes(s->dqkv_planes, M, 3 * E);

@@ -78,8 +78,8 @@ _SIGNATURES = {
     "oob_layernorm_fwd": (_I, [_P, _P, _P, _P, _P, _L, _I, _P, _P, _I, _I, _F, _P]),
     "oob_layernorm_bwd": (_I, [_P, _P, _P, _P, _P, _P, _P, _P, _L, _I, _P, _P, _P, _I, _I, _F, _P]),
     "oob_colsum_accumulate": (_I, [_P, _L, _I, _I, _P, _P, _F, _P]),
-    "oob_attention_fwd": (_I, [_P, _L, _P, _P, _L, _I, _P, _I, _I, _I, _I, _P]),
-    "oob_attention_bwd": (_I, [_P, _L, _P, _P, _P, _L, _P, _P, _P, _P, _L, _I, _I, _I, _I, _I, _P]),
+    "oob_attention_fwd": (_I, [_P, _L, _I, _P, _P, _L, _I, _P, _I, _I, _I, _I, _P]),
+    "oob_attention_bwd": (_I, [_P, _L, _I, _P, _P, _P, _L, _P, _P, _P, _P, _L, _I, _I, _I, _I, _I, _P]),
     "oob_embedding_fwd": (_I, [_P, _P, _P, _P, _I, _I, _I, _P]),
     "oob_embedding_bwd": (_I, [_P, _P, _P, _P, _I, _I, _I, _F, _P]),
     "oob_cross_entropy": (_I, [_P, _L, _P, _I, _I, _I, _P, _P, _P, _P, _L, _L, _I, _F, _P]),

@@ -40,7 +40,7 @@ def split(x: torch.Tensor, out: torch.Tensor | None = None, nplanes: int = 3) ->
     x = x.contiguous()
     rows, cols = x.shape
     if out is None:
-        out = new_planes(rows, cols, nplanes, x.device)
+        out = new_planes(rows, cols, 2 if nplanes == 22 else nplanes, x.device)   # 22 = fp16 pair only
     L.call("oob_split_planes", _ptr(x), _ptr(out), x.numel(), out.stride(0), nplanes, _stream())
     return out
 

@@ -196,15 +196,20 @@ def ref_attention(qkv, B, T, H, D):
     return (att @ v).transpose(1, 2).reshape(B * T, E)
 
 
+@pytest.mark.parametrize("h2", [0, 1])
 @pytest.mark.parametrize("B,T,H", [(2, 128, 3), (1, 100, 2), (2, 1024, 4)])
-def test_attention_fwd_bwd(B, T, H):
+def test_attention_fwd_bwd(B, T, H, h2):
+    """h2 = 1: q|k|v and dO as fp16 pairs (3 products per MAC), dO additionally loss-scaled like in the stage."""
     D, E = 64, H * 64
+    torch.manual_seed(B * 1000 + T + H)
     qkv = torch.randn(B * T, 3 * E, device=DEV)
     out = torch.empty(B * T, E, device=DEV)
     outp = ops.new_planes(B * T, E)
     lse = torch.empty(B, H, T, device=DEV)
-    qp = ops.split(qkv)
-    L.call("oob_attention_fwd", P(qp), qp.stride(0), P(out), P(outp), outp.stride(0), 3, P(lse), B, T, H, D, S())
+    code = ops.PLANES_FP16_PAIR if h2 else 3
+    gscale = 256.0 if h2 else 1.0
+    qp = ops.split(qkv, nplanes=code)
+    L.call("oob_attention_fwd", P(qp), qp.stride(0), h2, P(out), P(outp), outp.stride(0), 3, P(lse), B, T, H, D, S())
     q64 = qkv.double().requires_grad_(True)
     ref = ref_attention(q64, B, T, H, D)
     assert rel_err(out, ref) < 5e-6
@@ -214,11 +219,13 @@ def test_attention_fwd_bwd(B, T, H):
     dqkv = torch.full((B * T, 3 * E), float("nan"), device=DEV)
     dqp = ops.new_planes(B * T, 3 * E)
     delta = torch.empty(B, H, T, device=DEV)
-    dop = ops.split(dout)
-    L.call("oob_attention_bwd", P(qp), qp.stride(0), P(out), P(dout), P(dop), dop.stride(0), P(lse), P(delta), P(dqkv),
-           P(dqp), dqp.stride(0), 3, B, T, H, D, S())
-    assert rel_err(dqkv, q64.grad) < 1e-5
-    assert rel_err(ops.planes_to_float(dqp), q64.grad) < 1e-5
+    dout_s = dout * gscale
+    dop = ops.split(dout_s, nplanes=code)
+    L.call("oob_attention_bwd", P(qp), qp.stride(0), h2, P(out), P(dout_s), P(dop), dop.stride(0), P(lse), P(delta),
+           P(dqkv), P(dqp), dqp.stride(0), code, B, T, H, D, S())
+    assert rel_err(dqkv / gscale, q64.grad) < 1e-5
+    got = ops.pair_to_float(dqp) if h2 else ops.planes_to_float(dqp)
+    assert rel_err(got / gscale, q64.grad) < 1e-5
 
 
 def test_embedding_fwd_bwd():

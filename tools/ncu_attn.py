@@ -22,16 +22,18 @@ dqp = ops.new_planes(B * T, 3 * E)
 delta = torch.empty(B, H, T, device="cuda")
 
 
-qp, dop = ops.split(qkv), ops.split(dout)
+H2 = int(sys.argv[1]) if len(sys.argv) > 1 else 1      # 1: fp16-pair operands (3 products), 0: bf16 x 3 (6)
+CODE = ops.PLANES_FP16_PAIR if H2 else 3
+qp, dop = ops.split(qkv, nplanes=CODE), ops.split(dout, nplanes=CODE)
 
 
 def fwd():
-    L.call("oob_attention_fwd", P(qp), qp.stride(0), P(out), P(outp), outp.stride(0), 3, P(lse), B, T, H, D, S())
+    L.call("oob_attention_fwd", P(qp), qp.stride(0), H2, P(out), P(outp), outp.stride(0), 3, P(lse), B, T, H, D, S())
 
 
 def bwd():
-    L.call("oob_attention_bwd", P(qp), qp.stride(0), P(out), P(dout), P(dop), dop.stride(0), P(lse), P(delta), P(dqkv),
-           P(dqp), dqp.stride(0), 3, B, T, H, D, S())
+    L.call("oob_attention_bwd", P(qp), qp.stride(0), H2, P(out), P(dout), P(dop), dop.stride(0), P(lse), P(delta),
+           P(dqkv), P(dqp), dqp.stride(0), CODE, B, T, H, D, S())
 
 
 for fn, name, flops in [(fwd, "fwd", 4 * B * H * T * T * D / 2), (bwd, "bwd", 10 * B * H * T * T * D / 2)]:
@@ -45,4 +47,4 @@ for fn, name, flops in [(fwd, "fwd", 4 * B * H * T * T * D / 2), (bwd, "bwd", 10
     e1.record()
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / 10
-    print(f"attention {name}: {ms*1e3:.1f} us, {flops/ms/1e9:.1f} TFLOP/s (causal algorithmic)", flush=True)
+    print(f"attention (fp16 pair={H2}) {name}: {ms*1e3:.1f} us, {flops/ms/1e9:.1f} TFLOP/s (causal algorithmic)", flush=True)
