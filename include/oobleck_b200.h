@@ -127,9 +127,12 @@ typedef struct oob_dims {
   int nsplit;              /* bf16 planes per GEMM operand: 3 = fp32-grade (parity), 2, 1 */
   int fwd_fp16;            /* 1 (needs nsplit = 3): forward GEMMs read the fp16 x 2 planes -- every activation / weight
                               plane buffer marked [5] below must then have 5 planes; 0: 3-plane buffers, bf16 only */
-  int bwd_fp16;            /* 1 (needs fwd_fp16 = 1): backward GEMMs run on fp16 pairs too (3 products).  Gradients of
+  int bwd_fp16;            /* 1 (needs fwd_fp16 = 1): the all-fp16-pair mode.  Every plane buffer of the stage API is then
+                              PAIR-ONLY (2 planes, code OOB_PLANES_FP16_PAIR; buffers marked [3|5] below need 2 planes),
+                              except nothing -- attention reads q|k|v and dO as pairs as well.
+                              Backward GEMMs run on fp16 pairs too (3 products).  Gradients of
                               activations are then carried multiplied by loss_scale (fp32 values AND their fp16-pair
-                              planes: dy / dx of the stage API, everything in oob_bwd_scratch except datt_planes);
+                              planes: dy / dx of the stage API, everything in oob_bwd_scratch);
                               parameter gradients are unscaled where they are produced.  0: bf16 x 3 gradients */
   float loss_scale;        /* power of two; oob_head_forward scales dlogits by it (bwd_fp16 = 1 only) */
 } oob_dims;

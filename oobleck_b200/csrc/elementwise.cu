@@ -107,12 +107,19 @@ layernorm_fwd_kernel(const float* __restrict__ x, const float* __restrict__ gamm
         uint16_t pq[5][4];
 #pragma unroll
         for (int j = 0; j < 4; ++j) split5(o[j], pq[0][j], pq[1][j], pq[2][j], pq[3][j], pq[4][j]);
+        const bool h2 = nplanes == PLANES_H2;
+        const int cnt = planes_count(nplanes);
 #pragma unroll
         for (int p = 0; p < 5; ++p) {
-          if (p < nplanes) {
-            uint2 w;
-            w.x = (uint32_t)pq[p][0] | ((uint32_t)pq[p][1] << 16);
-            w.y = (uint32_t)pq[p][2] | ((uint32_t)pq[p][3] << 16);
+          if (p < cnt) {
+            uint2 w;   // pair-only buffers carry h0, h1 at planes 0, 1
+            if (h2 && p < 2) {
+              w.x = (uint32_t)pq[3 + (p & 1)][0] | ((uint32_t)pq[3 + (p & 1)][1] << 16);
+              w.y = (uint32_t)pq[3 + (p & 1)][2] | ((uint32_t)pq[3 + (p & 1)][3] << 16);
+            } else {
+              w.x = (uint32_t)pq[p][0] | ((uint32_t)pq[p][1] << 16);
+              w.y = (uint32_t)pq[p][2] | ((uint32_t)pq[p][3] << 16);
+            }
             *reinterpret_cast<uint2*>(planes + p * plane_stride + (long)row * E + c * 4) = w;
           }
         }
@@ -529,17 +536,22 @@ __global__ void adamw_kernel(float* __restrict__ p, const float* __restrict__ g,
       uint16_t q[5][4];
 #pragma unroll
       for (int j = 0; j < 4; ++j) split5(pv[j], q[0][j], q[1][j], q[2][j], q[3][j], q[4][j]);
+      const bool h2 = nplanes == PLANES_H2;
+      const int cnt = planes_count(nplanes);
 #pragma unroll
       for (int pl = 0; pl < 5; ++pl) {
-        if (pl >= nplanes) break;
+        if (pl >= cnt) break;
         uint16_t* dst = reinterpret_cast<uint16_t*>(planes) + pl * plane_stride + i;
+        uint16_t v4[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) v4[j] = (h2 && pl < 2) ? q[3 + (pl & 1)][j] : q[pl][j];
         if (full) {
           uint2 w;
-          w.x = (uint32_t)q[pl][0] | ((uint32_t)q[pl][1] << 16);
-          w.y = (uint32_t)q[pl][2] | ((uint32_t)q[pl][3] << 16);
+          w.x = (uint32_t)v4[0] | ((uint32_t)v4[1] << 16);
+          w.y = (uint32_t)v4[2] | ((uint32_t)v4[3] << 16);
           *reinterpret_cast<uint2*>(dst) = w;
         } else {
-          for (int j = 0; j < 4 && i + j < n; ++j) dst[j] = q[pl][j];
+          for (int j = 0; j < 4 && i + j < n; ++j) dst[j] = v4[j];
         }
       }
     }

@@ -36,12 +36,14 @@ inline PlaneMat act_planes(const void* base, long rows, long cols) {
   return PlaneMat{reinterpret_cast<const bf16*>(base), rows, cols, cols, rows * cols, 3};
 }
 // the fp16 x 2 pair of a 5-plane buffer (planes 3, 4): forward-GEMM operands when oob_dims.fwd_fp16 is set
-inline PlaneMat weight_planes_h(const oob_layer_params* p, long off, long rows, long cols) {
-  return PlaneMat{reinterpret_cast<const bf16*>(p->w_planes) + 3 * p->plane_stride + off, rows, cols, cols,
+// `at0`: the buffer is pair-only (PLANES_H2, all-fp16 mode) and the pair sits at planes 0, 1
+inline PlaneMat weight_planes_h(const oob_layer_params* p, long off, long rows, long cols, bool at0) {
+  return PlaneMat{reinterpret_cast<const bf16*>(p->w_planes) + (at0 ? 0 : 3) * p->plane_stride + off, rows, cols, cols,
                   p->plane_stride, 2, 1};
 }
-inline PlaneMat act_planes_h(const void* base, long rows, long cols) {
-  return PlaneMat{reinterpret_cast<const bf16*>(base) + 3 * rows * cols, rows, cols, cols, rows * cols, 2, 1};
+inline PlaneMat act_planes_h(const void* base, long rows, long cols, bool at0) {
+  return PlaneMat{reinterpret_cast<const bf16*>(base) + (at0 ? 0 : 3) * rows * cols, rows, cols, cols, rows * cols, 2,
+                  1};
 }
 // a loss-scaled gradient stored as an fp16 pair at planes 0, 1 (bwd_fp16 mode)
 inline PlaneMat grad_planes_h(const void* base, long rows, long cols) {
@@ -56,8 +58,8 @@ inline GemmEpilogue epi_none() {
 // D = A[M,K] . W[K,N] + bias (+resid); optionally the split planes of the result (or of GELU(result))
 // `a_base` is the input's plane buffer: bf16 x 3, or 5 planes when fp16_ops (then the fp16 pair is the operand and the
 // weights' fp16 pair is used: 3 tensor-core products instead of 6)
-int linear_fwd(const void* a_base, bool fp16_ops, const oob_layer_params* p, long w_off, long b_off, int M, int N, int K,
-               int nsplit, float* d, const float* resid, bf16* planes_out, int nplanes_out, bool gelu,
+int linear_fwd(const void* a_base, bool fp16_ops, bool at0, const oob_layer_params* p, long w_off, long b_off, int M, int N,
+               int K, int nsplit, float* d, const float* resid, bf16* planes_out, int nplanes_out, bool gelu,
                cudaStream_t st) {
   GemmParams gp{M, N, K, fp16_ops ? 2 : nsplit, epi_none()};
   gp.epi.d = d; gp.epi.ldd = N;
@@ -67,7 +69,7 @@ int linear_fwd(const void* a_base, bool fp16_ops, const oob_layer_params* p, lon
     gp.epi.act = gelu ? ACT_GELU : ACT_NONE;
     gp.epi.planes = planes_out; gp.epi.ldp = N; gp.epi.plane_stride = (long)M * N; gp.epi.nplanes_out = nplanes_out;
   }
-  if (fp16_ops) return gemm_launch(act_planes_h(a_base, M, K), 0, weight_planes_h(p, w_off, K, N), 1, gp, st);
+  if (fp16_ops) return gemm_launch(act_planes_h(a_base, M, K, at0), 0, weight_planes_h(p, w_off, K, N, at0), 1, gp, st);
   return gemm_launch(act_planes(a_base, M, K), 0, weight_planes(p, w_off, K, N), 1, gp, st);
 }
 // dA[M,K] = dY[M,N] . W[K,N]^T  (optionally * gelu'(aux), planes out)
@@ -80,7 +82,7 @@ int linear_dgrad(const PlaneMat& dy, const oob_layer_params* p, long w_off, int 
   if (planes_out) {
     gp.epi.planes = planes_out; gp.epi.ldp = K; gp.epi.plane_stride = (long)M * K; gp.epi.nplanes_out = nplanes_out;
   }
-  return gemm_launch(dy, 0, dy.fp16 ? weight_planes_h(p, w_off, K, N) : weight_planes(p, w_off, K, N), 0, gp, st);
+  return gemm_launch(dy, 0, dy.fp16 ? weight_planes_h(p, w_off, K, N, true) : weight_planes(p, w_off, K, N), 0, gp, st);
 }
 // dW[K,N] += A[M,K]^T . dY[M,N]
 // `a_base`: the saved activation's plane buffer; with an fp16-pair dy its fp16 pair (planes 3, 4) is the operand and
@@ -90,7 +92,7 @@ int linear_wgrad(const void* a_base, const PlaneMat& dy, const oob_layer_params*
   GemmParams gp{K, N, M, dy.fp16 ? 2 : nsplit, epi_none()};
   gp.epi.d = p->g + w_off; gp.epi.ldd = N; gp.epi.accumulate = 1;
   gp.epi.alpha = unscale;
-  return gemm_launch(dy.fp16 ? act_planes_h(a_base, M, K) : act_planes(a_base, M, K), 1, dy, 1, gp, st);
+  return gemm_launch(dy.fp16 ? act_planes_h(a_base, M, K, true) : act_planes(a_base, M, K), 1, dy, 1, gp, st);
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -159,7 +161,9 @@ int oob_block_forward(const oob_dims* d, const oob_layer_params* p, const float*
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   const int M = d->batch * d->seq, E = d->n_embd, ns = d->nsplit;
   const bool h = d->fwd_fp16 != 0;
-  const int np = h ? 5 : 3;   // planes of every buffer that feeds a forward GEMM (and, as bf16 x 3, a wgrad)
+  const bool at0 = d->bwd_fp16 != 0;   // all-fp16 mode: pair-only buffers, nothing reads bf16 planes any more
+  // plane set of every buffer that feeds a forward GEMM (and a wgrad): pair only / bf16 x 3 + pair / bf16 x 3
+  const int np = at0 ? PLANES_H2 : (h ? 5 : 3);
   const BlockOffsets o(E);
   const long ME = (long)M * E;
   int rc;
@@ -168,17 +172,17 @@ int oob_block_forward(const oob_dims* d, const oob_layer_params* p, const float*
   // q|k|v go straight to split planes: attention (forward and the recompute in backward) is their only consumer
   // (fp16 pairs when the backward runs on fp16 pairs too: the attention backward reads q|k|v and dO in ONE format)
   const int ha = d->bwd_fp16 ? 1 : 0;
-  if ((rc = linear_fwd(c->ln1_planes, h, p, o.attn_w, o.attn_b, M, 3 * E, E, ns, nullptr, nullptr,
+  if ((rc = linear_fwd(c->ln1_planes, h, at0, p, o.attn_w, o.attn_b, M, 3 * E, E, ns, nullptr, nullptr,
                        (bf16*)c->qkv_planes, ha ? PLANES_H2 : 3, false, st))) return rc;
   if ((rc = attention_fwd((const bf16*)c->qkv_planes, (long)M * 3 * E, ha, c->att, (bf16*)c->att_planes, ME, np, c->lse,
                           d->batch, d->seq, d->n_head, 64, st))) return rc;
-  if ((rc = linear_fwd(c->att_planes, h, p, o.proj_w, o.proj_b, M, E, E, ns, c->x2, x, nullptr, 0, false, st)))
+  if ((rc = linear_fwd(c->att_planes, h, at0, p, o.proj_w, o.proj_b, M, E, E, ns, c->x2, x, nullptr, 0, false, st)))
     return rc;
   if ((rc = layernorm_fwd(c->x2, p->w + o.ln2_w, p->w + o.ln2_b, nullptr, (bf16*)c->ln2_planes, ME, np, c->ln2_mean,
                           c->ln2_rstd, M, E, d->ln_eps, st))) return rc;
-  if ((rc = linear_fwd(c->ln2_planes, h, p, o.fc_w, o.fc_b, M, 4 * E, E, ns, c->fc, nullptr, (bf16*)c->gelu_planes, np,
+  if ((rc = linear_fwd(c->ln2_planes, h, at0, p, o.fc_w, o.fc_b, M, 4 * E, E, ns, c->fc, nullptr, (bf16*)c->gelu_planes, np,
                        true, st))) return rc;
-  if ((rc = linear_fwd(c->gelu_planes, h, p, o.proj2_w, o.proj2_b, M, E, 4 * E, ns, y, c->x2, nullptr, 0, false, st)))
+  if ((rc = linear_fwd(c->gelu_planes, h, at0, p, o.proj2_w, o.proj2_b, M, E, 4 * E, ns, y, c->x2, nullptr, 0, false, st)))
     return rc;
   return 0;
 }
@@ -288,11 +292,12 @@ int oob_head_forward(const oob_dims* d, const oob_layer_params* p, const float* 
   int rc;
   // flat layout: ln_f.weight [E], ln_f.bias [E], lm_head.weight [V,E]
   const bool h = d->fwd_fp16 != 0;
-  if ((rc = layernorm_fwd(x, p->w, p->w + E, nullptr, (bf16*)c->lnf_planes, ME, h ? 5 : 3, c->mean, c->rstd, M, E,
-                          d->ln_eps, st))) return rc;
+  const bool at0 = d->bwd_fp16 != 0;
+  if ((rc = layernorm_fwd(x, p->w, p->w + E, nullptr, (bf16*)c->lnf_planes, ME, at0 ? PLANES_H2 : (h ? 5 : 3), c->mean,
+                          c->rstd, M, E, d->ln_eps, st))) return rc;
   GemmParams gp{M, V, E, h ? 2 : ns, epi_none()};
   gp.epi.d = c->logits; gp.epi.ldd = Vp;
-  if (h) rc = gemm_launch(act_planes_h(c->lnf_planes, M, E), 0, weight_planes_h(p, 2 * E, V, E), 0, gp, st);
+  if (h) rc = gemm_launch(act_planes_h(c->lnf_planes, M, E, at0), 0, weight_planes_h(p, 2 * E, V, E, at0), 0, gp, st);
   else rc = gemm_launch(act_planes(c->lnf_planes, M, E), 0, weight_planes(p, 2 * E, V, E), 0, gp, st);
   if (rc) return rc;
   return cross_entropy(c->logits, Vp, labels, d->batch, d->seq, V, c->row_loss, c->loss, total_loss,
@@ -313,12 +318,13 @@ int oob_head_backward(const oob_dims* d, const oob_layer_params* p, const float*
   // d(ln_f out)[M,E] = dlogits[M,V] . Wlm[V,E]
   GemmParams g1{M, E, V, hb ? 2 : ns, epi_none()};
   g1.epi.d = s->dln; g1.epi.ldd = E;
-  if ((rc = gemm_launch(dlog, 0, hb ? weight_planes_h(p, 2 * E, V, E) : weight_planes(p, 2 * E, V, E), 1, g1, st)))
+  if ((rc = gemm_launch(dlog, 0, hb ? weight_planes_h(p, 2 * E, V, E, true) : weight_planes(p, 2 * E, V, E), 1, g1, st)))
     return rc;
   // dWlm[V,E] += dlogits^T . lnf
   GemmParams g2{V, E, M, hb ? 2 : ns, epi_none()};
   g2.epi.d = p->g + 2 * E; g2.epi.ldd = E; g2.epi.accumulate = 1; g2.epi.alpha = us;
-  if ((rc = gemm_launch(dlog, 1, hb ? act_planes_h(c->lnf_planes, M, E) : act_planes(c->lnf_planes, M, E), 1, g2, st)))
+  if ((rc = gemm_launch(dlog, 1, hb ? act_planes_h(c->lnf_planes, M, E, true) : act_planes(c->lnf_planes, M, E), 1, g2,
+                        st)))
     return rc;
   return layernorm_bwd(s->dln, x, c->mean, c->rstd, p->w, nullptr, dx, (bf16*)dx_planes, ME, hb ? PLANES_H2 : 3, p->g,
                        p->g + E, s->partials, M, E, us, st);

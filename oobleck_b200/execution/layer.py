@@ -148,11 +148,17 @@ class Layer:
         self.fwd_fp16 = 1 if nsplit == 3 else 0
         # backward GEMMs on loss-scaled fp16 pairs as well (3 products); activation gradients inside the stage -- and
         # across stage boundaries, both sides are this engine -- are carried multiplied by ``loss_scale``
-        self.bwd_fp16 = 1 if (self.fwd_fp16 and (DEFAULT_BWD_FP16 if bwd_fp16 is None else bwd_fp16)) else 0
         tokens = max(1, microbatch_size * ((seq_len or layer.n_positions) - 1))
         self.loss_scale = float(16 * 2 ** int(math.floor(math.log2(tokens))))   # dlogits * loss_scale is O(16)
-        self.nplanes = 5 if (self.fwd_fp16 and layer.kind != "embedding") else 3
-        self.planes = torch.empty(self.nplanes, self.plane_stride, dtype=torch.bfloat16, device=self.device)
+        # placed here because the plane layout depends on it: all-fp16 mode keeps pair-only buffers
+        self.bwd_fp16 = 1 if (self.fwd_fp16 and (DEFAULT_BWD_FP16 if bwd_fp16 is None else bwd_fp16)) else 0
+        # plane-set code handed to the producers (include/oobleck_b200.h) and the number of planes allocated
+        if layer.kind == "embedding" or not self.fwd_fp16:
+            self.nplanes = 3
+        else:
+            self.nplanes = 22 if self.bwd_fp16 else 5
+        self.nplane_count = 2 if self.nplanes == 22 else self.nplanes
+        self.planes = torch.empty(self.nplane_count, self.plane_stride, dtype=torch.bfloat16, device=self.device)
         self.refresh_planes()
 
         E, V = layer.n_embd, layer.vocab_size
@@ -207,7 +213,8 @@ class Layer:
         self.ctx_tensors, self.ctx, self.out, self.saved_in = [], [], [], [None] * self.num_pipe_buffers
         for _ in range(self.num_pipe_buffers):
             if self.spec.kind == "block":
-                np_ = 5 if self.fwd_fp16 else 3   # buffers that feed a forward GEMM also carry the fp16 pair
+                # buffers that feed a forward GEMM: pair only (all-fp16 mode) / bf16 x 3 + pair / bf16 x 3
+                np_ = 2 if self.bwd_fp16 else (5 if self.fwd_fp16 else 3)
                 t = {"ln1_planes": torch.empty(np_, M, E, **bf), "ln1_mean": torch.empty(M, **f32),
                      "ln1_rstd": torch.empty(M, **f32), "qkv_planes": torch.empty(3, M, 3 * E, **bf),
                      "att": torch.empty(M, E, **f32), "att_planes": torch.empty(np_, M, E, **bf),
@@ -219,7 +226,8 @@ class Layer:
                 self.out.append(torch.empty(self.mb, self.T, E, **f32).requires_grad_(True))
             elif self.spec.kind == "head":
                 Vp = self.dims.vocab_padded
-                t = {"lnf_planes": torch.empty(5 if self.fwd_fp16 else 3, M, E, **bf), "mean": torch.empty(M, **f32),
+                t = {"lnf_planes": torch.empty(2 if self.bwd_fp16 else (5 if self.fwd_fp16 else 3), M, E, **bf),
+                     "mean": torch.empty(M, **f32),
                      "rstd": torch.empty(M, **f32), "logits": torch.empty(M, Vp, **f32),
                      "dlogits_planes": torch.empty(3, M, Vp, **bf), "row_loss": torch.empty(M, **f32),
                      "loss": torch.zeros(1, **f32)}
