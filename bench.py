@@ -201,6 +201,9 @@ def run_ours(args, cfg):
     if args.bwd_fp16 is not None:
         _layer.DEFAULT_BWD_FP16 = bool(args.bwd_fp16)
     bwd_fp16 = bool(_layer.DEFAULT_BWD_FP16) and args.nsplit == 3
+    from oobleck_b200.execution import pipeline as _pipeline
+    if args.fb_overlap is not None:
+        _pipeline.FB_OVERLAP = bool(args.fb_overlap)
     torch.cuda.set_device(local_rank)
     L.load()
     ma = cfg["model_args"]
@@ -294,6 +297,7 @@ def run_ours(args, cfg):
                                f"micro-batch {mb}, {gb // mb} micro-batches/step, T={T}, AdamW",
                    "global_batch": gb, "seq_len": T, "parallelism": f"pp{world}", "nsplit": args.nsplit,
                    "wgrad_side_stream": bool(args.side_stream), "bwd_fp16": bwd_fp16,
+                   "fb_overlap": bool(_pipeline.FB_OVERLAP),
                    "l2": "working set per step (>6 GB of weights) far exceeds the 126 MB L2; no flush needed"},
         "clocks": clocks,
         "gpu_launches": int(launches),
@@ -311,10 +315,11 @@ def run_ours(args, cfg):
             "executed_frac_of_peak": (exec_tflops / peaks["bf16_tflops"]) if exec_tflops else None,
             "launches_timed": int(g_n.value),
             "timing_note": "last timed step runs with the wgrad side stream off so each launch is timed alone",
-            # dram__bytes_read.sum + dram__bytes_write.sum of ONE launch (forward FC GEMM 2048x6400x1600, nsplit 3) from
-            # profiles/r01_ncu_gemm_v3.txt; algorithmic bytes of that launch: 133 MB (3 planes of A and B + fp32 D)
-            "traffic": 107.3e6 if args.model == "gpt2-xl" and args.nsplit == 3 else None,
-            "traffic_note": "bytes/launch, ncu --set full, forward-FC shape; `achieved` aggregates all GEMM shapes",
+            # dram__bytes_read.sum + dram__bytes_write.sum of ONE launch (forward FC GEMM 2048x6400x1600 on fp16 pairs,
+            # bias + GELU epilogue writing fp32 + 5 planes) from profiles/r01_ncu_gemm_fwdfc_v5.txt: 60.7 MB read +
+            # 130.9 MB written; algorithmic bytes of that launch: 54 MB of operand planes + 183 MB of outputs
+            "traffic": 191.6e6 if args.model == "gpt2-xl" and args.nsplit == 3 else None,
+            "traffic_note": "bytes/launch, ncu --set full, forward-FC launch; `achieved` aggregates all GEMM shapes",
         },
     }
     if world == 1:
@@ -337,6 +342,8 @@ def main():
     ap.add_argument("--bwd-fp16", type=int, default=None, choices=[0, 1],
                     help="backward GEMMs on loss-scaled fp16 pairs (3 products) instead of bf16 x 3 (6); default: the "
                          "library default (oobleck_b200.execution.layer.DEFAULT_BWD_FP16)")
+    ap.add_argument("--fb-overlap", type=int, default=None, choices=[0, 1],
+                    help="forward(i+1) / backward(i) on two streams; default: oobleck_b200.execution.pipeline.FB_OVERLAP")
     ap.add_argument("--side-stream", type=int, default=1, choices=[0, 1],
                     help="0: weight-gradient kernels stay on the compute stream (A/B of the overlap)")
     args = ap.parse_args()

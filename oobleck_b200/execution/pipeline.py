@@ -20,6 +20,7 @@ What changed underneath:
 """
 from __future__ import annotations
 
+import os
 import weakref
 from collections.abc import Mapping
 from typing import Any
@@ -53,6 +54,10 @@ class RankGroup:
 
 def _my_rank() -> int:
     return dist.get_rank() if dist.is_initialized() else 0
+
+
+# forward / backward passes of consecutive micro-batches on two CUDA streams (OobleckPipeline.train)
+FB_OVERLAP = os.environ.get("OOB_FB_OVERLAP", "0") == "1"
 
 
 class PipelineExecution:
@@ -311,11 +316,45 @@ class OobleckPipeline:
             SendGrad: self.communication.send_gradients,
             RecvGrad: self.communication.recv_gradients,
         }
+        # Forward-family instructions of micro-batch i+1 and backward-family instructions of micro-batch i are
+        # independent (weights change only in optimizer_step): with FB_OVERLAP they are enqueued on two CUDA streams,
+        # ordered by three kinds of events only -- forward(b) -> backward(b), backward(b) -> next occupant of pipe
+        # buffer b, end of step -> optimizer.  The GPU then fills the short last waves / small kernels of one pass
+        # with CTAs of the other.  Issue order (the reference's 1F1B program) is unchanged.
+        overlap = FB_OVERLAP and self.device.type == "cuda" and torch.cuda.is_available()
+        if overlap:
+            if getattr(self, "_fwd_stream", None) is None:
+                self._fwd_stream = torch.cuda.Stream()
+            main, fwd = torch.cuda.current_stream(), self._fwd_stream
+            fwd.wait_stream(main)                       # previous optimizer step / reconfiguration copies
+            fwd_done: dict[int, torch.cuda.Event] = {}
+            bwd_done: dict[int, torch.cuda.Event] = {}
+        forward_family = (LoadMicroBatch, RecvActivation, ForwardPass, SendActivation)
         for step_cmds in self.train_schedule:
             for cmd in step_cmds:
                 if type(cmd) not in instruction_map:
                     raise RuntimeError(f"{self.__class__.__name__} does not understand instruction {repr(cmd)}")
-                instruction_map[type(cmd)](**cmd.kwargs)
+                if not overlap:
+                    instruction_map[type(cmd)](**cmd.kwargs)
+                    continue
+                b = cmd.kwargs.get("buffer_id")
+                if type(cmd) in forward_family:
+                    with torch.cuda.stream(fwd):
+                        if b in bwd_done:               # the previous occupant of this pipe buffer has been consumed
+                            fwd.wait_event(bwd_done.pop(b))
+                        instruction_map[type(cmd)](**cmd.kwargs)
+                        if type(cmd) is ForwardPass:
+                            fwd_done[b] = torch.cuda.Event()
+                            fwd_done[b].record(fwd)
+                else:
+                    if type(cmd) in (BackwardPass, RecvGrad) and b in fwd_done:
+                        main.wait_event(fwd_done.pop(b))
+                    instruction_map[type(cmd)](**cmd.kwargs)
+                    if type(cmd) is BackwardPass:
+                        bwd_done[b] = torch.cuda.Event()
+                        bwd_done[b].record(main)
+        if overlap:
+            main.wait_stream(fwd)                       # losses, activations still in flight -> optimizer / caller
         for name, pipe_buffers in self.pipe_buffers.items():      # :483-485
             self.pipe_buffers[name] = [None] * len(pipe_buffers)
         self._global_step += 1

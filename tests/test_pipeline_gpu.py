@@ -72,3 +72,34 @@ def test_training_loss_curve_matches_oracle():
     # test_layer.py:125-136: optimizer state keys exist after a step
     st = pipe.execution._optimizer.state[pipe.execution._layers[1].flat_param]
     assert {"step", "exp_avg", "exp_avg_sq"} <= set(st)
+
+
+def test_fb_overlap_gives_the_same_training():
+    """Forward of micro-batch i+1 overlapped with backward of micro-batch i (two streams) must train identically
+    (up to the float atomics of the embedding scatter)."""
+    from oobleck_b200.execution import pipeline as P
+    margs = dict(n_embd=128, n_head=2, num_hidden_layers=3, n_positions=64, vocab_size=500)
+    M, mb, steps = 4, 2, 3
+    curves = {}
+    for on in (False, True):
+        old = P.FB_OVERLAP
+        P.FB_OVERLAP = on
+        try:
+            args = OobleckArguments(job=JobArguments(microbatch_size=mb, global_microbatch_size=mb * M, steps=steps),
+                                    model=ModelArguments(model_name="gpt2", model_tag="t", model_args=margs))
+            ds = SyntheticTokenDataset(num_samples=256, seq_len=64, vocab_size=500)
+            eng = OobleckEngine(0, 1, 1, None, args, dataset=ds)
+            eng.initialize_distributed()
+            eng.instantiate_pipelines(M)
+            losses = []
+            for _ in range(steps):
+                eng._train_step()
+                losses.append(float(eng._pipeline.execution.total_loss.item()))
+            params = torch.cat([l.flat_param.flatten() for l in eng._pipeline.execution._layers]).clone()
+            curves[on] = (losses, params)
+        finally:
+            P.FB_OVERLAP = old
+    (l0, p0), (l1, p1) = curves[False], curves[True]
+    for a, b in zip(l0, l1):
+        assert abs(a - b) <= 1e-6 * abs(a), (l0, l1)
+    assert ((p0 - p1).abs().max() / p0.abs().max()).item() < 1e-5
