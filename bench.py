@@ -243,10 +243,12 @@ def run_ours(args, cfg):
                 # per-launch GEMM durations for the roofline: this one step keeps every kernel on the compute stream
                 # (no wgrad side stream), so a launch's event pair times that launch alone
                 L.call("oob_side_stream_enable", 0)
+                fb_saved, _pipeline.FB_OVERLAP = _pipeline.FB_OVERLAP, False
                 L.call("oob_gemm_timing_begin")
             engine._train_step()
             if time_gemms and i == nsteps - 1:
                 L.call("oob_side_stream_enable", args.side_stream)
+                _pipeline.FB_OVERLAP = fb_saved
             if read_loss and is_last:
                 losses.append(float(engine._pipeline.execution.total_loss.item()))   # D2H of the step's result
         e1.record()
@@ -314,7 +316,8 @@ def run_ours(args, cfg):
             "executed_tensor_tflops": exec_tflops,
             "executed_frac_of_peak": (exec_tflops / peaks["bf16_tflops"]) if exec_tflops else None,
             "launches_timed": int(g_n.value),
-            "timing_note": "last timed step runs with the wgrad side stream off so each launch is timed alone",
+            "timing_note": "the last timed step runs without the wgrad side stream and without forward/backward "
+                           "stream overlap, so each GEMM launch is timed alone",
             # dram__bytes_read.sum + dram__bytes_write.sum of ONE launch (forward FC GEMM 2048x6400x1600 on fp16 pairs,
             # bias + GELU epilogue writing fp32 + 5 planes) from profiles/r01_ncu_gemm_fwdfc_v5.txt: 60.7 MB read +
             # 130.9 MB written; algorithmic bytes of that launch: 54 MB of operand planes + 183 MB of outputs
