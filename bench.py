@@ -158,7 +158,11 @@ def run_reference(args, cfg):
         "impl": "reference", "metric": "training_tokens_per_s", "value": value, "unit": "tokens/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec * 1e3,
         "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"{args.model} pipeline train step (oracle port of the reference torch path, CPU)",
+        "config": {"workload": f"{args.model} 1F1B train step: {cfg['model_args']['num_hidden_layers'] + 2} stage layers, "
+                               f"micro-batch {cfg['microbatch']}, {cfg['global_batch'] // cfg['microbatch']} "
+                               f"micro-batches/step, T={cfg['model_args']['n_positions']} -- oracle port of the "
+                               "reference's torch path on the host cores, one bounded sample per step",
+                   "global_batch": cfg["global_batch"], "seq_len": cfg["model_args"]["n_positions"],
                    "sample": smp.sample},
         "cpu_baseline": {"value": value, "unit": "tokens/s", "cores": smp.cores, "kind": "port", "sample": smp.sample},
         "e2e": {"value": value, "unit": "tokens/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
