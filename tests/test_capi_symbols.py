@@ -22,3 +22,16 @@ def test_library_exports_all_symbols():
     assert lib.oob_version() >= 100
     for name in declared_symbols():
         assert hasattr(lib, name)
+
+
+def test_binding_argument_counts_match_the_prototypes():
+    """Every prototype in the header has as many parameters as the ctypes signature in lib.py."""
+    src = open(os.path.join(ROOT, "include", "oobleck_b200.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    src = re.sub(r"\s+", " ", src)
+    protos = dict(re.findall(r"\b(oob_[a-z0-9_]+) ?\(([^()]*)\) ?;", src))
+    assert set(protos) == set(L._SIGNATURES)
+    for name, params in protos.items():
+        params = params.strip()
+        n = 0 if params in ("", "void") else params.count(",") + 1
+        assert n == len(L._SIGNATURES[name][1]), (name, n, len(L._SIGNATURES[name][1]))
