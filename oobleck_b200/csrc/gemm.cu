@@ -1,4 +1,4 @@
-// Host launcher for the tcgen05 split-bf16 GEMM: builds the TMA tensor maps and picks the stage count.
+// Host launcher for the tcgen05 split-plane GEMM: builds the TMA tensor maps and picks the stage count.
 #include <cstdlib>
 #include <mutex>
 #include <vector>

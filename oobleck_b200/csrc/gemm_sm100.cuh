@@ -2,8 +2,9 @@
 //
 //   D[M,N] (fp32) = sum over split products of A_p[M,K] * B_q[K,N]      (+ fused epilogue)
 //
-// Operands are split-bf16 planes (common.cuh) so that the tensor cores reproduce the reference's fp32
-// Conv1D / Linear arithmetic (oobleck/execution/layer.py:104-105 pins fp32; HF GPT-2 addmm).
+// Operands are split 16-bit planes (common.cuh: fp16 pairs = 3 products per MAC, the default; bf16 x 3 = 6 products,
+// any range) so that the tensor cores reproduce the reference's fp32 Conv1D / Linear arithmetic
+// (oobleck/execution/layer.py:104-105 pins fp32; HF GPT-2 addmm).
 // Either operand may be K-major (contraction index contiguous) or MN-major (output index contiguous), which is
 // what lets forward (X.W), dgrad (dY.W^T) and wgrad (X^T.dY) all read the SAME natural row-major buffers
 // without a transpose pass:
@@ -11,13 +12,13 @@
 //     dgrad    dX = dY . W^T    A = dY [M,N] K-major    B = W  [K,N] as [N_out=K][contract=N] K-major
 //     wgrad    dW = X^T. dY     A = X  [tok,K] M-major  B = dY [tok,N] N-major
 //
-// Structure (one CTA per 128 x BN output tile, 192 threads):
+// Structure (gemm_sm100_persistent.cuh: a CTA pair walks 256 x BN output tiles; 192 threads per CTA):
 //   warp 0    TMA producer  : cp.async.bulk.tensor.3d of all planes of the A and B k-block into a
 //                             multi-stage SWIZZLE_128B shared-memory ring, mbarrier complete_tx
 //   warp 1    MMA issuer    : one elected thread issues tcgen05.mma (128 x BN x 16, bf16 -> fp32 in TMEM),
 //                             tcgen05.commit releases ring slots / signals the epilogue; owns TMEM alloc
-//   warps 2-5 epilogue      : tcgen05.ld 32x32b from TMEM, fused bias / residual / GELU / dGELU /
-//                             accumulate, fp32 and/or split-bf16 stores
+//   warps 2-5 epilogue      : tcgen05.ld 32x32b from TMEM + fp32 promotion, then the slab-transposed fused epilogue
+//                             below (bias / residual / GELU / dGELU / accumulate, fp32 and/or plane stores)
 #pragma once
 #include "common.cuh"
 
@@ -291,13 +292,13 @@ __device__ __forceinline__ void epilogue_slab(const float* x, float* stage, cons
 //     let the MMA warp run one chunk ahead of the fold;
 //   * the correction products ("corr", 2^-8 of main and smaller) accumulate over the whole contraction in a third
 //     TMEM region -- their truncation error is 2^-8 smaller still -- and are folded once at the end.
-// TMEM: main[2] + corr = 3 x BN columns.  (First version folded main+corr every 4 k-blocks: the extra TMEM reads
+// TMEM: main[2] + corr[2] (one per tile parity of the persistent loop) = 4 x BN = 512 columns.  (First version folded main+corr every 4 k-blocks: the extra TMEM reads
 // cost 35% of the GEMM's throughput -- profiles/README.md.)
 constexpr int GEMM_CHUNK_ELEMS = 512;   // contraction elements per promotion chunk = 32 main MMAs
 
 // Host side -----------------------------------------------------------------------------------------------------
 
-// A split-bf16 matrix as stored in HBM: [nplanes][rows][ld] row-major.
+// A split matrix as stored in HBM: [nplanes][rows][ld] row-major, 2-byte elements.
 struct PlaneMat {
   const bf16* base;
   long rows;          // number of rows of the stored matrix

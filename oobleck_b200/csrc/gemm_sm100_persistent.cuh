@@ -1,4 +1,4 @@
-// Persistent split-bf16 GEMM (1-CTA and 2-CTA/cta_group::2 in one template): one CTA (pair) per SM (pair) walks a
+// Persistent split-plane GEMM (1-CTA and 2-CTA/cta_group::2 in one template): one CTA (pair) per SM (pair) walks a
 // static list of output tiles, so the TMA ring, the MMA stream and the epilogue of consecutive tiles overlap:
 //
 //   producer  : keeps filling the smem ring straight across tile boundaries
