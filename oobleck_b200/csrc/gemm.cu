@@ -1,6 +1,8 @@
 // Host launcher for the tcgen05 split-plane GEMM: builds the TMA tensor maps and picks the stage count.
+#include <atomic>
 #include <cstdlib>
 #include <mutex>
+#include <unordered_map>
 #include <vector>
 
 #include "gemm_sm100.cuh"
@@ -44,6 +46,44 @@ static int make_map(CUtensorMap* m, const PlaneMat& a, int box_rows, int box_pla
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   OOB_CHECK(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed (%d): rows=%ld cols=%ld ld=%ld", (int)r, a.rows, a.cols,
             a.ld);
+  return 0;
+}
+
+// Descriptor cache.  A training step launches the same few hundred (buffer, shape, box) combinations every micro-batch
+// (round 1 encoded two maps per GEMM on the host: 74 k cuTensorMapEncodeTiled calls per GPT-2-XL step); a map depends
+// only on the key below, never on the buffer's contents, so entries stay valid for as long as the address is reused
+// for the same shape.  Per host thread (no lock); bounded.
+struct MapKey {
+  const void* base; long rows, cols, ld, plane_stride; int nplanes, box_rows, box_planes, bk;
+  bool operator==(const MapKey& o) const {
+    return base == o.base && rows == o.rows && cols == o.cols && ld == o.ld && plane_stride == o.plane_stride &&
+           nplanes == o.nplanes && box_rows == o.box_rows && box_planes == o.box_planes && bk == o.bk;
+  }
+};
+struct MapKeyHash {
+  size_t operator()(const MapKey& k) const {
+    size_t h = reinterpret_cast<size_t>(k.base) * 0x9E3779B97F4A7C15ull;
+    auto mix = [&h](size_t v) { h ^= v + 0x9E3779B97F4A7C15ull + (h << 6) + (h >> 2); };
+    mix((size_t)k.rows); mix((size_t)k.cols); mix((size_t)k.ld); mix((size_t)k.plane_stride);
+    mix((size_t)k.nplanes * 1000003u + (size_t)k.box_rows * 10007u + (size_t)k.box_planes * 101u + (size_t)k.bk);
+    return h;
+  }
+};
+static std::atomic<long> g_map_encodes{0};
+long tensor_map_encodes() { return g_map_encodes.load(); }
+
+int tensor_map_3d(const CUtensorMap** out, const PlaneMat& a, int box_rows, int box_planes, int bk) {
+  thread_local std::unordered_map<MapKey, CUtensorMap, MapKeyHash> cache;
+  const MapKey key{a.base, a.rows, a.cols, a.ld, a.plane_stride, a.nplanes, box_rows, box_planes, bk};
+  auto it = cache.find(key);
+  if (it == cache.end()) {
+    if (cache.size() >= 16384) cache.clear();
+    CUtensorMap m;
+    if (int rc = make_map(&m, a, box_rows, box_planes, bk)) return rc;
+    g_map_encodes.fetch_add(1, std::memory_order_relaxed);
+    it = cache.emplace(key, m).first;
+  }
+  *out = &it->second;
   return 0;
 }
 
@@ -165,26 +205,28 @@ int gemm_launch(const PlaneMat& A, int a_mn, const PlaneMat& B, int b_mn, const 
   static const int env_bk = [] { const char* e = getenv("OOB_GEMM_BK"); return e ? atoi(e) : -1; }();
   const int use_2cta = env_2cta >= 0 ? env_2cta : 1;
   const int bk = (env_bk == 32 || env_bk == 64) ? env_bk : 64;
-  CUtensorMap ta, tb;
+  const CUtensorMap *pta = nullptr, *ptb = nullptr;
   int rc;
   // K-major operand: stored [MN][K] -> box {bk k, tile rows, planes}; MN-major: stored [K][MN] -> box {bk mn, bk rows}
   if (!a_mn) {
     OOB_CHECK(A.rows >= p.M && A.cols >= p.K, "A (K-major) is %ld x %ld, need %d x %d", A.rows, A.cols, p.M, p.K);
-    rc = make_map(&ta, PlaneMat{A.base, (long)p.M, (long)p.K, A.ld, A.plane_stride, A.nplanes}, GEMM_BM, p.nsplit, bk);
+    rc = tensor_map_3d(&pta, PlaneMat{A.base, (long)p.M, (long)p.K, A.ld, A.plane_stride, A.nplanes}, GEMM_BM, p.nsplit, bk);
   } else {
     OOB_CHECK(A.rows >= p.K && A.cols >= p.M, "A (M-major) is %ld x %ld, need %d x %d", A.rows, A.cols, p.K, p.M);
-    rc = make_map(&ta, PlaneMat{A.base, (long)p.K, (long)p.M, A.ld, A.plane_stride, A.nplanes}, bk, p.nsplit, bk);
+    rc = tensor_map_3d(&pta, PlaneMat{A.base, (long)p.K, (long)p.M, A.ld, A.plane_stride, A.nplanes}, bk, p.nsplit, bk);
   }
   if (rc) return rc;
   if (!b_mn) {
     OOB_CHECK(B.rows >= p.N && B.cols >= p.K, "B (K-major) is %ld x %ld, need %d x %d", B.rows, B.cols, p.N, p.K);
-    rc = make_map(&tb, PlaneMat{B.base, (long)p.N, (long)p.K, B.ld, B.plane_stride, B.nplanes}, use_2cta ? BN / 2 : BN,
+    rc = tensor_map_3d(&ptb, PlaneMat{B.base, (long)p.N, (long)p.K, B.ld, B.plane_stride, B.nplanes}, use_2cta ? BN / 2 : BN,
                   p.nsplit, bk);
   } else {
     OOB_CHECK(B.rows >= p.K && B.cols >= p.N, "B (N-major) is %ld x %ld, need %d x %d", B.rows, B.cols, p.K, p.N);
-    rc = make_map(&tb, PlaneMat{B.base, (long)p.K, (long)p.N, B.ld, B.plane_stride, B.nplanes}, bk, p.nsplit, bk);
+    rc = tensor_map_3d(&ptb, PlaneMat{B.base, (long)p.K, (long)p.N, B.ld, B.plane_stride, B.nplanes}, bk, p.nsplit, bk);
   }
   if (rc) return rc;
+  const CUtensorMap& ta = *pta;
+  const CUtensorMap& tb = *ptb;
 #define OOB_DISPATCH_MAJORS(FN, ...)                                                       \
   do {                                                                                      \
     if (!a_mn && !b_mn) return FN<BN, false, false, __VA_ARGS__>(ta, tb, p, stream);        \

@@ -313,6 +313,11 @@ struct PlaneMat {
 int gemm_launch(const PlaneMat& A, int a_mn_major, const PlaneMat& B, int b_mn_major, const GemmParams& p,
                 cudaStream_t stream);
 
+// Cached TMA descriptor over a split matrix [nplanes][rows][ld]: box = {bk columns, box_rows, box_planes}, bk = 64 ->
+// SWIZZLE_128B, 32 -> SWIZZLE_64B.  The returned pointer is valid until the next call on this host thread.
+int tensor_map_3d(const CUtensorMap** out, const PlaneMat& a, int box_rows, int box_planes, int bk);
+long tensor_map_encodes();   // cuTensorMapEncodeTiled calls so far (cache misses)
+
 // CUDA-event instrumentation of GEMM launches (bench.py roofline): see oob_gemm_timing_begin/end
 int gemm_timing_begin();
 int gemm_timing_end(double* total_ms, double* total_flops, double* executed_flops, long* launches);

@@ -18,6 +18,8 @@ from __future__ import annotations
 
 import copy
 import os
+import queue
+import socket
 import threading
 import time
 import weakref
@@ -71,8 +73,28 @@ class OobleckArguments:
     model: ModelArguments = field(default_factory=ModelArguments)
 
 
+@dataclass
+class DistributionInfo:
+    """What the agent sends once on the worker pipe (oobleck/elastic/message_util.py:11-13).  The engine only reads
+    ``agent_ips`` and ``world_size``: the control plane's own class is accepted as is (duck typing)."""
+    agent_ips: list[str]
+    world_size: int
+
+
+class PipelineAborted(RuntimeError):
+    """A train step was cut short because a peer was lost (transport abort or communicator abort)."""
+
+
 def _rank() -> int:
     return dist.get_rank() if dist.is_initialized() else 0
+
+
+def _my_ip() -> str:
+    """engine.py:555 (``socket.gethostbyname(socket.gethostname())``; the reference's tests patch it)."""
+    try:
+        return socket.gethostbyname(socket.gethostname())
+    except OSError:
+        return "127.0.0.1"
 
 
 # Communicators survive pipeline rebuilds: one per rank set for the life of the process.  (torch names group-local
@@ -145,8 +167,11 @@ class ReconfigurationEngine:
         t0 = engine._pipeline_templates[0]
         self._min_num_ranks = t0._num_nodes * t0._num_gpus_per_node          # engine.py:46-49
         self.last_reconfiguration_seconds: float | None = None
+        self.last_notification_time: float | None = None
+        # lost-rank lists received by the listener thread, applied by the training thread at its next safe point
+        self._pending: "queue.Queue[tuple[list[int], float]]" = queue.Queue()
         self._reconfiguration_listener = None
-        if start_listener and getattr(engine, "_agent_pipe", None) is not None:
+        if start_listener and getattr(engine, "_agent_pipe", None) is not None and engine._listen:
             self._reconfiguration_listener = threading.Thread(target=self._reconfiguration_listener_fn, daemon=True)
             self._reconfiguration_listener.start()
 
@@ -155,17 +180,51 @@ class ReconfigurationEngine:
         return self._engine()
 
     def _reconfiguration_listener_fn(self):
-        while self._on_receive_reconfiguration_notification():
-            pass
+        """Daemon thread (engine.py:50-61).  The reference rebuilds the pipelines from this thread while the training
+        thread is inside a step, with no lock; here the listener only does what cannot wait -- the pipe round trip and
+        releasing every stream / communicator that is stuck on the lost ranks -- and hands the re-planning to the
+        training thread (``poll``), which applies it between two steps."""
+        while True:
+            try:
+                engine = self.engine
+                if engine is None:
+                    return
+                lost_node: str = engine._agent_pipe.recv()
+            except (EOFError, ValueError, OSError):
+                return                                          # connection closed (engine.py:78-80)
+            t0 = time.perf_counter()
+            try:
+                lost_ranks = self.remove_lost_node_from_dist_info(lost_node)
+                engine.on_ranks_lost(lost_ranks)                # first: un-wedge the GPU
+                engine.initialize_distributed()                 # port round trip with the agent (engine.py:572-578)
+            except (EOFError, ValueError, OSError):
+                return
+            self._pending.put((lost_ranks, t0))
+
+    def poll(self) -> bool:
+        """Training thread: apply every reconfiguration the listener has queued.  True if the pipelines changed."""
+        changed = False
+        while True:
+            try:
+                lost_ranks, t0 = self._pending.get_nowait()
+            except queue.Empty:
+                return changed
+            self.last_notification_time = t0
+            self.on_reconfigure(lost_ranks)
+            self.last_reconfiguration_seconds = time.perf_counter() - t0
+            changed = True
 
     def _on_receive_reconfiguration_notification(self) -> bool:
-        """engine.py:63-80.  Returns False when the agent pipe is closed."""
+        """engine.py:63-80, synchronous form (the reference's tests call it directly,
+        tests/execution/test_engine.py:967-1019).  Returns False when the agent pipe is closed."""
         try:
             engine = self.engine
             lost_node: str = engine._agent_pipe.recv()
             t0 = time.perf_counter()
             lost_ranks = self.remove_lost_node_from_dist_info(lost_node)
             engine.on_ranks_lost(lost_ranks)
+            engine.initialize_distributed()
+            self.last_notification_time = t0
             self.on_reconfigure(lost_ranks)
             self.last_reconfiguration_seconds = time.perf_counter() - t0
             return True

@@ -152,13 +152,20 @@ class Layer:
         self.loss_scale = float(16 * 2 ** int(math.floor(math.log2(tokens))))   # dlogits * loss_scale is O(16)
         # placed here because the plane layout depends on it: all-fp16 mode keeps pair-only buffers
         self.bwd_fp16 = 1 if (self.fwd_fp16 and (DEFAULT_BWD_FP16 if bwd_fp16 is None else bwd_fp16)) else 0
-        # plane-set code handed to the producers (include/oobleck_b200.h) and the number of planes allocated
-        if layer.kind == "embedding" or not self.fwd_fp16:
+        # plane-set code handed to the producers (include/oobleck_b200.h) and the number of planes allocated.  The
+        # embedding layer feeds no GEMM (wte / wpe are gathered in fp32): it carries no planes at all.
+        if layer.kind == "embed":
+            self.nplanes = 0
+        elif not self.fwd_fp16:
             self.nplanes = 3
         else:
             self.nplanes = 22 if self.bwd_fp16 else 5
         self.nplane_count = 2 if self.nplanes == 22 else self.nplanes
-        self.planes = torch.empty(self.nplane_count, self.plane_stride, dtype=torch.bfloat16, device=self.device)
+        self.planes = (torch.empty(self.nplane_count, self.plane_stride, dtype=torch.bfloat16, device=self.device)
+                       if self.nplanes else None)
+        # AdamW step count of THIS layer's moments: travels with exp_avg / exp_avg_sq through reconfigurations so the
+        # bias correction matches the moments (optimizer.py)
+        self.opt_step = 0
         self.refresh_planes()
 
         E, V = layer.n_embd, layer.vocab_size
@@ -175,11 +182,16 @@ class Layer:
     def flat_grad(self) -> torch.Tensor:
         return self._param_handle.flat_param.grad
 
+    def planes_ptr(self) -> int:
+        return self.planes.data_ptr() if self.planes is not None and self.planes.numel() else 0
+
     def _params_struct(self) -> OobLayerParams:
-        return OobLayerParams(self.flat_param.data_ptr(), self.planes.data_ptr(), self.plane_stride,
+        return OobLayerParams(self.flat_param.data_ptr(), self.planes_ptr(), self.plane_stride,
                               self.flat_grad.data_ptr())
 
     def refresh_planes(self) -> None:
+        if not self.nplanes:
+            return
         L.call("oob_split_planes", C.c_void_p(self.flat_param.data_ptr()), C.c_void_p(self.planes.data_ptr()),
                self.numel, self.plane_stride, self.nplanes, _stream())
 
@@ -188,6 +200,29 @@ class Layer:
         assert flat.numel() == self.numel
         self.flat_param.copy_(flat.to(self.device, torch.float32))
         self.refresh_planes()
+
+    def state_tensors(self) -> list[torch.Tensor]:
+        """What has to move when this layer changes owner: parameters and both Adam moments (the reference moves
+        ``flat_param`` only, engine.py:284-306, and silently restarts the moments)."""
+        return [self.flat_param, self.exp_avg, self.exp_avg_sq]
+
+    def adopt_state_(self, other: "Layer") -> None:
+        """Take over parameters, gradients-in-progress, moments and step count of ``other`` (same layer id, same
+        device): used when a reused layer needs more pipe buffers than it was built with."""
+        assert other.numel == self.numel and other.layer_id == self.layer_id
+        self.flat_param.copy_(other.flat_param)
+        self.flat_grad.copy_(other.flat_grad)
+        self.exp_avg.copy_(other.exp_avg)
+        self.exp_avg_sq.copy_(other.exp_avg_sq)
+        self.opt_step = other.opt_step
+        self.refresh_planes()
+
+    def grow_pipe_buffers(self, num_pipe_buffers: int) -> None:
+        """Re-allocate the per-slot activation contexts for a deeper schedule; parameters and optimizer state are
+        untouched (contexts only live inside a train step)."""
+        if num_pipe_buffers > self.num_pipe_buffers:
+            self.num_pipe_buffers = num_pipe_buffers
+            self._alloc_contexts()
 
     def zero_grad(self) -> None:
         self.flat_grad.zero_()
@@ -201,8 +236,11 @@ class Layer:
         self.ctx_tensors, self.out = [], []
 
     @classmethod
-    def create_layer_from_layer(cls, existing_layer: "Layer", process_group) -> "Layer":  # layer.py:41-64
+    def create_layer_from_layer(cls, existing_layer: "Layer", process_group,
+                                num_pipe_buffers: int | None = None) -> "Layer":  # layer.py:41-64
         existing_layer._param_handle.process_group = process_group
+        if num_pipe_buffers is not None:
+            existing_layer.grow_pipe_buffers(num_pipe_buffers)   # never shrinks; weights / moments stay in place
         return existing_layer
 
     # -- activations -----------------------------------------------------------------------------------------------

@@ -29,11 +29,14 @@ class FusedAdamW:
         g = self.param_groups[0]
         stream = C.c_void_p(torch.cuda.current_stream().cuda_stream)
         for l in self.layers:
+            # the bias correction follows the layer's own moments (torch keeps ``step`` per parameter too): a layer
+            # that arrives through a reconfiguration brings its count with it, a fresh optimizer does not reset it
+            l.opt_step = getattr(l, "opt_step", 0) + 1
             L.call("oob_adamw_step", C.c_void_p(l.flat_param.data_ptr()), C.c_void_p(l.flat_grad.data_ptr()),
                    C.c_void_p(l.exp_avg.data_ptr()), C.c_void_p(l.exp_avg_sq.data_ptr()),
-                   C.c_void_p(l.planes.data_ptr()), l.plane_stride, l.nplanes, l.numel, float(g["lr"]), g["betas"][0],
-                   g["betas"][1], g["eps"], g["weight_decay"], self._step, stream)
-            self.state[l.flat_param] = {"step": self._step, "exp_avg": l.exp_avg, "exp_avg_sq": l.exp_avg_sq}
+                   C.c_void_p(l.planes_ptr()), l.plane_stride, l.nplanes, l.numel, float(g["lr"]), g["betas"][0],
+                   g["betas"][1], g["eps"], g["weight_decay"], l.opt_step, stream)
+            self.state[l.flat_param] = {"step": l.opt_step, "exp_avg": l.exp_avg, "exp_avg_sq": l.exp_avg_sq}
 
     def zero_grad(self) -> None:
         for l in self.layers:

@@ -432,8 +432,13 @@ class OobleckPipeline:
             shard_id = idx
             if existing_pipeline is not None and existing_pipeline.execution is not None:   # :509-520
                 existing_layer = next((l for l in existing_pipeline.execution._layers if l.layer_id == layer_id), None)
-                if existing_layer is not None and getattr(existing_layer, "num_pipe_buffers", 0) >= num_pipe_buffers:
-                    layers.append(layer_cls.create_layer_from_layer(existing_layer, pg))
+                if existing_layer is not None:
+                    # a reused layer keeps its weights, moments and step count; if the new schedule is deeper its
+                    # activation contexts are grown in place (a rebuilt Layer would restart from init_flat())
+                    try:
+                        layers.append(layer_cls.create_layer_from_layer(existing_layer, pg, num_pipe_buffers))
+                    except TypeError:   # layer classes with the reference's two-argument signature
+                        layers.append(layer_cls.create_layer_from_layer(existing_layer, pg))
                     continue
             layers.append(layer_cls(layer_id, model.layers[layer_id], pg, None, None, microbatch_size=mb,
                                     num_pipe_buffers=num_pipe_buffers, workspace=workspace, nsplit=self._nsplit))

@@ -197,7 +197,8 @@ def ref_attention(qkv, B, T, H, D):
 
 
 @pytest.mark.parametrize("h2", [0, 1])
-@pytest.mark.parametrize("B,T,H", [(2, 128, 3), (1, 100, 2), (2, 1024, 4)])
+@pytest.mark.parametrize("B,T,H", [(2, 128, 3), (1, 100, 2), (3, 64, 2), (1, 192, 1), (2, 333, 2), (2, 1024, 4),
+                                   (2, 1024, 25)])
 def test_attention_fwd_bwd(B, T, H, h2):
     """h2 = 1: q|k|v and dO as fp16 pairs (3 products per MAC), dO additionally loss-scaled like in the stage."""
     D, E = 64, H * 64
