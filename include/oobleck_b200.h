@@ -209,7 +209,8 @@ int oob_p2p_alloc(long ring_bytes, void** mailbox, void* ipc_handle_out /* 64 by
 int oob_p2p_open(const void* ipc_handle /* 64 bytes */, void** peer_mailbox);
 int oob_p2p_close(void* peer_mailbox);
 int oob_p2p_free(void* mailbox);
-int oob_p2p_abort(void* mailbox, void* stream);
+int oob_p2p_abort(void* mailbox, void* stream /* ignored: a host store into pinned memory */);
+int oob_p2p_status(void* mailbox, int* status /* 0 ok, 1 aborted, 2 watchdog */);
 int oob_p2p_send(const void* src, long bytes, void* my_mailbox, void* peer_mailbox, int nslots, long slot_bytes,
                  long offset_in_slot, unsigned seq, int first, int last, void* stream);
 int oob_p2p_recv(void* dst, long bytes, void* my_mailbox, void* peer_mailbox, int nslots, long slot_bytes,

@@ -17,6 +17,8 @@
 #include "../../include/oobleck_b200.h"
 #include <cstdlib>
 #include <cstring>
+#include <mutex>
+#include <unordered_map>
 
 #include "kernels.h"
 
@@ -44,7 +46,7 @@ __device__ __forceinline__ void st_release_sys(unsigned* p, unsigned v) {
 }
 
 // Watchdog: a spin that outlives this many ns (peer died before anyone called oob_p2p_abort, or a rendezvous bug)
-// sets the local abort word to 2 and gives up, so a lost neighbour can never wedge the GPU.  OOB_P2P_TIMEOUT_S.
+// gives up with status 2, so a lost neighbour can never wedge the GPU.  OOB_P2P_TIMEOUT_S.
 __device__ unsigned long long g_spin_timeout_ns = 120ull * 1000000000ull;
 
 __device__ __forceinline__ unsigned long long globaltimer_ns() {
@@ -53,23 +55,38 @@ __device__ __forceinline__ unsigned long long globaltimer_ns() {
   return t;
 }
 
-// wait until *word >= target (wrap-safe), or the local abort word is set
-__device__ __forceinline__ void spin_until(const unsigned* word, unsigned target, const unsigned* abort_word) {
-  if (threadIdx.x == 0) {
-    unsigned ns = 32;
-    const unsigned long long t0 = globaltimer_ns();
-    while ((int)(ld_acquire_sys(word) - target) < 0) {
-      if (ld_acquire_sys(abort_word)) break;
-      __nanosleep(ns);
-      if (ns < 1024) ns <<= 1;
-      else if (globaltimer_ns() - t0 > g_spin_timeout_ns) {
-        atomicExch(const_cast<unsigned*>(abort_word), 2u);
-        break;
-      }
+// Host-visible control block of a mailbox (pinned, mapped): `abort` is written by the HOST with a plain store --
+// no stream, no CUDA call, so the listener thread can release a GPU whose copy streams are all blocked behind
+// spinning kernels -- and polled by the waiting kernel; `status` is written by the device when a wait gave up
+// (1 = aborted, 2 = watchdog) and read by the host after the step (oob_p2p_status).
+struct HostCtrl {
+  volatile unsigned abort;
+  volatile unsigned status;
+};
+
+// One warp waits until *word >= target (wrap-safe).  On abort / timeout it latches the DEVICE abort word of the
+// mailbox: every later copy kernel of this link then skips its copy and its publish, so a lost or late peer can never
+// turn into silently corrupted activations or a corrupted flag / ack sequence.
+__global__ void p2p_wait_kernel(const unsigned* word, unsigned target, unsigned* abort_dev, HostCtrl* ctrl) {
+  if (threadIdx.x != 0) return;
+  unsigned ns = 32;
+  const unsigned long long t0 = globaltimer_ns();
+  while ((int)(ld_acquire_sys(word) - target) < 0) {
+    unsigned why = 0;
+    if (ld_acquire_sys(abort_dev)) why = 1;
+    else if (ns >= 1024) {   // slow path only: the host word costs a PCIe round trip per poll
+      if (ctrl->abort) why = 1;
+      else if (globaltimer_ns() - t0 > g_spin_timeout_ns) why = 2;
     }
+    if (why) {
+      atomicExch(abort_dev, why);
+      ctrl->status = why;
+      __threadfence_system();
+      return;
+    }
+    __nanosleep(ns);
+    if (ns < 1024) ns <<= 1;
   }
-  __syncthreads();
-  __threadfence_system();
 }
 
 __device__ __forceinline__ void copy_bytes(const char* src, char* dst, long bytes) {
@@ -101,21 +118,25 @@ __device__ __forceinline__ void publish_when_all_done(unsigned* counter, unsigne
   }
 }
 
+// The copy itself: ordered behind p2p_wait_kernel by the stream (one resident spinning WARP per pending message instead
+// of round 1's up-to-64 spinning CTAs next to the persistent GEMM).  An aborted link copies and publishes nothing.
 __global__ void __launch_bounds__(256)
-p2p_send_kernel(const char* __restrict__ src, char* __restrict__ peer_dst, long bytes, const unsigned* local_ack,
-                unsigned ack_needed, int wait_ack, unsigned* peer_flag, unsigned seq, unsigned* counter,
-                const unsigned* abort_word) {
-  if (wait_ack) spin_until(local_ack, ack_needed, abort_word);
-  copy_bytes(src, peer_dst, bytes);
-  publish_when_all_done(counter, peer_flag, seq);
+p2p_copy_kernel(const char* __restrict__ src, char* __restrict__ dst, long bytes, unsigned* publish_word, unsigned seq,
+                unsigned* counter, const unsigned* abort_dev) {
+  if (ld_acquire_sys(abort_dev)) return;
+  copy_bytes(src, dst, bytes);
+  publish_when_all_done(counter, publish_word, seq);
 }
 
-__global__ void __launch_bounds__(256)
-p2p_recv_kernel(const char* __restrict__ local_src, char* __restrict__ dst, long bytes, const unsigned* local_flag,
-                unsigned seq, int wait_flag, unsigned* peer_ack, unsigned* counter, const unsigned* abort_word) {
-  if (wait_flag) spin_until(local_flag, seq, abort_word);
-  copy_bytes(local_src, dst, bytes);
-  publish_when_all_done(counter, peer_ack, seq);
+struct CtrlEntry { HostCtrl* host; HostCtrl* dev; };
+std::mutex g_ctrl_mu;
+std::unordered_map<const void*, CtrlEntry> g_ctrl;
+bool ctrl_of(const void* mailbox, CtrlEntry* out) {
+  std::lock_guard<std::mutex> lk(g_ctrl_mu);
+  auto it = g_ctrl.find(mailbox);
+  if (it == g_ctrl.end()) return false;
+  *out = it->second;
+  return true;
 }
 
 }  // namespace
@@ -134,6 +155,15 @@ int oob_p2p_alloc(long ring_bytes, void** mailbox, void* ipc_handle_out) {
   OOB_CUDA_OK(cudaIpcGetMemHandle(&h, p));
   memcpy(ipc_handle_out, &h, sizeof(h));
   static_assert(sizeof(cudaIpcMemHandle_t) == 64, "ipc handle size");
+  CtrlEntry ce{};
+  OOB_CUDA_OK(cudaHostAlloc(reinterpret_cast<void**>(&ce.host), 64, cudaHostAllocMapped | cudaHostAllocPortable));
+  ce.host->abort = 0;
+  ce.host->status = 0;
+  OOB_CUDA_OK(cudaHostGetDevicePointer(reinterpret_cast<void**>(&ce.dev), ce.host, 0));
+  {
+    std::lock_guard<std::mutex> lk(g_ctrl_mu);
+    g_ctrl[p] = ce;
+  }
   *mailbox = p;
   return 0;
 }
@@ -151,6 +181,14 @@ int oob_p2p_close(void* peer_mailbox) {
 }
 
 int oob_p2p_free(void* mailbox) {
+  CtrlEntry ce{};
+  if (ctrl_of(mailbox, &ce)) {
+    {
+      std::lock_guard<std::mutex> lk(g_ctrl_mu);
+      g_ctrl.erase(mailbox);
+    }
+    cudaFreeHost(ce.host);
+  }
   OOB_CUDA_OK(cudaFree(mailbox));
   return 0;
 }
@@ -166,11 +204,23 @@ static int apply_timeout_env() {
   return 0;
 }
 
-/* make every spinning kernel on this rank's mailbox give up (peer lost); callable from the listener thread */
+/* Make every kernel waiting on this rank's mailbox give up (peer lost).  A plain store into pinned host memory: no
+ * CUDA call, no stream -- callable from the listener thread while every stream of the process is blocked behind a
+ * spinning kernel.  `stream` is ignored (kept for ABI compatibility with round 1). */
 int oob_p2p_abort(void* mailbox, void* stream) {
-  static const unsigned one = 1;
-  MailboxHeader* h = reinterpret_cast<MailboxHeader*>(mailbox);
-  OOB_CUDA_OK(cudaMemcpyAsync(&h->abort, &one, sizeof(one), cudaMemcpyHostToDevice, reinterpret_cast<cudaStream_t>(stream)));
+  (void)stream;
+  CtrlEntry ce{};
+  OOB_CHECK(ctrl_of(mailbox, &ce), "oob_p2p_abort: unknown mailbox");
+  ce.host->abort = 1;
+  return 0;
+}
+
+/* 0 = healthy, 1 = a wait on this mailbox was aborted, 2 = a wait hit the watchdog.  Host-side read, no sync. */
+int oob_p2p_status(void* mailbox, int* status) {
+  CtrlEntry ce{};
+  OOB_CHECK(ctrl_of(mailbox, &ce) && status, "oob_p2p_status: unknown mailbox");
+  *status = (int)ce.host->status;
+  if (*status == 0 && ce.host->abort) *status = 1;
   return 0;
 }
 
@@ -189,9 +239,16 @@ int oob_p2p_send(const void* src, long bytes, void* my_mailbox, void* peer_mailb
   blocks = blocks < 1 ? 1 : (blocks > 64 ? 64 : blocks);
   const int wait_ack = first && seq > (unsigned)nslots;
   if (int rc = apply_timeout_env()) return rc;
-  p2p_send_kernel<<<blocks, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
-      reinterpret_cast<const char*>(src), dst, bytes, &mine->acks[slot], seq - (unsigned)nslots, wait_ack,
-      last ? &peer->flags[slot] : nullptr, seq, &mine->counters[0], &mine->abort);
+  CtrlEntry ce{};
+  OOB_CHECK(ctrl_of(my_mailbox, &ce), "oob_p2p_send: unknown mailbox");
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  if (wait_ack) {   // the peer must have drained this slot (message seq - nslots)
+    p2p_wait_kernel<<<1, 32, 0, st>>>(&mine->acks[slot], seq - (unsigned)nslots, &mine->abort, ce.dev);
+    OOB_CUDA_OK(cudaGetLastError());
+    count_launch();
+  }
+  p2p_copy_kernel<<<blocks, 256, 0, st>>>(reinterpret_cast<const char*>(src), dst, bytes,
+                                          last ? &peer->flags[slot] : nullptr, seq, &mine->counters[0], &mine->abort);
   OOB_CUDA_OK(cudaGetLastError());
   count_launch();
   return 0;
@@ -209,9 +266,16 @@ int oob_p2p_recv(void* dst, long bytes, void* my_mailbox, void* peer_mailbox, in
   int blocks = (int)((bytes / 16 + 256 * 4 - 1) / (256 * 4));
   blocks = blocks < 1 ? 1 : (blocks > 64 ? 64 : blocks);
   if (int rc = apply_timeout_env()) return rc;
-  p2p_recv_kernel<<<blocks, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
-      src, reinterpret_cast<char*>(dst), bytes, &mine->flags[slot], seq, first, last ? &peer->acks[slot] : nullptr,
-      &mine->counters[1], &mine->abort);
+  CtrlEntry ce{};
+  OOB_CHECK(ctrl_of(my_mailbox, &ce), "oob_p2p_recv: unknown mailbox");
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  if (first) {      // the peer's flag for this message
+    p2p_wait_kernel<<<1, 32, 0, st>>>(&mine->flags[slot], seq, &mine->abort, ce.dev);
+    OOB_CUDA_OK(cudaGetLastError());
+    count_launch();
+  }
+  p2p_copy_kernel<<<blocks, 256, 0, st>>>(src, reinterpret_cast<char*>(dst), bytes, last ? &peer->acks[slot] : nullptr,
+                                          seq, &mine->counters[1], &mine->abort);
   OOB_CUDA_OK(cudaGetLastError());
   count_launch();
   return 0;

@@ -17,6 +17,7 @@ The policy code (which ranks go where) is bit-exact with the reference (golden v
 from __future__ import annotations
 
 import copy
+import datetime
 import os
 import queue
 import socket
@@ -33,7 +34,7 @@ import torch.distributed as dist
 from ..module.model import OobleckModel
 from ..planning.pipeline_template import PipelineTemplate, balanced_template
 from .dataloader import LoaderType, OobleckDataLoader, SyntheticTokenDataset
-from .pipeline import OobleckPipeline, RankGroup
+from .pipeline import OobleckPipeline, PipelineAborted, RankGroup, bump_generation, run_interruptible
 from .training_args import TrainingArguments
 
 
@@ -81,12 +82,17 @@ class DistributionInfo:
     world_size: int
 
 
-class PipelineAborted(RuntimeError):
-    """A train step was cut short because a peer was lost (transport abort or communicator abort)."""
-
-
 def _rank() -> int:
     return dist.get_rank() if dist.is_initialized() else 0
+
+
+_DEBUG = os.environ.get("OOB_ELASTIC_DEBUG", "0") == "1"
+
+
+def _dbg(msg: str) -> None:
+    if _DEBUG:
+        import sys
+        print(f"[elastic rank {_rank()} {time.perf_counter():.3f}] {msg}", file=sys.stderr, flush=True)
 
 
 def _my_ip() -> str:
@@ -100,6 +106,33 @@ def _my_ip() -> str:
 # Communicators survive pipeline rebuilds: one per rank set for the life of the process.  (torch names group-local
 # groups by a hash of their ranks, so creating the same set twice would also collide in the rendezvous store.)
 _COMMUNICATORS: dict[tuple[int, ...], Any] = {}
+
+
+_GROUP_CREATIONS: dict[tuple[int, ...], int] = {}
+
+
+def _new_member_group(ranks, timeout=None):
+    """``dist.new_group(ranks, use_local_synchronization=True)`` -- only the member ranks take part, which is what lets
+    survivors build communicators after a loss -- with a rendezvous name every member derives identically.  torch
+    hashes the rank list together with ``len(_world.pg_names)``, the number of groups THIS process has created so far
+    (distributed_c10d._hash_ranks_to_str); after a reconfiguration that count differs between members (they belonged to
+    different groups before) and their rendezvous keys never meet.  The name used here is the rank set plus how many
+    times this very set has been created -- every member has taken part in each of those creations."""
+    import hashlib
+
+    import torch.distributed.distributed_c10d as c10d
+    key = tuple(sorted(ranks))
+    n = _GROUP_CREATIONS[key] = _GROUP_CREATIONS.get(key, 0) + 1
+    name = hashlib.sha1(("oobleck_b200_" + "_".join(map(str, key)) + f"#{n}").encode(), usedforsecurity=False).hexdigest()
+    kw = {} if timeout is None else {"timeout": timeout}
+    orig = getattr(c10d, "_hash_ranks_to_str", None)
+    if orig is None:
+        return dist.new_group(list(key), use_local_synchronization=True, **kw)
+    c10d._hash_ranks_to_str = lambda _ranks: name
+    try:
+        return dist.new_group(list(key), use_local_synchronization=True, **kw)
+    finally:
+        c10d._hash_ranks_to_str = orig
 
 
 # ---- data parallel -------------------------------------------------------------------------------------------------
@@ -125,7 +158,7 @@ class DataParallelEngine:
                 return None
             key = tuple(sorted(ranks))
             if key not in _COMMUNICATORS:
-                _COMMUNICATORS[key] = dist.new_group(list(key), use_local_synchronization=True)
+                _COMMUNICATORS[key] = _new_member_group(key, engine._comm_timeout)
             return _COMMUNICATORS[key]
 
         make = new_group or _make
@@ -146,6 +179,31 @@ class DataParallelEngine:
     @property
     def engine(self):
         return self._engine()
+
+    def vote(self, ok: bool, device, lost: set[int], aborted) -> bool:
+        """Elastic runs only: the commit point of a step.  Before any gradient is exchanged every rank tells its
+        cross-replica partners whether its own pipeline finished this step's micro-batches and no loss notification is
+        pending (MIN all-reduce of one flag per distinct communicator; every rank votes exactly once per step, so
+        nobody waits for a partner that will not come).  One 0 anywhere and every replica drops the step -- instead
+        of waiting in a gradient all-reduce for a partner whose pipeline was cut short, or reducing with its half-built
+        gradients.  Communicators that contain a rank this process already knows is lost are skipped; a partner that is
+        dead without our knowing makes the vote itself fail (gloo: peer reset; NCCL: the listener aborts that
+        communicator), which also counts as 0."""
+        groups = []
+        for per_layer in self._dp_process_groups.values():
+            for pg in per_layer.values():
+                if pg.rank_index() >= 0 and pg.size() > 1 and pg.group is not None and pg.group not in groups \
+                        and not (lost & set(pg.ranks)):
+                    groups.append(pg.group)
+        if not groups:
+            return ok
+        flag = torch.tensor([1 if ok else 0], dtype=torch.int32, device=device)
+        for g in groups:
+            if flag.device.type == "cpu":
+                run_interruptible(lambda g=g: dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=g), aborted)
+            else:
+                dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=g)
+        return bool(flag.item())      # device -> host read: the only synchronisation an elastic step adds
 
     def do_allreduce(self):
         """engine.py:404-412: every local layer reduces over the groups that contain this rank."""
@@ -193,12 +251,14 @@ class ReconfigurationEngine:
             except (EOFError, ValueError, OSError):
                 return                                          # connection closed (engine.py:78-80)
             t0 = time.perf_counter()
+            _dbg(f"listener: lost node {lost_node}")
             try:
                 lost_ranks = self.remove_lost_node_from_dist_info(lost_node)
                 engine.on_ranks_lost(lost_ranks)                # first: un-wedge the GPU
                 engine.initialize_distributed()                 # port round trip with the agent (engine.py:572-578)
             except (EOFError, ValueError, OSError):
                 return
+            _dbg(f"listener: queued reconfiguration for lost ranks {lost_ranks}")
             self._pending.put((lost_ranks, t0))
 
     def poll(self) -> bool:
@@ -210,8 +270,11 @@ class ReconfigurationEngine:
             except queue.Empty:
                 return changed
             self.last_notification_time = t0
+            _dbg(f"poll: reconfiguring for lost ranks {lost_ranks}")
             self.on_reconfigure(lost_ranks)
             self.last_reconfiguration_seconds = time.perf_counter() - t0
+            _dbg(f"poll: done in {self.last_reconfiguration_seconds:.3f}s")
+            self.engine._notified = not self._pending.empty()
             changed = True
 
     def _on_receive_reconfiguration_notification(self) -> bool:
@@ -227,6 +290,7 @@ class ReconfigurationEngine:
             self.last_notification_time = t0
             self.on_reconfigure(lost_ranks)
             self.last_reconfiguration_seconds = time.perf_counter() - t0
+            engine._notified = False
             return True
         except (EOFError, ValueError, OSError):
             return False
@@ -316,6 +380,7 @@ class ReconfigurationEngine:
     # -- mechanism ---------------------------------------------------------------------------------------------------
     def _reinstantiate(self, num_instances_set, new_ranks_list) -> OobleckPipeline:
         engine = self.engine
+        bump_generation()     # wire traffic of the new pipelines can never match a receive abandoned by the old ones
         global_num_microbatch = engine._args.job.global_microbatch_size // engine._args.job.microbatch_size
         templates = [t for t, n in num_instances_set.items() for _ in range(n)]
         num_microbatches = engine.distribute_microbatches(templates, global_num_microbatch)
@@ -339,9 +404,11 @@ class ReconfigurationEngine:
         return mine
 
     def _copy_model_states(self, old_rank_grids, new_rank_grids, new_pipeline: OobleckPipeline):
-        """engine.py:238-309: per layer, some old owner whose rank list survives unchanged sends the flat parameters
-        to the new owners.  Same sender choice and the same RuntimeError; the transfer itself is a broadcast inside the
-        (cached) DP communicator of that layer."""
+        """engine.py:238-309: per layer, some old owner whose rank list survives unchanged sends the layer to the new
+        owners.  Same sender choice and the same RuntimeError; the transfer itself is a broadcast inside the (cached)
+        DP communicator of that layer.  Beyond the reference (which moves ``flat_param`` only and lets the moved
+        layer's Adam moments restart from zero): ``exp_avg``, ``exp_avg_sq`` and the layer's AdamW step count travel
+        too, so every replica of a layer holds the same optimizer state after the move."""
         engine = self.engine
         works = []
         for layer_index in range(len(old_rank_grids[0])):
@@ -353,23 +420,35 @@ class ReconfigurationEngine:
             if not alive:
                 raise RuntimeError(f"No alive ranks for the layer {layer_index}. Terminating.")
             ranks_to_send = alive[0]
-            my_rank = _rank()
+            my_rank = engine._rank if dist.is_initialized() else _rank()
             for ranks_recv in new_ranks:
                 if my_rank not in ranks_recv:
                     continue
                 fsdp_index = ranks_recv.index(my_rank)
                 dp_group = engine._dp_engine._dp_process_groups[layer_index][fsdp_index]
                 new_layer = next(l for l in new_pipeline.execution._layers if l.layer_id == layer_index)
-                if my_rank == ranks_to_send[fsdp_index]:
+                src = ranks_to_send[fsdp_index]
+                if my_rank == src:
                     old_layer = next(l for l in engine._pipeline.execution._layers if l.layer_id == layer_index)
                     if new_layer is not old_layer:
-                        new_layer.load_flat_(old_layer.flat_param)
+                        if hasattr(new_layer, "adopt_state_"):
+                            new_layer.adopt_state_(old_layer)
+                        else:
+                            new_layer.load_flat_(old_layer.flat_param)
                 if dp_group.group is not None:
-                    works.append((dist.broadcast(new_layer.flat_param, src=ranks_to_send[fsdp_index],
-                                                 group=dp_group.group, async_op=True), new_layer))
-        for work, layer in works:
+                    tensors = (new_layer.state_tensors() if hasattr(new_layer, "state_tensors")
+                               else [new_layer.flat_param])
+                    step = torch.tensor([int(getattr(new_layer, "opt_step", 0))], dtype=torch.int64,
+                                        device=new_layer.flat_param.device)
+                    for t in tensors + [step]:
+                        works.append((dist.broadcast(t, src=src, group=dp_group.group, async_op=True), new_layer,
+                                      step if t is step else None))
+        for work, layer, step in works:
             work.wait()
-            layer.refresh_planes()
+            if step is not None:
+                if hasattr(layer, "opt_step"):
+                    layer.opt_step = int(step.item())
+                layer.refresh_planes()
         # no world barrier (engine.py:308): a lost rank can never join it; the broadcasts above are the only ordering
         if torch.cuda.is_available():
             torch.cuda.synchronize()
@@ -397,8 +476,21 @@ class OobleckEngine:
 
     def __init__(self, local_rank: int, num_nodes: int, num_gpus_per_node: int, pipe, args: OobleckArguments, *,
                  dataset=None, templates: list[PipelineTemplate] | None = None, nsplit: int = 3, layer_cls=None,
-                 transport_cls=None, device_resident: bool = False):
+                 transport_cls=None, device_resident: bool = False, listen: bool = True, backend: str | None = None,
+                 comm_timeout_s: float | None = None):
         self._agent_pipe = pipe
+        # timeout of every communicator this engine creates (None: torch's default); a replica that waits in an
+        # all-reduce for a partner that dropped the step is released by ``on_ranks_lost`` (NCCL) or by this timeout
+        self._comm_timeout = None if comm_timeout_s is None else datetime.timedelta(seconds=comm_timeout_s)
+        self._listen = listen            # start the reconfiguration listener thread (engine.py:50-53) when a pipe exists
+        self._backend = backend          # None: nccl on GPUs, gloo on CPU
+        self._dist_info = None
+        self._rank_map: dict[str, list[int]] = {}
+        self._store = None
+        self._store_port: int | None = None
+        self._reconfigured = False
+        self._lost_ranks: set[int] = set()
+        self._notified = False           # a loss notification has arrived and has not been applied yet
         self._args = args
         self._hf_training_args = TrainingArguments(per_device_train_batch_size=args.job.microbatch_size,
                                                    max_steps=args.job.steps)
@@ -412,6 +504,8 @@ class OobleckEngine:
         self._rank = 0
         self._world_size = num_nodes * num_gpus_per_node
         self.step_seconds: list[float] = []
+        self._reconfiguration = None
+        self._step_aborted = False
 
         margs = dict(args.model.model_args)
         n_positions = margs.get("n_positions", 1024)
@@ -427,21 +521,96 @@ class OobleckEngine:
 
     # -- distributed -------------------------------------------------------------------------------------------------
     def initialize_distributed(self, backend: str | None = None):
-        """engine.py:526-596 without the agent round trip when launched by torchrun."""
-        if dist.is_initialized():
-            self._rank, self._world_size = dist.get_rank(), dist.get_world_size()
+        """engine.py:526-596.  With an agent pipe the reference's protocol is followed message for message:
+
+            first call : recv DistributionInfo; rank 0 (first agent IP, local rank 0) creates TCPStore(port=0),
+                         sends the port up the pipe and discards the agent's echo; everyone else receives the port
+            later calls: (after a lost-node notification) the same port round trip, so the agent's pipe stays in step
+
+        What differs is what happens around it: the reference destroys the NCCL world here and re-creates it on every
+        reconfiguration (:532-540, :588-593); this engine keeps the world it built on the first call -- ranks keep
+        their numbers (``_rank_map`` is only popped, like the reference's) and survivors talk over communicators that
+        never contained the lost ranks.  Without a pipe (torchrun launch) rank / world come from the environment."""
+        backend = backend or self._backend or ("nccl" if torch.cuda.is_available() else "gloo")
+        if self._agent_pipe is None:
+            if dist.is_initialized():
+                self._rank, self._world_size = dist.get_rank(), dist.get_world_size()
+                return
+            world = int(os.environ.get("WORLD_SIZE", "1"))
+            if world > 1:
+                dist.init_process_group(backend=backend)
+                self._rank, self._world_size = dist.get_rank(), dist.get_world_size()
+            else:
+                self._rank, self._world_size = 0, 1
             return
-        world = int(os.environ.get("WORLD_SIZE", "1"))
-        if world > 1:
-            backend = backend or ("nccl" if torch.cuda.is_available() else "gloo")
-            dist.init_process_group(backend=backend)
-            self._rank, self._world_size = dist.get_rank(), dist.get_world_size()
+
+        pipe = self._agent_pipe
+        if self._dist_info is None:
+            self._dist_info = pipe.recv()                                              # engine.py:543
+            self._rank_map = {ip: list(range(i * self._num_gpus_per_node, (i + 1) * self._num_gpus_per_node))
+                              for i, ip in enumerate(self._dist_info.agent_ips)}       # :544-552
+        dist_info = self._dist_info
+        my_ip = _my_ip()
+        assert my_ip in dist_info.agent_ips, f"My IP {my_ip} is not in dist info {dist_info.agent_ips}."
+        self._num_nodes = len(dist_info.agent_ips)
+        self._world_size = dist_info.world_size
+        self._rank = self._rank_map[my_ip][self._local_rank]
+        is_master = next(iter(self._rank_map)) == my_ip and self._local_rank == 0      # :563
+
+        if dist.is_initialized():
+            # reconfiguration: the world stays; only the agent's port round trip is honoured (:572-578)
+            if is_master:
+                pipe.send(self._store_port if self._store_port is not None else 0)
+                pipe.recv()
+            else:
+                pipe.recv()
+            return
+        if is_master:
+            store = dist.TCPStore(host_name=my_ip, port=0, world_size=dist_info.world_size, is_master=True,
+                                  wait_for_workers=False)
+            self._store_port = store.port
+            pipe.send(store.port)
+            pipe.recv()            # the agent sends the port back to every worker, rank 0 included: discard it
         else:
-            self._rank, self._world_size = 0, 1
+            port: int = pipe.recv()
+            self._store_port = port
+            store = dist.TCPStore(host_name=dist_info.agent_ips[0], port=port, world_size=dist_info.world_size,
+                                  is_master=False, wait_for_workers=False)
+        self._store = store
+        kw = {} if self._comm_timeout is None else {"timeout": self._comm_timeout}
+        dist.init_process_group(backend=backend, store=store, rank=self._rank, world_size=dist_info.world_size, **kw)
+        assert dist.is_initialized()
 
     def on_ranks_lost(self, lost_ranks: list[int]):
-        """Hook for the transport layer to drop peers (no world process-group teardown; engine.py:532-540 destroys and
-        re-creates the NCCL world here)."""
+        """Release everything on this rank that is (or would get) stuck on a lost rank.  Callable from the listener
+        thread while the training thread is inside a step:
+
+        * inter-stage links: ``transport.abort()`` writes the abort word of every mailbox through host-mapped memory, so
+          send / recv kernels spinning on a dead neighbour return at once (otherwise: the 120 s watchdog of
+          csrc/p2p.cu);
+        * cross-replica communicators that contain a lost rank are aborted (``ncclCommAbort`` under
+          ``ProcessGroup.abort``) and dropped from the cache; survivors get fresh ones in ``DataParallelEngine``.
+
+        The reference has no counterpart: it destroys the whole NCCL world from the listener thread (engine.py:532-540)
+        and notes that this may hang when a collective is in flight."""
+        lost = set(lost_ranks)
+        self._reconfigured = True
+        self._lost_ranks |= lost
+        self._notified = True
+        # my stage may be waiting for a neighbour that is lost -- or alive but already dropping the step: release it
+        pipeline = getattr(self, "_pipeline", None)
+        if pipeline is not None and pipeline.communication is not None:
+            transport = getattr(pipeline.communication, "transport", None)
+            if transport is not None and hasattr(transport, "abort"):
+                transport.abort()
+        # communicators that contain a lost rank can never complete anything again
+        for key in [k for k in _COMMUNICATORS if lost & set(k)]:
+            group = _COMMUNICATORS.pop(key)
+            try:
+                if hasattr(group, "abort") and dist.get_backend(group) == "nccl":
+                    group.abort()          # ncclCommAbort: releases kernels blocked on the dead peer
+            except Exception:  # noqa: BLE001  (gloo cannot abort; an op on a dead peer ends with a peer-reset error)
+                pass
 
     # -- planning stand-ins ------------------------------------------------------------------------------------------
     def distribute_microbatches(self, templates: list[PipelineTemplate], global_num_microbatch: int) -> list[int]:
@@ -494,6 +663,7 @@ class OobleckEngine:
         assert self._pipeline.communication is not None and self._pipeline.execution is not None
         self._dp_engine = DataParallelEngine(self, pipelines)
         self._reconfiguration = ReconfigurationEngine(self, pipelines)
+        self._step_aborted = False
 
     # -- training ----------------------------------------------------------------------------------------------------
     def _train_step(self):
@@ -502,16 +672,94 @@ class OobleckEngine:
         self._dp_engine.do_allreduce()
         self._pipeline.execution.optimizer_step()
 
+    def _guarded_train_step(self) -> bool:
+        """One ``_train_step`` that survives the loss of a peer (elastic runs: an agent pipe exists).
+
+            1. unless a loss notification is already pending: run the pipeline's micro-batches; a transport abort or a
+               torch.distributed error on a dead neighbour marks the attempt as failed instead of propagating;
+            2. vote (``DataParallelEngine.vote``): the step is committed only if every replica finished and nobody has
+               a notification pending;
+            3. committed: gradient all-reduce + optimizer, exactly ``_train_step``.
+               dropped : gradients are zeroed, the queued reconfiguration is applied (waiting for the agent's message if
+               the failure was noticed first), and the caller runs the step again on the new pipelines.
+
+        Parameters are only written by ``optimizer_step``, the last action of a committed step, so a dropped step leaves
+        the model exactly as the previous step left it.  Returns False for a dropped step."""
+        if self._agent_pipe is None:
+            self._train_step()
+            return True
+        failure: Exception | None = None
+        ok = not self._notified
+        global_step = self._pipeline._global_step
+        if ok:
+            try:
+                self._pipeline.train()
+                transport = getattr(self._pipeline.communication, "transport", None)
+                if transport is not None and hasattr(transport, "aborted") and transport.aborted():
+                    raise PipelineAborted("an inter-stage link was aborted")
+            except (PipelineAborted, RuntimeError) as e:
+                ok, failure = False, e
+        _dbg(f"step: pipeline ok={ok} failure={type(failure).__name__ if failure else None}; voting")
+        try:
+            agreed = self._dp_engine.vote(ok, self._pipeline.device, set(self._lost_ranks), lambda: False)
+        except (PipelineAborted, RuntimeError) as e:
+            _dbg(f"step: vote failed: {str(e)[:120]}")
+            agreed = False
+        _dbg(f"step: agreed={agreed}")
+        if agreed:
+            self._dp_engine.do_allreduce()
+            self._pipeline.execution.optimizer_step()
+            return True
+        self._pipeline._global_step = global_step      # the dropped step never happened
+        try:
+            self._pipeline.execution._optimizer.zero_grad()
+            if torch.cuda.is_available() and self._pipeline.device.type == "cuda":
+                torch.cuda.synchronize()
+        except RuntimeError:
+            pass                      # a poisoned stream: everything on it is rebuilt below anyway
+        if not self._reconfiguration.poll() and not self._wait_for_notification():
+            raise failure if failure is not None else PipelineAborted("step dropped but no loss was announced")
+        return False
+
+    def _wait_for_notification(self, timeout: float = 60.0) -> bool:
+        """A failure was noticed before the agent's lost-node message arrived: wait for the listener to queue it, then
+        apply it."""
+        t0 = time.perf_counter()
+        while time.perf_counter() - t0 < timeout:
+            if self._reconfiguration.poll():
+                return True
+            time.sleep(0.002)
+        return False
+
     def train(self):
         assert self._hf_training_args.max_steps > 0
-        for _ in range(self._hf_training_args.max_steps):
+        done = 0
+        while done < self._hf_training_args.max_steps:
             try:
                 t0 = time.perf_counter()
-                self._train_step()
-                self.step_seconds.append(time.perf_counter() - t0)
+                if self._guarded_train_step():
+                    self.step_seconds.append(time.perf_counter() - t0)
+                    done += 1
             except StopIteration:
                 self._pipeline.reset_iterator()                      # engine.py:660-663
-        if dist.is_initialized():
-            dist.barrier()
+                done += 1
+        self.barrier()
         if torch.cuda.is_available():
             torch.cuda.synchronize()
+
+    def barrier(self):
+        """End-of-training rendezvous.  The world group still contains every rank that was ever lost (it is never
+        rebuilt), so after a reconfiguration the barrier runs over a communicator of the survivors only."""
+        if not dist.is_initialized():
+            return
+        if not self._reconfigured:
+            dist.barrier()
+            return
+        alive = sorted(r for ranks in self._rank_map.values() for r in ranks) if self._rank_map else \
+            sorted(r for p in self._reconfiguration._pipelines for r in p._ranks)
+        if len(alive) <= 1:
+            return
+        key = tuple(alive)
+        if key not in _COMMUNICATORS:
+            _COMMUNICATORS[key] = _new_member_group(key, self._comm_timeout)
+        dist.barrier(group=_COMMUNICATORS[key])

@@ -154,5 +154,18 @@ class NvlinkRingTransport(DistTransport):
         return DistTransport.recv_meta(self, sender_rank)
 
     def abort(self):
-        for link in self.links.values():
-            L.load().oob_p2p_abort(link.mine, C.c_void_p(self.send_stream.cuda_stream))
+        """Listener thread: release every kernel of this rank that waits on a neighbour (a host store per mailbox)."""
+        self._abort = True
+        for link in list(self.links.values()):
+            if link.mine:
+                L.load().oob_p2p_abort(link.mine, None)
+
+    def aborted(self) -> bool:
+        """Host-side read of the mailboxes' control words: did any wait of this transport give up?"""
+        if self._abort:
+            return True
+        st = C.c_int(0)
+        for link in list(self.links.values()):
+            if link.mine and L.load().oob_p2p_status(link.mine, C.byref(st)) == 0 and st.value != 0:
+                return True
+        return False

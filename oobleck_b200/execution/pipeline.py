@@ -21,6 +21,7 @@ What changed underneath:
 from __future__ import annotations
 
 import os
+import threading
 import weakref
 from collections.abc import Mapping
 from typing import Any
@@ -33,7 +34,45 @@ from .schedule import (BackwardPass, ForwardPass, LoadMicroBatch, OobleckPipelin
                        SendActivation, SendGrad)
 from .utils import DTYPE_TO_ID, ID_TO_DTYPE, zero_grads
 
-__all__ = ["OobleckPipelineSchedule", "PipelineExecution", "PipelineCommunication", "OobleckPipeline", "RankGroup"]
+__all__ = ["OobleckPipelineSchedule", "PipelineExecution", "PipelineCommunication", "OobleckPipeline", "RankGroup",
+           "PipelineAborted"]
+
+
+class PipelineAborted(RuntimeError):
+    """A train step was cut short because a peer was lost (transport abort or communicator abort)."""
+
+
+def run_interruptible(fn, aborted) -> None:
+    """Run a blocking torch.distributed call (gloo) while staying interruptible: the call runs on a helper thread, the
+    caller polls ``aborted()`` and leaves with :class:`PipelineAborted` when it fires.  gloo can neither cancel a posted
+    operation nor report completion without blocking, so an abandoned call simply stays behind on its daemon thread --
+    messages are tagged with the pipeline generation, so an abandoned receive can never match a later message."""
+    done = threading.Event()
+    err: list[BaseException] = []
+
+    def run():
+        try:
+            fn()
+        except BaseException as e:  # noqa: BLE001
+            err.append(e)
+        finally:
+            done.set()
+
+    threading.Thread(target=run, daemon=True).start()
+    while not done.wait(0.002):
+        if aborted():
+            raise PipelineAborted("transfer abandoned: a peer was lost")
+    if err:
+        raise err[0]
+
+
+# every rebuild of the pipelines (initial build = 0, then +1 per reconfiguration) tags its wire traffic differently
+_GENERATION = [0]
+
+
+def bump_generation() -> int:
+    _GENERATION[0] += 1
+    return _GENERATION[0]
 
 
 class RankGroup:
@@ -86,7 +125,11 @@ class PipelineExecution:
         )
         num_training_steps = len(self._dataloader)
         # 2nd positional of deepspeed WarmupLR is warmup_min_lr (pipeline.py:125-127) -- kept as is
-        self._lr_scheduler = scheduler_cls(self._optimizer, self._training_args.get_warmup_steps(num_training_steps))
+        # A pipeline rebuilt after a reconfiguration continues the schedule where the job is (``step`` optimizer steps
+        # done => the next step reads lr(step - 1), deepspeed's indexing); the reference builds a fresh scheduler
+        # (pipeline.py:125-127 inside a new PipelineExecution) and so restarts the warm-up from lr = 0.
+        self._lr_scheduler = scheduler_cls(self._optimizer, self._training_args.get_warmup_steps(num_training_steps),
+                                           last_batch_iteration=pipeline._global_step - 1)
 
     @property
     def pipeline(self) -> "OobleckPipeline":
@@ -166,15 +209,37 @@ class DistTransport:
 
     def __init__(self, comm: "PipelineCommunication"):
         self.comm = weakref.ref(comm)
+        self._abort = False
+        self._tag = _GENERATION[0]
 
     def _device(self):
         return self.comm().pipeline.device
 
+    # On CPU (gloo) transfers are posted asynchronously and polled, so that a stage waiting for a neighbour that will
+    # never answer (lost, or already dropped the step) can be released by ``abort()`` from the listener thread.  NCCL
+    # point-to-point (the one-off meta handshake of the NVLink transport) keeps the reference's blocking calls.
+    def _interruptible(self) -> bool:
+        return self._device().type == "cpu"
+
     def _send(self, tensor: torch.Tensor, dest_rank: int):
-        dist.send(tensor.contiguous(), dest_rank, self.comm()._process_group)
+        if not self._interruptible():
+            dist.send(tensor.contiguous(), dest_rank, self.comm()._process_group)
+            return
+        t, pg, tag = tensor.contiguous(), self.comm()._process_group, self._tag
+        run_interruptible(lambda: dist.send(t, dest_rank, pg, tag), lambda: self._abort)
 
     def _recv(self, tensor: torch.Tensor, src_rank: int):
-        dist.recv(tensor, src_rank, self.comm()._process_group)
+        if not self._interruptible():
+            dist.recv(tensor, src_rank, self.comm()._process_group)
+            return
+        pg, tag = self.comm()._process_group, self._tag
+        run_interruptible(lambda: dist.recv(tensor, src_rank, pg, tag), lambda: self._abort)
+
+    def abort(self):
+        self._abort = True
+
+    def aborted(self) -> bool:
+        return self._abort
 
     def _long(self, data) -> torch.Tensor:
         return torch.tensor(data, dtype=torch.int64).to(self._device())

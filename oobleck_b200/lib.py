@@ -98,6 +98,7 @@ _SIGNATURES = {
     "oob_p2p_close": (_I, [_P]),
     "oob_p2p_free": (_I, [_P]),
     "oob_p2p_abort": (_I, [_P, _P]),
+    "oob_p2p_status": (_I, [_P, C.POINTER(C.c_int)]),
     "oob_p2p_send": (_I, [_P, _L, _P, _P, _I, _L, _L, C.c_uint, _I, _I, _P]),
     "oob_p2p_recv": (_I, [_P, _L, _P, _P, _I, _L, _L, C.c_uint, _I, _I, _P]),
 }

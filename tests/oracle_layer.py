@@ -30,7 +30,8 @@ class OracleAdamW:
         g = self.param_groups[0]
         for l in self.layers:
             l.sync_grads()
-            oo.adamw_step_(l.flat_param, l.flat_param.grad, l.exp_avg, l.exp_avg_sq, self._step, g["lr"], g["betas"][0],
+            l.opt_step += 1
+            oo.adamw_step_(l.flat_param, l.flat_param.grad, l.exp_avg, l.exp_avg_sq, l.opt_step, g["lr"], g["betas"][0],
                            g["betas"][1], g["eps"], g["weight_decay"])
             og.load_flat_(l.module, l.flat_param)
 
@@ -61,10 +62,17 @@ class OracleLayer:
         self._param_handle = _Handle(flat)
         self.exp_avg, self.exp_avg_sq = torch.zeros_like(flat), torch.zeros_like(flat)
         self.saved = [None] * num_pipe_buffers
+        self.opt_step = 0
 
     @classmethod
-    def create_layer_from_layer(cls, existing, pg):
+    def create_layer_from_layer(cls, existing, pg, num_pipe_buffers=None):
+        if num_pipe_buffers is not None and num_pipe_buffers > existing.num_pipe_buffers:
+            existing.saved += [None] * (num_pipe_buffers - existing.num_pipe_buffers)
+            existing.num_pipe_buffers = num_pipe_buffers
         return existing
+
+    def state_tensors(self):
+        return [self.flat_param, self.exp_avg, self.exp_avg_sq]
 
     @property
     def flat_param(self):
