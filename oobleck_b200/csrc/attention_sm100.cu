@@ -23,6 +23,8 @@
 //   backward dQ    grid (H, B, T/128 q tiles)  : per 64-key tile  S = Q K^T, dP = dO V^T, dQ += dS K
 // Warp roles: warp 0 TMA producer, warp 1 MMA issuer + TMEM owner, warps 2.. one (forward) or two (backward; each
 // half of the columns) groups of 128 row-owning threads.
+#include <type_traits>
+
 #include "kernels.h"
 
 namespace oob {
@@ -68,6 +70,15 @@ __device__ __forceinline__ void tmem_ld_x16(uint32_t taddr, uint32_t (&v)[16]) {
       : "r"(taddr)
       : "memory");
 }
+__device__ __forceinline__ void tmem_st_x16(uint32_t taddr, const uint32_t (&v)[16]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};" ::"r"(taddr),
+      "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "r"(v[8]), "r"(v[9]),
+      "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15])
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 // 16 consecutive columns of this thread's row: main + CS * corr
 template <int NPL>
 __device__ __forceinline__ void ld_combined16(uint32_t t_main, uint32_t t_corr, float (&s)[16]) {
@@ -110,33 +121,49 @@ __device__ __forceinline__ void issue_product(uint32_t sa, uint32_t sb, uint32_t
   }
 }
 
+// Two fp32 values -> packed planes (low half = x).  The packed converts (F2FP) produce both halves in one instruction
+// and the plane words need no further shuffling (the scalar version spent ~5 LOP3 / PRMT per element on packing).
+__device__ __forceinline__ void split_h2_x2(float x, float y, uint32_t& h0, uint32_t& h1) {
+  asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(h0) : "f"(y), "f"(x));
+  float fx, fy;
+  asm("{\n\t.reg .f16 lo, hi;\n\tmov.b32 {lo, hi}, %2;\n\tcvt.f32.f16 %0, lo;\n\tcvt.f32.f16 %1, hi;\n\t}"
+      : "=f"(fx), "=f"(fy)
+      : "r"(h0));
+  asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(h1) : "f"((y - fy) * H1_SCALE), "f"((x - fx) * H1_SCALE));
+}
+__device__ __forceinline__ void split3_x2(float x, float y, uint32_t& p0, uint32_t& p1, uint32_t& p2) {
+  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(p0) : "f"(y), "f"(x));
+  float rx = x - __uint_as_float(p0 << 16), ry = y - __uint_as_float(p0 & 0xffff0000u);
+  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(p1) : "f"(ry), "f"(rx));
+  rx -= __uint_as_float(p1 << 16);
+  ry -= __uint_as_float(p1 & 0xffff0000u);
+  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(p2) : "f"(ry), "f"(rx));
+}
+
 // 8 consecutive values of row `row` (columns 8*c8 ..) -> the planes of a thread-written A tile (K-major, SWIZZLE_128B:
 // the 16-byte chunk index is XORed with row & 7 -- the pattern TMA produces for the loaded tiles)
 template <int NPL>
 __device__ __forceinline__ void store_split8(uint32_t s_tile, int row, int c8, const float (&x)[8]) {
   const uint32_t addr = s_tile + row * ROWB + ((c8 ^ (row & 7)) << 4);
   if constexpr (Fmt<NPL>::FP16) {
-    uint16_t h0[8], h1[8];
+    uint32_t h0[4], h1[4];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) split_h2(x[i], h0[i], h1[i]);
-    sts_v4(addr, h0[0] | ((uint32_t)h0[1] << 16), h0[2] | ((uint32_t)h0[3] << 16), h0[4] | ((uint32_t)h0[5] << 16),
-           h0[6] | ((uint32_t)h0[7] << 16));
-    sts_v4(addr + A_PLANE, h1[0] | ((uint32_t)h1[1] << 16), h1[2] | ((uint32_t)h1[3] << 16),
-           h1[4] | ((uint32_t)h1[5] << 16), h1[6] | ((uint32_t)h1[7] << 16));
+    for (int i = 0; i < 4; ++i) split_h2_x2(x[2 * i], x[2 * i + 1], h0[i], h1[i]);
+    sts_v4(addr, h0[0], h0[1], h0[2], h0[3]);
+    sts_v4(addr + A_PLANE, h1[0], h1[1], h1[2], h1[3]);
   } else {
     uint32_t w[3][4];
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      bf16 a0, a1, a2, b0, b1, b2;
-      split3(x[2 * i], a0, a1, a2);
-      split3(x[2 * i + 1], b0, b1, b2);
-      w[0][i] = (uint32_t)__bfloat16_as_ushort(a0) | ((uint32_t)__bfloat16_as_ushort(b0) << 16);
-      w[1][i] = (uint32_t)__bfloat16_as_ushort(a1) | ((uint32_t)__bfloat16_as_ushort(b1) << 16);
-      w[2][i] = (uint32_t)__bfloat16_as_ushort(a2) | ((uint32_t)__bfloat16_as_ushort(b2) << 16);
-    }
+    for (int i = 0; i < 4; ++i) split3_x2(x[2 * i], x[2 * i + 1], w[0][i], w[1][i], w[2][i]);
 #pragma unroll
     for (int p = 0; p < 3; ++p) sts_v4(addr + p * A_PLANE, w[p][0], w[p][1], w[p][2], w[p][3]);
   }
+}
+template <int NPL>
+__device__ __forceinline__ void store_zero8(uint32_t s_tile, int row, int c8) {
+  const uint32_t addr = s_tile + row * ROWB + ((c8 ^ (row & 7)) << 4);
+#pragma unroll
+  for (int p = 0; p < NPL; ++p) sts_v4(addr + p * A_PLANE, 0u, 0u, 0u, 0u);
 }
 
 // 4 consecutive output elements: fp32 and / or split planes (plane-set codes of common.cuh)
@@ -185,7 +212,33 @@ __device__ __forceinline__ void stage_writeout(uint32_t s_stage, int tid, int nt
 
 // ---------------------------------------------------------------------------------------------------------------
 // forward.  TMEM (256 columns, two CTAs per SM): S main | S corr | O main | O corr, 64 columns each.
-enum { FB_QFULL = 0, FB_KFULL, FB_VFULL, FB_KFREE, FB_VFREE, FB_SREADY, FB_PREADY, FB_OREADY, FB_COUNT };
+//
+// Per 64-key tile j the three actors run a software pipeline (measured on the first tcgen05 version, which kept O in
+// registers and folded every tile: 70 us, tensor pipe 19 %, issue slots 41 % -- every tile was one serial round trip
+// MMA -> softmax -> MMA -> fold; profiles/r02_ncu_attn_fwd_v1_tcgen05.txt):
+//   MMA warp : S(j+1) is issued as soon as the softmax threads have pulled S(j) into registers (SFREE), i.e. it runs
+//              under the exponentials of tile j; PV(j) follows when P(j) is in shared memory.  K is double-buffered so
+//              that S(j+1) never waits for its TMA.
+//   softmax  : ONE pass over S (64 scores stay in registers), lazy running maximum: the reference point m_ref of a row
+//              only moves when the row maximum has grown by more than 2^8 (then O, still in TMEM, is rescaled with
+//              tcgen05.ld/st -- rare after the first tiles); P = exp(s - m_ref) <= 2^8 fits the fp16 pair.
+//   O        : accumulated in TMEM over all key tiles (<= 64 main MMAs per row: truncation bias ~1e-6 relative, the
+//              same budget the backward accumulators use), read once in the epilogue.
+enum { FB_QFULL = 0, FB_KFULL0, FB_KFULL1, FB_KFREE0, FB_KFREE1, FB_VFULL, FB_VFREE, FB_SREADY, FB_SFREE, FB_PREADY,
+       FB_OREADY, FB_COUNT };
+constexpr float LAZY_RESCALE_LOG2 = 8.0f;
+
+// the softmax work of one tile for one row; DIAG: the tile crosses the causal diagonal for this warp (masking needed)
+template <int NPL, bool DIAG>
+__device__ __forceinline__ void fwd_tile_scores(uint32_t tS_main, uint32_t tS_corr, int k0, int qi, float (&s)[64]) {
+#pragma unroll
+  for (int g = 0; g < 4; ++g) {
+    float t[16];
+    ld_combined16<NPL>(tS_main + g * 16, tS_corr + g * 16, t);
+#pragma unroll
+    for (int i = 0; i < 16; ++i) s[g * 16 + i] = (DIAG && k0 + g * 16 + i > qi) ? -INFINITY : t[i];
+  }
+}
 
 template <int NPL>
 __global__ void __launch_bounds__(192, NPL == 2 ? 2 : 1)
@@ -193,12 +246,10 @@ attn_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_con
                       float* __restrict__ out, uint16_t* __restrict__ planes, long plane_stride, int nplanes,
                       float* __restrict__ lse, int T, int H, float scale) {
   using F = Fmt<NPL>;
-  extern __shared__ uint8_t smem_raw[];
-  const uint32_t raw = smem_u32(smem_raw);
-  const uint32_t sQ = (raw + 1023u) & ~1023u;
-  uint8_t* smem = smem_raw + (sQ - raw);
-  const uint32_t sK = sQ + F::A_TILE, sV = sK + F::B_TILE, sP = sV + F::B_TILE;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 2 * F::A_TILE + 2 * F::B_TILE);
+  extern __shared__ __align__(1024) uint8_t smem[];   // SWIZZLE_128B tiles need 1024-B alignment (checked below)
+  const uint32_t sQ = smem_u32(smem);
+  const uint32_t sK = sQ + F::A_TILE, sV = sK + 2 * F::B_TILE, sP = sV + F::B_TILE;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 2 * F::A_TILE + 3 * F::B_TILE);
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + FB_COUNT);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -210,11 +261,12 @@ attn_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_con
   const int nkt = (kv_len + B_ROWS - 1) / B_ROWS;
   const int grow0 = b * T;   // first row of this sequence in the [B*T, *] matrices
   constexpr uint32_t TMEM_COLS = 256;
+  if ((sQ & 1023u) != 0) __trap();
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tm_q);
     tma_prefetch_desc(&tm_kv);
-    for (int i = 0; i < FB_COUNT; ++i) mbar_init(&bars[i], i == FB_PREADY ? 4 : 1);
+    for (int i = 0; i < FB_COUNT; ++i) mbar_init(&bars[i], (i == FB_PREADY || i == FB_SFREE) ? 4 : 1);
     mbar_fence_init();
   }
   if (warp == 1) tmem_alloc(tmem_slot, TMEM_COLS);
@@ -227,41 +279,53 @@ attn_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_con
   if (warp == 0) {
     // ===================== TMA producer =====================
     for (int j = 0; j < nkt; ++j) {
-      if (j > 0) mbar_wait(&bars[FB_KFREE], (j - 1) & 1);
+      const int st = j & 1;
+      if (j >= 2) mbar_wait(&bars[FB_KFREE0 + st], ((j >> 1) - 1) & 1);
       if (elect_one()) {
         if (j == 0) {
           mbar_arrive_expect_tx(&bars[FB_QFULL], F::A_TILE);
           tma_load_3d(smem, &tm_q, &bars[FB_QFULL], h * AD, grow0 + q0, 0);
         }
-        mbar_arrive_expect_tx(&bars[FB_KFULL], F::B_TILE);
-        tma_load_3d(smem + F::A_TILE, &tm_kv, &bars[FB_KFULL], E + h * AD, grow0 + j * B_ROWS, 0);
+        mbar_arrive_expect_tx(&bars[FB_KFULL0 + st], F::B_TILE);
+        tma_load_3d(smem + F::A_TILE + st * F::B_TILE, &tm_kv, &bars[FB_KFULL0 + st], E + h * AD, grow0 + j * B_ROWS, 0);
       }
       __syncwarp();
       if (j > 0) mbar_wait(&bars[FB_VFREE], (j - 1) & 1);
       if (elect_one()) {
         mbar_arrive_expect_tx(&bars[FB_VFULL], F::B_TILE);
-        tma_load_3d(smem + F::A_TILE + F::B_TILE, &tm_kv, &bars[FB_VFULL], 2 * E + h * AD, grow0 + j * B_ROWS, 0);
+        tma_load_3d(smem + F::A_TILE + 2 * F::B_TILE, &tm_kv, &bars[FB_VFULL], 2 * E + h * AD, grow0 + j * B_ROWS, 0);
       }
       __syncwarp();
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
     mbar_wait(&bars[FB_QFULL], 0);
+    mbar_wait(&bars[FB_KFULL0], 0);
+    tc_fence_after();
+    if (elect_one()) {
+      issue_product<NPL, false>(sQ, sK, tS_main, tS_corr, 0u);
+      umma_commit(&bars[FB_KFREE0]);
+      umma_commit(&bars[FB_SREADY]);
+    }
+    __syncwarp();
     for (int j = 0; j < nkt; ++j) {
-      mbar_wait(&bars[FB_KFULL], j & 1);
-      tc_fence_after();
-      // S region is free: the softmax threads arrived on PREADY(j-1) after their last read of S(j-1)
-      if (elect_one()) {
-        issue_product<NPL, false>(sQ, sK, tS_main, tS_corr, 0u);
-        umma_commit(&bars[FB_KFREE]);
-        umma_commit(&bars[FB_SREADY]);
+      if (j + 1 < nkt) {   // S(j+1): under the softmax of tile j
+        const int st = (j + 1) & 1;
+        mbar_wait(&bars[FB_KFULL0 + st], ((j + 1) >> 1) & 1);
+        mbar_wait(&bars[FB_SFREE], j & 1);      // every softmax thread holds S(j) in registers
+        tc_fence_after();
+        if (elect_one()) {
+          issue_product<NPL, false>(sQ, sK + st * F::B_TILE, tS_main, tS_corr, 0u);
+          umma_commit(&bars[FB_KFREE0 + st]);
+          umma_commit(&bars[FB_SREADY]);
+        }
+        __syncwarp();
       }
-      __syncwarp();
-      mbar_wait(&bars[FB_PREADY], j & 1);   // also: every O(j-1) read is over (program order of the softmax threads)
+      mbar_wait(&bars[FB_PREADY], j & 1);       // P(j) is in shared memory, O is rescaled if it had to be
       mbar_wait(&bars[FB_VFULL], j & 1);
       tc_fence_after();
       if (elect_one()) {
-        issue_product<NPL, true>(sP, sV, tO_main, tO_corr, 0u);
+        issue_product<NPL, true>(sP, sV, tO_main, tO_corr, j > 0 ? 1u : 0u);
         umma_commit(&bars[FB_VFREE]);
         umma_commit(&bars[FB_OREADY]);
       }
@@ -274,76 +338,88 @@ attn_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_con
     const int qi = q0 + r;
     const uint32_t lane_off = (uint32_t)(quarter * 32) << 16;
     const float sl2 = scale * LOG2E;
-    float m = -INFINITY, l = 0.f;            // running max (raw score units) and sum
-    float o[AD];
-#pragma unroll
-    for (int i = 0; i < AD; ++i) o[i] = 0.f;
+    float m_ref = -INFINITY, l = 0.f;        // reference point of the exponentials (raw score units), running sum
     for (int j = 0; j < nkt; ++j) {
       const int k0 = j * B_ROWS;
       mbar_wait(&bars[FB_SREADY], j & 1);
       tc_fence_after();
       const bool active = k0 <= q0 + quarter * 32 + 31;   // some row of this warp sees a key of this tile
       const bool diag = k0 + B_ROWS - 1 > q0 + quarter * 32;
-      float alpha = 1.f;
+      float s[64];
       if (active) {
-        float mx = m;
+        if (diag) fwd_tile_scores<NPL, true>(tS_main + lane_off, tS_corr + lane_off, k0, qi, s);
+        else fwd_tile_scores<NPL, false>(tS_main + lane_off, tS_corr + lane_off, k0, qi, s);
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&bars[FB_SFREE]);        // the tensor core may overwrite S
+      if (j > 0) {                                        // PV(j-1) done: P buffer free, O at rest
+        mbar_wait(&bars[FB_OREADY], (j - 1) & 1);
+        tc_fence_after();
+      }
+      if (active) {
+        float mx = s[0];
 #pragma unroll
-        for (int g = 0; g < 4; ++g) {
-          float s[16];
-          ld_combined16<NPL>(tS_main + lane_off + g * 16, tS_corr + lane_off + g * 16, s);
+        for (int i = 1; i < 64; ++i) mx = fmaxf(mx, s[i]);
+        const bool need = (mx - m_ref) * sl2 > LAZY_RESCALE_LOG2;   // first tile: m_ref = -inf
+        if (__any_sync(0xffffffffu, need)) {
+          const float new_ref = need ? mx : m_ref;
+          const float alpha = need ? ex2f((m_ref - new_ref) * sl2) : 1.f;
+          l *= alpha;
+          if (j > 0) {
 #pragma unroll
-          for (int i = 0; i < 16; ++i) {
-            if (diag && k0 + g * 16 + i > qi) s[i] = -INFINITY;
-            mx = fmaxf(mx, s[i]);
+            for (int g = 0; g < 8; ++g) {   // O main (4 x 16 columns) then O corr
+              uint32_t v[16];
+              tmem_ld_x16(tO_main + lane_off + g * 16, v);
+              tmem_ld_wait();
+#pragma unroll
+              for (int i = 0; i < 16; ++i) v[i] = __float_as_uint(__uint_as_float(v[i]) * alpha);
+              tmem_st_x16(tO_main + lane_off + g * 16, v);
+            }
+            tmem_st_wait();
           }
+          m_ref = new_ref;
         }
-        alpha = ex2f((m - mx) * sl2);        // m = -inf on the first tile: ex2(-inf) = 0
-        const float negm = -mx * sl2;
+        const float negm = -m_ref * sl2;
         float rowsum = 0.f;
 #pragma unroll
-        for (int g = 0; g < 4; ++g) {
-          float s[16];
-          ld_combined16<NPL>(tS_main + lane_off + g * 16, tS_corr + lane_off + g * 16, s);
+        for (int c = 0; c < 8; ++c) {
 #pragma unroll
-          for (int i = 0; i < 16; ++i) {
-            float p = ex2f(fmaf(s[i], sl2, negm));
-            if (diag && k0 + g * 16 + i > qi) p = 0.f;
-            s[i] = p;
+          for (int i = 0; i < 8; ++i) {
+            const float p = ex2f(fmaf(s[c * 8 + i], sl2, negm));   // masked scores are -inf: p = 0
+            s[c * 8 + i] = p;
             rowsum += p;
           }
-          store_split8<NPL>(sP, r, 2 * g, reinterpret_cast<const float(&)[8]>(s[0]));
-          store_split8<NPL>(sP, r, 2 * g + 1, reinterpret_cast<const float(&)[8]>(s[8]));
+          store_split8<NPL>(sP, r, c, reinterpret_cast<const float(&)[8]>(s[c * 8]));
         }
-        l = l * alpha + rowsum;
-        m = mx;
+        l += rowsum;
+      } else {
+#pragma unroll
+        for (int c = 0; c < 8; ++c) store_zero8<NPL>(sP, r, c);   // PV accumulates every row: masked rows add zero
       }
       tc_fence_before();
       fence_proxy_async();
       __syncwarp();
       if (lane == 0) mbar_arrive(&bars[FB_PREADY]);
-      mbar_wait(&bars[FB_OREADY], j & 1);
-      tc_fence_after();
-      if (active) {
+    }
+    // every MMA has completed (OREADY of the last tile): read O, normalise, stage through the dead Q tile
+    mbar_wait(&bars[FB_OREADY], (nkt - 1) & 1);
+    tc_fence_after();
+    const float inv = 1.f / l;
+    if (qi < T) lse[((long)b * H + h) * T + qi] = m_ref * scale + __logf(l);
 #pragma unroll
-        for (int g = 0; g < 4; ++g) {
-          float t[16];
-          ld_combined16<NPL>(tO_main + lane_off + g * 16, tO_corr + lane_off + g * 16, t);
+    for (int g = 0; g < 4; ++g) {
+      float o[16];
+      ld_combined16<NPL>(tO_main + lane_off + g * 16, tO_corr + lane_off + g * 16, o);
 #pragma unroll
-          for (int i = 0; i < 16; ++i) o[g * 16 + i] = fmaf(o[g * 16 + i], alpha, t[i]);
-        }
+      for (int c = 0; c < 4; ++c) {
+        const uint32_t a = stage_addr(sQ, r, g * 4 + c);
+        asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(a), "f"(o[4 * c] * inv), "f"(o[4 * c + 1] * inv),
+                     "f"(o[4 * c + 2] * inv), "f"(o[4 * c + 3] * inv)
+                     : "memory");
       }
     }
-    // every MMA has completed (OREADY of the last tile): the Q tile is dead, stage the output rows through it
     tc_fence_before();
-    const float inv = 1.f / l;
-    if (qi < T) lse[((long)b * H + h) * T + qi] = m * scale + __logf(l);
-#pragma unroll
-    for (int c = 0; c < 16; ++c) {
-      const uint32_t a = stage_addr(sQ, r, c);
-      asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(a), "f"(o[4 * c] * inv), "f"(o[4 * c + 1] * inv),
-                   "f"(o[4 * c + 2] * inv), "f"(o[4 * c + 3] * inv)
-                   : "memory");
-    }
     named_bar_sync(1, 128);
     stage_writeout(sQ, threadIdx.x - 64, 128, out, planes, plane_stride, nplanes, (long)grow0 + q0, min(A_ROWS, T - q0),
                    E, (long)h * AD);
@@ -502,23 +578,28 @@ attn_bwd_kv_sm100_kernel(const __grid_constant__ CUtensorMap tm_kv, const __grid
       tc_fence_after();
       const bool diag = q0 < k0 + A_ROWS;     // some (key, query) pair of this tile is masked
       float ds[32];
+      auto tile_body = [&](auto diag_c) {     // two instantiations: the mask costs 2 instructions per element
+        constexpr bool DIAG = decltype(diag_c)::value;
 #pragma unroll
-      for (int g = 0; g < 2; ++g) {
-        float p[16], dp[16];
-        const uint32_t c = col0 + g * 16;
-        ld_combined16<NPL>(tST + lane_off + c, tST + 64 + lane_off + c, p);
-        ld_combined16<NPL>(tDPT + lane_off + c, tDPT + 64 + lane_off + c, dp);
+        for (int g = 0; g < 2; ++g) {
+          float p[16], dp[16];
+          const uint32_t c = col0 + g * 16;
+          ld_combined16<NPL>(tST + lane_off + c, tST + 64 + lane_off + c, p);
+          ld_combined16<NPL>(tDPT + lane_off + c, tDPT + 64 + lane_off + c, dp);
 #pragma unroll
-        for (int i = 0; i < 16; ++i) {
-          const int ql = (int)c + i;
-          float pv = ex2f(fmaf(p[i], sl2, sNl[pb * B_ROWS + ql]));
-          if (diag && kj > q0 + ql) pv = 0.f;
-          p[i] = pv;
-          ds[g * 16 + i] = pv * (dp[i] - sDel[pb * B_ROWS + ql]) * scale;
+          for (int i = 0; i < 16; ++i) {
+            const int ql = (int)c + i;
+            float pv = ex2f(fmaf(p[i], sl2, sNl[pb * B_ROWS + ql]));
+            if (DIAG && kj > q0 + ql) pv = 0.f;
+            p[i] = pv;
+            ds[g * 16 + i] = pv * (dp[i] - sDel[pb * B_ROWS + ql]) * scale;
+          }
+          store_split8<NPL>(sPT, r, (int)(c >> 3), reinterpret_cast<const float(&)[8]>(p[0]));
+          store_split8<NPL>(sPT, r, (int)(c >> 3) + 1, reinterpret_cast<const float(&)[8]>(p[8]));
         }
-        store_split8<NPL>(sPT, r, (int)(c >> 3), reinterpret_cast<const float(&)[8]>(p[0]));
-        store_split8<NPL>(sPT, r, (int)(c >> 3) + 1, reinterpret_cast<const float(&)[8]>(p[8]));
-      }
+      };
+      if (diag) tile_body(std::true_type{});
+      else tile_body(std::false_type{});
       tc_fence_before();
       if constexpr (SHARED_PS) {
         fence_proxy_async();
@@ -673,21 +754,26 @@ attn_bwd_q_sm100_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_c
       mbar_wait(&bars[QB_SREADY], j & 1);     // also: dQ MMAs of the previous tile are complete -> dS buffer is free
       tc_fence_after();
       const bool diag = k0 + B_ROWS - 1 > q0;
+      auto tile_body = [&](auto diag_c) {
+        constexpr bool DIAG = decltype(diag_c)::value;
 #pragma unroll
-      for (int g = 0; g < 2; ++g) {
-        float p[16], dp[16];
-        const uint32_t c = col0 + g * 16;
-        ld_combined16<NPL>(tS + lane_off + c, tS + 64 + lane_off + c, p);
-        ld_combined16<NPL>(tDP + lane_off + c, tDP + 64 + lane_off + c, dp);
+        for (int g = 0; g < 2; ++g) {
+          float p[16], dp[16];
+          const uint32_t c = col0 + g * 16;
+          ld_combined16<NPL>(tS + lane_off + c, tS + 64 + lane_off + c, p);
+          ld_combined16<NPL>(tDP + lane_off + c, tDP + 64 + lane_off + c, dp);
 #pragma unroll
-        for (int i = 0; i < 16; ++i) {
-          float pv = ex2f(fmaf(p[i], sl2, nl));
-          if (diag && k0 + (int)c + i > qi) pv = 0.f;
-          p[i] = pv * (dp[i] - del) * scale;
+          for (int i = 0; i < 16; ++i) {
+            float pv = ex2f(fmaf(p[i], sl2, nl));
+            if (DIAG && k0 + (int)c + i > qi) pv = 0.f;
+            p[i] = pv * (dp[i] - del) * scale;
+          }
+          store_split8<NPL>(sDS, r, (int)(c >> 3), reinterpret_cast<const float(&)[8]>(p[0]));
+          store_split8<NPL>(sDS, r, (int)(c >> 3) + 1, reinterpret_cast<const float(&)[8]>(p[8]));
         }
-        store_split8<NPL>(sDS, r, (int)(c >> 3), reinterpret_cast<const float(&)[8]>(p[0]));
-        store_split8<NPL>(sDS, r, (int)(c >> 3) + 1, reinterpret_cast<const float(&)[8]>(p[8]));
-      }
+      };
+      if (diag) tile_body(std::true_type{});
+      else tile_body(std::false_type{});
       tc_fence_before();
       fence_proxy_async();
       __syncwarp();
@@ -738,7 +824,7 @@ int attention_fwd_t(const bf16* qkv, long qkv_ps, float* out, bf16* out_planes, 
   int rc;
   if ((rc = tensor_map_3d(&tq, qm, A_ROWS, NPL, 64))) return rc;
   if ((rc = tensor_map_3d(&tkv, qm, B_ROWS, NPL, 64))) return rc;
-  const size_t smem = 2 * F::A_TILE + 2 * F::B_TILE + 1024 + 128;
+  const size_t smem = 2 * F::A_TILE + 3 * F::B_TILE + 128;
   static bool once = false;
   if (!once) {
     if (set_smem((const void*)attn_fwd_sm100_kernel<NPL>, smem)) return -1;

@@ -41,6 +41,19 @@ def _round8(n: int) -> int:
     return (n + 7) // 8 * 8
 
 
+def init_tensors(layer, device) -> None:
+    """oobleck/execution/layer.py:26-37 (called by planning/profiler.py:272-274 for every ``model.layers`` entry before
+    profiling): put the layer's tensors on ``device``.  The reference fills parameters with ``torch.rand`` ("TODO: must
+    use checkpointed data"); here the layer gets its deterministic HF-style initial values (``StageLayerSpec.init_flat``)
+    when its kernels-side ``Layer`` is built, which happens on the first call (the micro-batch shape is not known
+    before)."""
+    device = torch.device(device)
+    if device.type != "cuda":
+        raise L.OobleckB200Error("oobleck_b200 stage layers live on CUDA devices only (there is no CPU path)")
+    L.load()   # fail loudly if the CUDA extension is missing
+    layer.to(device)
+
+
 class StageWorkspace:
     """Backward temporaries of one stage (``oob_bwd_scratch``) plus the two ping-pong gradient buffers that carry
     d(hidden) from layer to layer.  Shared by all layers of the stage: backward is serial on one stream."""
@@ -121,7 +134,8 @@ class Layer:
         if not torch.cuda.is_available():
             raise L.OobleckB200Error("oobleck_b200.Layer needs a CUDA device (there is no CPU path)")
         self.layer_id = layer_id
-        self.spec = layer
+        self.spec = getattr(layer, "spec", layer)      # a model.layers entry (StageLayer) or the bare spec
+        layer = self.spec
         self.device = device or torch.device("cuda", torch.cuda.current_device())
         self._rank_index = process_group.rank_index() if hasattr(process_group, "rank_index") else 0
         self._group_size = process_group.size() if hasattr(process_group, "size") else 1

@@ -109,6 +109,62 @@ class StageLayerSpec:
         return M * E * 4
 
 
+class StageLayer:
+    """What ``OobleckModel.layers`` holds: one fx shard as the control plane sees it (planning/profiler.py:66-91 and
+    :272-274): an object that ``init_tensors(layer, device)`` can materialise, that survives ``copy.deepcopy`` and
+    ``.to("cuda")``, whose ``parameters()`` can be counted and which is CALLABLE -- ``layer(*inputs) -> tuple`` with the
+    wire tuples of the fx shards (shard 0: ``(input_ids, attention_mask, labels) -> (hidden, labels)``; block:
+    ``(hidden, labels) -> (hidden, labels)``; last: ``(hidden, labels) -> (loss, logits)``).
+
+    Everything static is delegated to the :class:`StageLayerSpec`; the compute is an
+    ``oobleck_b200.execution.layer.Layer`` (CUDA kernels through the C ABI) built on first use for the micro-batch
+    shape of the call.  There is no CPU path: without a GPU / without the extension the call raises."""
+
+    def __init__(self, spec: StageLayerSpec):
+        self.spec = spec
+        self._impl = None
+        self._device = None
+
+    def __getattr__(self, name):            # kind, n_embd, num_params, init_flat(), param_shapes(), ...
+        if name in ("spec", "_impl", "_device"):
+            raise AttributeError(name)
+        return getattr(self.spec, name)
+
+    def __deepcopy__(self, memo):            # profiler.py:66: copy.deepcopy(layer).to("cuda") -- copies share the spec
+        return StageLayer(self.spec)
+
+    def __repr__(self):
+        return f"StageLayer({self.spec.kind} #{self.spec.index}, {self.spec.num_params} params)"
+
+    def parameters(self):
+        return self.spec.parameters()
+
+    def to(self, device):
+        self._device = torch.device(device)
+        return self
+
+    def materialise(self, microbatch: int, seq_len: int):
+        from ..execution.layer import Layer   # needs CUDA + the extension: fails loudly otherwise
+        impl = self._impl
+        if impl is None or impl.mb != microbatch or impl.T != seq_len:
+            dev = self._device if self._device is not None and self._device.type == "cuda" and \
+                self._device.index is not None else None
+            self._impl = Layer(self.spec.index, self.spec, None, None, None, microbatch_size=microbatch,
+                               num_pipe_buffers=1, workspace=None, seq_len=seq_len, device=dev)
+        return self._impl
+
+    def __call__(self, *inputs):
+        first = inputs[0]
+        impl = self.materialise(int(first.shape[0]), int(first.shape[1]))
+        if self.spec.kind == "embed":
+            ids, mask, labels = inputs
+            args = (ids.to(impl.device).contiguous(), mask, labels.to(impl.device).contiguous())
+        else:
+            hidden, labels = inputs
+            args = (hidden.to(impl.device, torch.float32).contiguous(), labels.to(impl.device).contiguous())
+        return tuple(impl(args, buffer_id=0))
+
+
 class OobleckModel:
     """Same constructor and attributes as oobleck/module/model.py:48-91."""
 
@@ -131,7 +187,7 @@ class OobleckModel:
         common = dict(n_embd=cfg.n_embd, n_head=cfg.n_head, n_positions=cfg.n_positions, vocab_size=cfg.vocab_size,
                       n_layer=cfg.n_layer, layer_norm_epsilon=cfg.layer_norm_epsilon)
         kinds = ["embed"] + ["block"] * cfg.n_layer + ["head"]   # sharding.py:15-18 => L + 2 shards
-        self.layers = [StageLayerSpec(index=i, kind=k, **common) for i, k in enumerate(kinds)]
+        self.layers = [StageLayer(StageLayerSpec(index=i, kind=k, **common)) for i, k in enumerate(kinds)]
         self.model_name = model_name
         self.model_tag = model_tag
         self.total_num_params = sum(layer.num_params for layer in self.layers)

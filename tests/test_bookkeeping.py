@@ -190,3 +190,28 @@ def test_copy_plan_single_pipeline_loss_raises():
     t3 = bk.dummy_template(NUM_LAYERS, 3, 1, 3)
     with pytest.raises(RuntimeError, match="No alive ranks"):
         bk.copy_plan([t4.get_rank_grid([0, 1, 2, 3])], [t3.get_rank_grid([0, 1, 2])])
+
+
+def test_model_layers_are_callable_objects_for_the_profiler():
+    """planning/profiler.py:66-91, 272-274 treats ``model.layers`` entries as modules: init_tensors(layer, device),
+    copy.deepcopy(layer).to("cuda"), layer(*input) -> tuple, layer.parameters().  Without a GPU the call must fail
+    loudly (no CPU fallback)."""
+    import copy
+
+    import pytest
+    import torch
+
+    from oobleck_b200.execution.layer import init_tensors
+    from oobleck_b200.lib import OobleckB200Error
+    from oobleck_b200.module.model import OobleckModel, StageLayer
+    m = OobleckModel("gpt2", {"input_ids": None}, None, "t", dict(n_embd=64, n_head=1, n_layer=2, n_positions=32,
+                                                                   vocab_size=101))
+    assert len(m.layers) == 4 and all(isinstance(l, StageLayer) and callable(l) for l in m.layers)
+    assert sum(p.numel() for l in m.layers for p in l.parameters()) == m.total_num_params
+    clone = copy.deepcopy(m.layers[1]).to("cuda")
+    assert clone is not m.layers[1] and clone.spec is m.layers[1].spec and clone.kind == "block"
+    with pytest.raises(OobleckB200Error):
+        init_tensors(m.layers[0], torch.device("cpu"))
+    if not torch.cuda.is_available():
+        with pytest.raises(Exception):
+            clone(torch.zeros(1, 32, 64), torch.zeros(1, 32, dtype=torch.int64))

@@ -229,6 +229,43 @@ def test_attention_fwd_bwd(B, T, H, h2):
     assert rel_err(got / gscale, q64.grad) < 1e-5
 
 
+def test_attention_lazy_rescale_and_wide_scores():
+    """The forward keeps O in TMEM and moves a row's softmax reference point only when its maximum has grown by more
+    than 2^8 (attention_sm100.cu).  Keys whose norm grows along the sequence force that rescale path many times per
+    row; scores spanning +-60 also exercise the exponent range of the fp16-pair probabilities."""
+    B, T, H, D = 2, 512, 2, 64
+    E = H * D
+    torch.manual_seed(5)
+    qkv = torch.randn(B * T, 3 * E, device=DEV)
+    ramp = torch.linspace(0.2, 6.0, T, device=DEV).repeat(B).unsqueeze(1)
+    qkv[:, E:2 * E] *= ramp                       # |k_t| grows with t: the running maximum keeps jumping
+    qkv[:, :E] *= 1.5
+    for h2 in (1, 0):
+        code = ops.PLANES_FP16_PAIR if h2 else 3
+        qp = ops.split(qkv, nplanes=code)
+        out = torch.empty(B * T, E, device=DEV)
+        outp = ops.new_planes(B * T, E)
+        lse = torch.empty(B, H, T, device=DEV)
+        L.call("oob_attention_fwd", P(qp), qp.stride(0), h2, P(out), P(outp), outp.stride(0), 3, P(lse), B, T, H, D, S())
+        q64 = qkv.double().requires_grad_(True)
+        ref = ref_attention(q64, B, T, H, D)
+        assert rel_err(out, ref) < 5e-6, (h2, rel_err(out, ref))
+        q, k, _ = q64.detach().view(B, T, 3 * E).split(E, dim=2)
+        sc = (q.view(B, T, H, D).transpose(1, 2) @ k.view(B, T, H, D).transpose(1, 2).transpose(-1, -2)) / 8.0
+        sc = sc.masked_fill(~torch.tril(torch.ones(T, T, dtype=torch.bool, device=DEV)), float("-inf"))
+        assert rel_err(lse, torch.logsumexp(sc, -1)) < 2e-6
+        dout = torch.randn(B * T, E, device=DEV)
+        ref.backward(dout.double())
+        dqkv = torch.full((B * T, 3 * E), float("nan"), device=DEV)
+        dqp = ops.new_planes(B * T, 3 * E)
+        delta = torch.empty(B, H, T, device=DEV)
+        gs = 64.0 if h2 else 1.0
+        dop = ops.split(dout * gs, nplanes=code)
+        L.call("oob_attention_bwd", P(qp), qp.stride(0), h2, P(out), P(dout * gs), P(dop), dop.stride(0), P(lse), P(delta),
+               P(dqkv), P(dqp), dqp.stride(0), code, B, T, H, D, S())
+        assert rel_err(dqkv / gs, q64.grad) < 1e-5, (h2, rel_err(dqkv / gs, q64.grad))
+
+
 def test_embedding_fwd_bwd():
     B, T, E, V = 2, 64, 128, 1000
     ids = torch.randint(0, V, (B, T), device=DEV)

@@ -103,3 +103,36 @@ def test_fb_overlap_gives_the_same_training():
     for a, b in zip(l0, l1):
         assert abs(a - b) <= 1e-6 * abs(a), (l0, l1)
     assert ((p0 - p1).abs().max() / p0.abs().max()).item() < 1e-5
+
+
+def test_profiler_style_layer_calls_match_oracle():
+    """The reference's profiler loop (planning/profiler.py:41-91, 272-274) over ``model.layers``: init_tensors, deep copy,
+    ``.to("cuda")``, ``layer(*input)`` feeding each output tuple to the next layer.  The loss that comes out of the last
+    layer must be the oracle's."""
+    import copy
+
+    from oobleck_b200.execution.layer import init_tensors
+    from oobleck_b200.module.model import OobleckModel
+    from oracle import gpt2 as og
+    margs = dict(n_embd=128, n_head=2, n_layer=2, n_positions=64, vocab_size=503)
+    model = OobleckModel("gpt2", {"input_ids": None, "attention_mask": None, "labels": None}, None, "t", margs)
+    device = torch.device("cuda")
+    for layer in model.layers:
+        init_tensors(layer, device)
+    batch = og.synthetic_batch(3, 64, 503)
+    inp = tuple(t.detach().clone().to("cuda") for t in (batch["input_ids"], batch["attention_mask"], batch["labels"]))
+    for layer in model.layers:
+        gpu_layer = copy.deepcopy(layer).to("cuda")
+        with torch.no_grad():
+            out = gpu_layer(*inp)
+            torch.cuda.synchronize()
+        assert isinstance(out, tuple)
+        inp = tuple(t.detach().clone() if isinstance(t, torch.Tensor) else t for t in out)
+    d = og.GPT2Dims(n_embd=128, n_head=2, n_layer=2, n_positions=64, vocab_size=503)
+    olayers = og.build_layers(d)
+    for ol, l in zip(olayers, model.layers):
+        og.load_flat_(ol, l.init_flat())
+    x = (batch["input_ids"], batch["attention_mask"], batch["labels"])
+    for ol in olayers:
+        x = ol(*x)
+    assert abs(float(inp[0]) - float(x[0])) < 1e-5 * abs(float(x[0]))
