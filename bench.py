@@ -3,6 +3,8 @@
 
     python bench.py --gpus N --steps K --warmup W            # this framework (CUDA, sm_100a)
     python bench.py --impl reference --gpus N --steps K ...   # the reference path's CPU restatement (oracle port)
+    python bench.py --gpus 8 --replicas 2 --model gpt2        # BASELINE config 4: 2 replicas x 4 stages (DP all-reduce)
+    python bench.py --reconfig --gpus 8 --replicas 2          # second half of the metric: kill a rank, time the recovery
 
 Workload (BASELINE.json metric / configs[2], examples/gpt3.yaml): GPT-2-XL shape (48 x 1600 x 25 heads, T=1024,
 V=50257), micro-batch 2, global batch 128 sequences (64 micro-batches) per optimizer step, 1F1B over N pipeline
@@ -16,6 +18,7 @@ import argparse
 import ctypes as C
 import json
 import os
+import socket
 import statistics
 import subprocess
 import sys
@@ -59,6 +62,23 @@ def measured_peaks():
     return {"bf16_tflops": 1400.0, "hbm_gbs": 6650.0, "source": "fallback"}
 
 
+def workload_config(model: str, cfg: dict, gpus: int, replicas: int) -> dict:
+    """The workload both arms are quoted on (identical dict in both JSON lines)."""
+    ma = cfg["model_args"]
+    stages = gpus // replicas
+    return {"workload": f"{model} 1F1B train step: {ma['num_hidden_layers'] + 2} stage layers over {stages} stage(s)"
+                        f" x {replicas} replica(s), micro-batch {cfg['microbatch']}, "
+                        f"{cfg['global_batch'] // cfg['microbatch']} micro-batches/step, T={ma['n_positions']}, AdamW",
+            "global_batch": cfg["global_batch"], "seq_len": ma["n_positions"],
+            "parallelism": (f"pp{stages}" if replicas == 1 else f"dp{replicas} x pp{stages}")}
+
+
+def free_port() -> int:
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)."""
 
@@ -95,90 +115,137 @@ class ClockSampler:
 
 
 # ---------------------------------------------------------------------------------------------------------------
-class CpuOracleSample:
-    """Bounded CPU sample of the workload: fwd+bwd of ONE sequence (1 x T tokens) through the embedding layer,
-    ``nblocks`` of the L transformer blocks and the head, timed per layer kind and scaled to the full depth
-    (t = t_embed + L * t_block + t_head).  All L blocks are identical, so the scaling is exact up to cache effects;
-    running all 48 GPT-2-XL blocks on the host costs minutes per sample."""
+# CPU arm: the oracle's torch layers behind the engine's own pipeline code -- P gloo processes,
+# a real 1F1B step over the FULL-DEPTH model, torch.set_num_threads(cores // P) -- on a bounded sample of the workload:
+# micro-batch 1 x REF_SEQ tokens, P micro-batches per step.  Nothing is extrapolated: ``value`` is the tokens the sample
+# really processed divided by the wall time it really took (max over the processes).
+REF_SEQ = int(os.environ.get("OOB_REF_SEQ", "256"))
 
-    def __init__(self, cfg, nblocks: int = 2):
-        from oracle import gpt2 as og
-        ma = cfg["model_args"]
-        self.d = og.GPT2Dims(n_embd=ma["n_embd"], n_head=ma["n_head"], n_layer=ma["num_hidden_layers"],
-                             n_positions=ma["n_positions"], vocab_size=ma.get("vocab_size", VOCAB))
-        self.og = og
-        self.cores = min(os.cpu_count() or 1, 64)
-        torch.set_num_threads(self.cores)
-        small = og.GPT2Dims(n_embd=self.d.n_embd, n_head=self.d.n_head, n_layer=min(nblocks, self.d.n_layer),
-                            n_positions=self.d.n_positions, vocab_size=self.d.vocab_size)
-        self.nblocks = small.n_layer
-        self.layers = og.build_layers(small)
-        og.init_layers_(self.layers)
-        self.sample = (f"fwd+bwd of 1 sequence x {self.d.n_positions} tokens through embedding + {self.nblocks} of "
-                       f"{self.d.n_layer} blocks + head, block time scaled to {self.d.n_layer} blocks")
 
-    def run_once(self, index: int) -> float:
-        """seconds for the full-depth model, extrapolated from this sample"""
-        og, d = self.og, self.d
-        batch = og.synthetic_batch(1, d.n_positions, d.vocab_size, index=index)
-        x = (batch["input_ids"], batch["attention_mask"], batch["labels"])
-        t_fwd = []
-        for l in self.layers:
+def _cpu_worker(rank, world, port, model, replicas, seq, steps, warmup, threads, depth, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world),
+                      LOCAL_RANK=str(rank))
+    torch.set_num_threads(threads)
+    try:
+        import torch.distributed as dist
+
+        from oobleck_b200.execution.dataloader import SyntheticTokenDataset
+        from oobleck_b200.execution.engine import (JobArguments, ModelArguments, OobleckArguments, OobleckEngine,
+                                                   layer_cost_model)
+        from oobleck_b200.planning.pipeline_template import balanced_template
+        from oracle.layer import OracleLayer
+        cfg = MODELS[model]
+        ma = dict(cfg["model_args"])
+        ma["num_hidden_layers"] = depth
+        stages = world // replicas
+        M = stages * replicas                      # one micro-batch per stage and replica in flight
+        oargs = OobleckArguments(job=JobArguments(microbatch_size=1, global_microbatch_size=M, steps=steps),
+                                 model=ModelArguments(model_name="gpt2", model_tag=model, model_args=ma))
+        ds = SyntheticTokenDataset(num_samples=max(64, M * (steps + warmup + 2)), seq_len=seq,
+                                   vocab_size=ma.get("vocab_size", VOCAB), pin_memory=False)
+        eng = OobleckEngine(rank, world, 1, None, oargs, dataset=ds, layer_cls=OracleLayer, backend="gloo")
+        eng.initialize_distributed("gloo")
+        t = balanced_template(layer_cost_model(eng._model, 1), stages, 1)
+        eng._pipeline_templates = [t]
+        eng.instantiate_pipelines(M, plan=[t] * replicas)
+        times = []
+        for it in range(warmup + steps):
+            if world > 1:
+                dist.barrier()
             t0 = time.perf_counter()
-            x = l(*x)
-            t_fwd.append(time.perf_counter() - t0)
-        t0 = time.perf_counter()
-        x[0].backward()
-        t_bwd = time.perf_counter() - t0
-        fwd_block = sum(t_fwd[1:-1]) / self.nblocks
-        fwd_rest = t_fwd[0] + t_fwd[-1]
-        # backward is timed as a whole: attribute it to blocks / rest in proportion to their forward cost
-        share_blocks = sum(t_fwd[1:-1]) / sum(t_fwd)
-        bwd_block = t_bwd * share_blocks / self.nblocks
-        bwd_rest = t_bwd * (1 - share_blocks)
-        return fwd_rest + bwd_rest + d.n_layer * (fwd_block + bwd_block)
+            try:
+                eng._train_step()
+            except StopIteration:
+                eng._pipeline.reset_iterator()
+                eng._train_step()
+            dt = torch.tensor([time.perf_counter() - t0], dtype=torch.float64)
+            if world > 1:
+                dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+            if it >= warmup:
+                times.append(float(dt))
+        if rank == 0:
+            q.put(("ok", times, M * seq))
+        if world > 1:
+            dist.barrier()
+    except Exception:  # noqa: BLE001
+        import traceback
+        q.put(("error", traceback.format_exc(), 0))
+        raise
+
+
+def cpu_pipeline_sample(model: str, gpus: int, replicas: int, steps: int, warmup: int, timeout: float = 3000.0):
+    """Spawn the P gloo processes of the CPU arm and return (seconds per step list, tokens per step, description)."""
+    import torch.multiprocessing as mp
+    cfg = MODELS[model]
+    ma = cfg["model_args"]
+    cores = os.cpu_count() or 1
+    P = gpus
+    threads = max(1, cores // P)
+    depth = ma["num_hidden_layers"]
+    # host memory: module + flat copies of parameters and gradients + two Adam moments = 24 B per parameter
+    E, V = ma["n_embd"], ma.get("vocab_size", VOCAB)
+    need = 24.0 * (12 * depth * E * E + 2 * E * V)
+    try:
+        import psutil
+        avail = float(psutil.virtual_memory().available)
+    except Exception:  # noqa: BLE001
+        avail = float("inf")
+    depth_note = ""
+    while need > 0.6 * avail and depth > 2:
+        depth //= 2
+        need = 24.0 * (12 * depth * E * E + 2 * E * V)
+        depth_note = f" (host RAM {avail / 2**30:.0f} GiB: depth reduced to {depth} of {ma['num_hidden_layers']} blocks)"
+    seq = min(REF_SEQ, ma["n_positions"])
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = free_port()
+    procs = [ctx.Process(target=_cpu_worker, args=(r, P, port, model, replicas, seq, steps, warmup, threads, depth, q))
+             for r in range(P)]
+    for p in procs:
+        p.start()
+    status, payload, tokens = q.get(timeout=timeout)
+    for p in procs:
+        p.join(timeout=120)
+    if status != "ok":
+        raise RuntimeError("CPU arm failed:\n" + str(payload))
+    sample = (f"real 1F1B train step (pipeline.train + all-reduce + AdamW) of the oracle port over {P} gloo process(es) x "
+              f"{threads} threads: full depth ({depth + 2} stage layers{depth_note}), micro-batch 1 x {seq} tokens, "
+              f"{tokens // seq} micro-batches per step; nothing extrapolated")
+    return payload, tokens, {"cores": threads * P, "sample": sample}
 
 
 def run_reference(args, cfg):
     """CPU arm: the oracle port of the reference's per-stage fwd/bwd path on the host cores (the reference itself
     hard-codes cuda/nccl/fused AdamW and cannot be installed here -- deepspeed, accelerate, HF-fx, cppcoro, oneTBB
-    are all missing).  One step = one bounded sample (see CpuOracleSample)."""
+    are all missing).  Under torchrun only rank 0 works: it spawns its own P gloo processes."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    smp = CpuOracleSample(cfg)
-    times = []
-    for it in range(args.warmup + args.steps):
-        dt = smp.run_once(it)
-        if it >= args.warmup:
-            times.append(dt)
+    for k in list(os.environ):       # the children get their own rendezvous: nothing of torchrun's may leak into them
+        if k.startswith("TORCHELASTIC") or k in ("RANK", "WORLD_SIZE", "LOCAL_RANK", "MASTER_ADDR", "MASTER_PORT",
+                                                 "LOCAL_WORLD_SIZE", "GROUP_RANK", "GROUP_WORLD_SIZE", "ROLE_RANK",
+                                                 "ROLE_WORLD_SIZE", "ROLE_NAME", "OMP_NUM_THREADS",
+                                                 "TORCH_NCCL_ASYNC_ERROR_HANDLING"):
+            os.environ.pop(k, None)
+    times, tokens, info = cpu_pipeline_sample(args.model, args.gpus, args.replicas, args.steps, args.warmup)
     sec = sum(times) / len(times)
-    value = smp.d.n_positions / sec
+    value = tokens / sec
     print(json.dumps({
         "impl": "reference", "metric": "training_tokens_per_s", "value": value, "unit": "tokens/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec * 1e3,
         "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"{args.model} 1F1B train step: {cfg['model_args']['num_hidden_layers'] + 2} stage layers, "
-                               f"micro-batch {cfg['microbatch']}, {cfg['global_batch'] // cfg['microbatch']} "
-                               f"micro-batches/step, T={cfg['model_args']['n_positions']} -- oracle port of the "
-                               "reference's torch path on the host cores, one bounded sample per step",
-                   "global_batch": cfg["global_batch"], "seq_len": cfg["model_args"]["n_positions"],
-                   "sample": smp.sample},
-        "cpu_baseline": {"value": value, "unit": "tokens/s", "cores": smp.cores, "kind": "port", "sample": smp.sample},
+        "config": workload_config(args.model, cfg, args.gpus, args.replicas),
+        "cpu_baseline": {"value": value, "unit": "tokens/s", "cores": info["cores"], "kind": "port",
+                         "sample": info["sample"]},
         "e2e": {"value": value, "unit": "tokens/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }), flush=True)
 
 
-def cpu_baseline_sample(cfg, budget_s: float = 20.0):
-    """Bounded CPU sample on rank 0 (N=1 only)."""
-    smp = CpuOracleSample(cfg)
-    smp.run_once(0)   # warm-up (allocator, thread pool)
-    t_all, n, wall = 0.0, 0, time.perf_counter()
-    while n < 1 or (time.perf_counter() - wall < budget_s and n < 3):
-        t_all += smp.run_once(n + 1)
-        n += 1
-    return {"value": n * smp.d.n_positions / t_all, "unit": "tokens/s", "cores": smp.cores, "kind": "port",
-            "sample": f"{n} x ({smp.sample})"}
+def cpu_baseline_sample(model: str):
+    """Bounded CPU sample for the N=1 line of our arm: one warm-up + two timed steps of the same CPU pipeline."""
+    times, tokens, info = cpu_pipeline_sample(model, 1, 1, steps=2, warmup=1)
+    return {"value": tokens * len(times) / sum(times), "unit": "tokens/s", "cores": info["cores"], "kind": "port",
+            "sample": f"{len(times)} x ({info['sample']})"}
 
 
 # ---------------------------------------------------------------------------------------------------------------
@@ -187,6 +254,90 @@ def _quiet_nccl():
     # NCCL_DEBUG=VERSION and above) out of it
     if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
         os.environ["NCCL_DEBUG"] = "WARN"
+
+
+def parity_check(args, cfg, world: int, rank: int, local_rank: int, transport_cls) -> dict:
+    """Before anything is timed: the benchmarked configuration (width, heads, T, micro-batch, operand format, the same
+    number of pipeline stages over the same transport) at reduced depth -- one train step of 2 micro-batches -- against
+    the oracle on the host: total loss and the global L2 norm of all parameter gradients.  Raises if either is off, so a
+    line that was printed carries a passed check (and makes multi-GPU parity visible in the driver's records)."""
+    import torch.distributed as dist
+
+    from oobleck_b200.execution.dataloader import OobleckSampler, SyntheticTokenDataset
+    from oobleck_b200.execution.engine import JobArguments, ModelArguments, OobleckArguments, OobleckEngine
+    from oobleck_b200.planning.pipeline_template import even_template
+    ma = dict(cfg["model_args"])
+    depth = max(2, world - 2) if world > 2 else 2
+    ma["num_hidden_layers"] = depth
+    T, vocab, mb, M = ma["n_positions"], ma.get("vocab_size", VOCAB), cfg["microbatch"], 2
+    oargs = OobleckArguments(job=JobArguments(microbatch_size=mb, global_microbatch_size=mb * M, steps=1),
+                             model=ModelArguments(model_name="gpt2", model_tag="parity", model_args=ma))
+    ds = SyntheticTokenDataset(num_samples=64, seq_len=T, vocab_size=vocab)
+    eng = OobleckEngine(local_rank, world, 1, None, oargs, dataset=ds, nsplit=args.nsplit, transport_cls=transport_cls,
+                        templates=[even_template(depth + 2, world)])
+    eng.initialize_distributed()
+    eng.instantiate_pipelines(M)
+    eng._pipeline.train()
+    torch.cuda.synchronize()
+    sq = torch.zeros(1, dtype=torch.float64, device="cuda")
+    for l in eng._pipeline.execution._layers:
+        sq += l.flat_grad.double().pow(2).sum()
+    loss = eng._pipeline.execution.total_loss.double().reshape(1) if eng._pipeline.is_last_stage() else \
+        torch.zeros(1, dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(sq)
+        dist.all_reduce(loss)
+    got_loss, got_gn = float(loss), float(sq.sqrt())
+    res = {"config": f"{args.model} width at depth {depth} blocks, {world} stage(s), {M} micro-batches of {mb} x {T}",
+           "loss": got_loss, "grad_norm": got_gn}
+    verdict = torch.zeros(1, device="cuda")
+    if rank == 0:
+        from oracle import gpt2 as og
+        torch.set_num_threads(min(os.cpu_count() or 1, 64))
+        d = og.GPT2Dims(n_embd=ma["n_embd"], n_head=ma["n_head"], n_layer=depth, n_positions=T, vocab_size=vocab)
+        olayers = og.build_layers(d)
+        for ol, spec in zip(olayers, eng._model.layers):
+            og.load_flat_(ol, spec.init_flat())
+        it = iter(OobleckSampler(ds, mb, 0, [M], 0))
+        ref_loss = 0.0
+        for _ in range(M):
+            ids = ds.input_ids[next(it)]
+            x = (ids, torch.ones_like(ids), ids)
+            for ol in olayers:
+                x = ol(*x)
+            x[0].backward()
+            ref_loss += float(x[0])
+        ref_gn = float(sum(og.flat_grads(ol).double().pow(2).sum() for ol in olayers).sqrt())
+        res.update(oracle_loss=ref_loss, oracle_grad_norm=ref_gn,
+                   loss_rel_err=abs(got_loss - ref_loss) / abs(ref_loss),
+                   grad_norm_rel_err=abs(got_gn - ref_gn) / abs(ref_gn), rtol=1e-4)
+        res["ok"] = bool(res["loss_rel_err"] < 1e-4 and res["grad_norm_rel_err"] < 1e-4)
+        verdict[0] = 1.0 if res["ok"] else 0.0
+    if world > 1:
+        dist.broadcast(verdict, 0)
+    del eng
+    import gc
+    gc.collect()
+    torch.cuda.empty_cache()
+    if float(verdict) != 1.0:
+        raise RuntimeError(f"parity check against the oracle failed: {res}")
+    return res
+
+
+def busy_intervals_ms(prof, base):
+    """Union length of the [start, end] windows of every forward / backward pass of one step, on this rank."""
+    iv = sorted((base.elapsed_time(a), base.elapsed_time(b)) for _, a, b in prof)
+    busy, cur_s, cur_e = 0.0, None, None
+    for s, e in iv:
+        if cur_e is None or s > cur_e:
+            if cur_e is not None:
+                busy += cur_e - cur_s
+            cur_s, cur_e = s, e
+        else:
+            cur_e = max(cur_e, e)
+    if cur_e is not None:
+        busy += cur_e - cur_s
+    return busy
 
 
 def run_ours(args, cfg):
@@ -200,6 +351,7 @@ def run_ours(args, cfg):
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     assert world == args.gpus, f"launch with torchrun --nproc-per-node {args.gpus} (WORLD_SIZE={world})"
+    assert world % args.replicas == 0, "--replicas must divide --gpus"
     _quiet_nccl()
     from oobleck_b200.execution import layer as _layer
     if args.bwd_fp16 is not None:
@@ -213,18 +365,26 @@ def run_ours(args, cfg):
     ma = cfg["model_args"]
     T, vocab = ma["n_positions"], ma.get("vocab_size", VOCAB)
     mb, gb = cfg["microbatch"], cfg["global_batch"]
+    transport_cls = None
+    if world > 1:
+        from oobleck_b200.execution.p2p import NvlinkRingTransport
+        transport_cls = NvlinkRingTransport
+
+    parity = None
+    if args.parity_check:
+        if world > 1 and not dist.is_initialized():
+            dist.init_process_group(backend="nccl", device_id=torch.device("cuda", local_rank))
+        parity = parity_check(args, cfg, world, rank, local_rank, transport_cls if args.replicas == 1 else transport_cls)
+
     oargs = OobleckArguments(job=JobArguments(microbatch_size=mb, global_microbatch_size=gb, steps=args.steps),
                              model=ModelArguments(model_name="gpt2", model_tag=args.model, model_args=dict(ma)))
     n_samples = max(2334, gb * (args.steps + args.warmup + 2) * 2)
     dataset = SyntheticTokenDataset(num_samples=n_samples, seq_len=T, vocab_size=vocab)
     dataset.to_device(torch.device("cuda", local_rank))
-
-    transport_cls = None
-    if world > 1:
-        from oobleck_b200.execution.p2p import NvlinkRingTransport
-        transport_cls = NvlinkRingTransport
-    engine = OobleckEngine(local_rank, world, 1, None, oargs, dataset=dataset, nsplit=args.nsplit,
-                           transport_cls=transport_cls, device_resident=True)
+    stages = world // args.replicas
+    engine = OobleckEngine(local_rank, stages if args.replicas > 1 else world, 1, None, oargs, dataset=dataset,
+                           nsplit=args.nsplit, transport_cls=transport_cls, device_resident=True)
+    engine._world_size = world
     engine.initialize_distributed()
     engine.instantiate_pipelines(gb // mb)
     loader = engine._pipeline._dataloader
@@ -265,8 +425,7 @@ def run_ours(args, cfg):
         return ms, losses
 
     L.call("oob_side_stream_enable", args.side_stream)
-    for _ in range(1):
-        timed(args.warmup, True, False)          # W untimed warm-up steps
+    timed(args.warmup, True, False)          # W untimed warm-up steps
     sampler = ClockSampler(local_rank)
     launches0 = L.load().oob_launch_count()
     sampler.start()
@@ -277,10 +436,32 @@ def run_ours(args, cfg):
     L.call("oob_gemm_timing_end", C.byref(g_ms), C.byref(g_fl), C.byref(g_ex), C.byref(g_n))
     ms_e2e, losses = timed(args.steps, False, True)
 
+    # one more (untimed) step with CUDA events around every forward / backward pass: how busy was each stage?
+    loader.device_resident = True
+    engine._pipeline.reset_iterator()
+    barrier()
+    engine._pipeline.profile = []
+    b0, b1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    b0.record()
+    engine._train_step()
+    b1.record()
+    barrier()
+    step_ms = b0.elapsed_time(b1)
+    busy = busy_intervals_ms(engine._pipeline.profile, b0)
+    engine._pipeline.profile = None
+    stage_stats = torch.tensor([busy, step_ms - busy], device="cuda")
+    if world > 1:
+        gathered = [torch.zeros_like(stage_stats) for _ in range(world)]
+        dist.all_gather(gathered, stage_stats)
+    else:
+        gathered = [stage_stats]
+    stage_busy = [round(float(g[0]), 2) for g in gathered]
+    stage_bubble = [round(float(g[1]), 2) for g in gathered]
+
     last_loss = losses[-1] if losses else None
-    if world > 1:   # the loss lives on the last stage; rank 0 prints
-        t = torch.tensor([last_loss if last_loss is not None else float("-inf")], device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    if world > 1:   # the loss lives on the last stage(s); rank 0 prints the sum over replicas
+        t = torch.tensor([last_loss if last_loss is not None else 0.0], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t)
         last_loss = float(t.item())
     tokens_per_step = gb * T
     value = tokens_per_step * args.steps / (ms / 1e3)
@@ -290,6 +471,7 @@ def run_ours(args, cfg):
     fpt = flops_per_token(E, Lh, T, vocab)
     exec_tflops = (g_ex.value / (g_ms.value / 1e3) / 1e12) if g_ms.value > 0 else None
     gemm_tflops = (g_fl.value / (g_ms.value / 1e3) / 1e12) if g_ms.value > 0 else None
+    template = engine._pipeline._template
     out = {
         "metric": "training_tokens_per_s", "value": value, "unit": "tokens/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong",
@@ -299,43 +481,52 @@ def run_ours(args, cfg):
                    "f32 (fp16 x2 planes forward / bf16 x3 planes backward on tcgen05, fp32 accumulate + promotion)")
                   if args.nsplit == 3 else "split-bf16 x%d on tcgen05, fp32 accumulate" % args.nsplit),
         "data": "synthetic",
-        "config": {"workload": f"{args.model} 1F1B train step: {Lh + 2} stage layers over {world} stage(s), "
-                               f"micro-batch {mb}, {gb // mb} micro-batches/step, T={T}, AdamW",
-                   "global_batch": gb, "seq_len": T, "parallelism": f"pp{world}", "nsplit": args.nsplit,
-                   "wgrad_side_stream": bool(args.side_stream), "bwd_fp16": bwd_fp16,
-                   "fb_overlap": bool(_pipeline.FB_OVERLAP),
-                   "l2": "working set per step (>6 GB of weights) far exceeds the 126 MB L2; no flush needed"},
+        "config": workload_config(args.model, cfg, world, args.replicas),
+        "engine": {"nsplit": args.nsplit, "wgrad_side_stream": bool(args.side_stream), "bwd_fp16": bwd_fp16,
+                   "fb_overlap": bool(_pipeline.FB_OVERLAP), "fb_overlap_multi_stage": bool(_pipeline.FB_OVERLAP_PP),
+                   "l2": "working set per step (>6 GB of weights) far exceeds the 126 MB L2; no flush needed",
+                   "stage_layers": [len(s._layer_indices) for s in template.get_stages()],
+                   "stage_balance_from": engine.layer_costs_source,
+                   "tensor_map_encodes": int(L.load().oob_tensor_map_encodes())},
+        "parity_check": parity,
+        "stage_busy_ms": stage_busy, "bubble_ms": stage_bubble,
         "clocks": clocks,
         "gpu_launches": int(launches),
         "e2e": {"value": e2e, "unit": "tokens/s", "h2d_bytes_per_step": 2 * 8 * gb * T,
-                "d2h_bytes_per_step": 4, "loss": last_loss},
+                "d2h_bytes_per_step": 4 * args.replicas, "loss": last_loss},
         "model_flops_fraction_of_bf16_peak": value * fpt / (world * peaks["bf16_tflops"] * 1e12),
         "roofline": {
-            "bound": "tensor", "kernel": "gemm_bf16x3_kernel (tcgen05, all GEMM launches of the last timed step)",
+            "bound": "tensor", "kernel": "gemm_bf16x3_persistent_kernel (tcgen05, all GEMM launches of the last timed step)",
             "achieved": gemm_tflops, "peak": peaks["bf16_tflops"], "unit": "TFLOP/s",
             "frac": (gemm_tflops / peaks["bf16_tflops"]) if gemm_tflops else None,
             "peak_source": peaks["source"] + " (cuBLAS bf16, sustained)",
             "tensor_products_per_algorithmic_flop": (g_ex.value / g_fl.value) if g_fl.value else None,
-            "products_note": "GEMMs on fp16 x 2 planes issue 3 products per MAC, on bf16 x 3 planes 6",
+            "products_note": "GEMMs on fp16 x 2 planes issue 3 products per MAC, on bf16 x 3 planes 6: with 3 products "
+                             "the algorithmic ceiling is peak / 3; executed_frac_of_peak is the tensor-pipe reading",
             "executed_tensor_tflops": exec_tflops,
             "executed_frac_of_peak": (exec_tflops / peaks["bf16_tflops"]) if exec_tflops else None,
             "launches_timed": int(g_n.value),
             "timing_note": "the last timed step runs without the wgrad side stream and without forward/backward "
                            "stream overlap, so each GEMM launch is timed alone",
-            # dram__bytes_read.sum + dram__bytes_write.sum of ONE launch (forward FC GEMM 2048x6400x1600 on fp16 pairs,
-            # bias + GELU epilogue writing fp32 + 5 planes) from profiles/r01_ncu_gemm_fwdfc_v5.txt: 60.7 MB read +
-            # 130.9 MB written; algorithmic bytes of that launch: 54 MB of operand planes + 183 MB of outputs
-            "traffic": 191.6e6 if args.model == "gpt2-xl" and args.nsplit == 3 else None,
-            "traffic_note": "bytes/launch, ncu --set full, forward-FC launch; `achieved` aggregates all GEMM shapes",
+            "traffic": GEMM_TRAFFIC_BYTES if args.model == "gpt2-xl" and args.nsplit == 3 and bwd_fp16 else None,
+            "traffic_note": GEMM_TRAFFIC_NOTE,
         },
     }
-    if world == 1:
-        out["cpu_baseline"] = cpu_baseline_sample(cfg)
+    if world == 1 and args.cpu_baseline:
+        out["cpu_baseline"] = cpu_baseline_sample(args.model)
     if rank == 0:
         print(json.dumps(out), flush=True)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
+
+
+# dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of the dominant GEMM shape in the DEFAULT build (fp16 pairs
+# everywhere, pair-only plane buffers): forward FC 2048 x 6400 x 1600, bias + GELU epilogue writing the fp32
+# pre-activation and the two fp16 planes of GELU(x).  Source: profiles/ (see GEMM_TRAFFIC_NOTE).
+GEMM_TRAFFIC_BYTES = None
+GEMM_TRAFFIC_NOTE = ("bytes/launch from ncu --set full of the forward-FC launch in the default (pair-only) build; "
+                     "`achieved` aggregates all GEMM shapes")
 
 
 def main():
@@ -345,6 +536,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--model", default="gpt2-xl", choices=sorted(MODELS))
+    ap.add_argument("--replicas", type=int, default=1,
+                    help="pipeline replicas (BASELINE config 4: --gpus 8 --replicas 2 = 2 x 4 stages + DP all-reduce)")
     ap.add_argument("--nsplit", type=int, default=3, choices=[1, 2, 3])
     ap.add_argument("--bwd-fp16", type=int, default=None, choices=[0, 1],
                     help="backward GEMMs on loss-scaled fp16 pairs (3 products) instead of bf16 x 3 (6); default: the "
@@ -353,9 +546,18 @@ def main():
                     help="forward(i+1) / backward(i) on two streams; default: oobleck_b200.execution.pipeline.FB_OVERLAP")
     ap.add_argument("--side-stream", type=int, default=1, choices=[0, 1],
                     help="0: weight-gradient kernels stay on the compute stream (A/B of the overlap)")
+    ap.add_argument("--parity-check", type=int, default=1, choices=[0, 1],
+                    help="check a reduced-depth model of the benchmarked width against the oracle before timing")
+    ap.add_argument("--cpu-baseline", type=int, default=1, choices=[0, 1])
+    ap.add_argument("--reconfig", action="store_true",
+                    help="reconfiguration latency after a real kill of one rank (spawns its own workers; see "
+                         "tools/reconfig_bench.py)")
     args = ap.parse_args()
     cfg = MODELS[args.model]
-    if args.impl == "reference":
+    if args.reconfig:
+        from tools.reconfig_bench import main as reconfig_main
+        reconfig_main(args)
+    elif args.impl == "reference":
         run_reference(args, cfg)
     else:
         run_ours(args, cfg)

@@ -31,6 +31,8 @@ const char* oob_last_error(void);
 /* instrumentation used by bench.py: kernels launched so far by this library, and CUDA-event timing of every
  * tcgen05 GEMM launch between begin/end (events are recorded on the launching stream; end synchronises them) */
 long oob_launch_count(void);
+/* host-side cuTensorMapEncodeTiled calls so far (TMA descriptors are cached per (buffer, shape, box)) */
+long oob_tensor_map_encodes(void);
 int oob_gemm_timing_begin(void);
 /* total_flops: algorithmic 2MNK; executed_flops: 2MNK x tensor-core products issued per MAC (1, 3 or 6) */
 int oob_gemm_timing_end(double* total_ms, double* total_flops, double* executed_flops, long* launches);

@@ -451,12 +451,20 @@ __global__ void attention_delta_kernel(const float* __restrict__ o, const float*
 //   S^T = K Q^T, dP^T = V dO^T  ->  P^T = exp(S^T scale - lse[q]),  dS^T = P^T (dP^T - delta[q]) scale
 //   dV += P^T dO,  dK += dS^T Q    (Q / dO tiles reused as MN-major B operands)
 // TMEM (512 columns): S^T | dP^T | dV | dK, each main + corr of 64 columns.
-// 10 warps: producer, MMA, and two groups of 128 row-owning threads (query columns 0-31 / 32-63 of the tile).
-enum { KB_KVFULL = 0, KB_SREADY, KB_PSREADY, KB_PTDONE, KB_DSREADY, KB_DONE, KB_QFULL0, KB_QFULL1, KB_QFREE0, KB_QFREE1,
-       KB_COUNT };
+// 18 warps: producer, MMA, and BWD_NCG groups of 128 row-owning threads, each group taking 64 / BWD_NCG query columns
+// (4 warps per scheduler hide the TMEM-load and SFU latencies; the first version ran 2 groups, sequential MMA and
+// element phases: 99 us, issue slots 34 % busy -- profiles/r02_ncu_attn_bwd_v1_tcgen05.txt).
+// Pipeline (fp16 pairs, two Q / dO stages): the element threads pull S^T / dP^T of tile i into registers and release
+// the TMEM regions at once (SFREE), so the tensor core computes S^T / dP^T of tile i+1 under the exponentials of tile i;
+// dV / dK of tile i follow when P^T / dS^T are in shared memory.
+constexpr int BWD_NCG = 4;                         // column groups
+constexpr int BWD_COLS = B_ROWS / BWD_NCG;         // 16 columns per thread
+constexpr int BWD_THREADS = 64 + 128 * BWD_NCG;    // 576
+enum { KB_KVFULL = 0, KB_SREADY, KB_SFREE, KB_PSREADY, KB_PSFREE, KB_PTDONE, KB_DSREADY, KB_DONE, KB_QFULL0, KB_QFULL1,
+       KB_QFREE0, KB_QFREE1, KB_COUNT };
 
 template <int NPL>
-__global__ void __launch_bounds__(320, 1)
+__global__ void __launch_bounds__(BWD_THREADS, 1)
 attn_bwd_kv_sm100_kernel(const __grid_constant__ CUtensorMap tm_kv, const __grid_constant__ CUtensorMap tm_q,
                          const __grid_constant__ CUtensorMap tm_do, const float* __restrict__ lse,
                          const float* __restrict__ delta, float* __restrict__ dqkv, uint16_t* __restrict__ planes,
@@ -464,10 +472,8 @@ attn_bwd_kv_sm100_kernel(const __grid_constant__ CUtensorMap tm_kv, const __grid
   using F = Fmt<NPL>;
   constexpr int STAGES = NPL == 2 ? 2 : 1;         // Q / dO ring depth (smem budget)
   constexpr bool SHARED_PS = NPL == 3;             // P^T and dS^T share one buffer (bf16 x 3 tiles are 1.5x larger)
-  extern __shared__ uint8_t smem_raw[];
-  const uint32_t raw = smem_u32(smem_raw);
-  const uint32_t sK = (raw + 1023u) & ~1023u;
-  uint8_t* smem = smem_raw + (sK - raw);
+  extern __shared__ __align__(1024) uint8_t smem[];
+  const uint32_t sK = smem_u32(smem);
   const uint32_t sV = sK + F::A_TILE;
   const uint32_t sQ0 = sV + F::A_TILE;                       // stage s: Q at sQ0 + s * 2 * B_TILE, dO right behind it
   const uint32_t sPT = sQ0 + STAGES * 2 * F::B_TILE;
@@ -487,12 +493,14 @@ attn_bwd_kv_sm100_kernel(const __grid_constant__ CUtensorMap tm_kv, const __grid
   const int ntiles = nq64 - it0;
   const int grow0 = b * T;
   constexpr uint32_t TMEM_COLS = 512;
+  if ((sK & 1023u) != 0) __trap();
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tm_kv);
     tma_prefetch_desc(&tm_q);
     tma_prefetch_desc(&tm_do);
-    for (int i = 0; i < KB_COUNT; ++i) mbar_init(&bars[i], (i == KB_PSREADY || i == KB_DSREADY) ? 8 : 1);
+    for (int i = 0; i < KB_COUNT; ++i)
+      mbar_init(&bars[i], (i == KB_PSREADY || i == KB_DSREADY || i == KB_SFREE) ? 4 * BWD_NCG : 1);
     mbar_fence_init();
   }
   if (warp == 1) tmem_alloc(tmem_slot, TMEM_COLS);
@@ -524,19 +532,25 @@ attn_bwd_kv_sm100_kernel(const __grid_constant__ CUtensorMap tm_kv, const __grid
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
-    mbar_wait(&bars[KB_KVFULL], 0);
-    for (int it = 0; it < ntiles; ++it) {
+    auto issue_scores = [&](int it) {     // S^T, dP^T of tile `it` (fresh accumulators)
       const int s = it % STAGES;
       const uint32_t sQ = sQ0 + s * 2 * F::B_TILE, sdO = sQ + F::B_TILE;
       mbar_wait(&bars[KB_QFULL0 + s], (it / STAGES) & 1);
+      if (it > 0) mbar_wait(&bars[KB_SFREE], (it - 1) & 1);   // the element threads hold tile it-1 in registers
       tc_fence_after();
-      // S^T / dP^T regions are free: PSREADY(it-1) (and DSREADY) were waited on below before the previous dV / dK
       if (elect_one()) {
         issue_product<NPL, false>(sK, sQ, tST, tST + 64, 0u);
         issue_product<NPL, false>(sV, sdO, tDPT, tDPT + 64, 0u);
         umma_commit(&bars[KB_SREADY]);
       }
       __syncwarp();
+    };
+    mbar_wait(&bars[KB_KVFULL], 0);
+    issue_scores(0);
+    for (int it = 0; it < ntiles; ++it) {
+      const int s = it % STAGES;
+      const uint32_t sQ = sQ0 + s * 2 * F::B_TILE, sdO = sQ + F::B_TILE;
+      if (STAGES == 2 && it + 1 < ntiles) issue_scores(it + 1);   // under the exponentials of tile `it`
       mbar_wait(&bars[KB_PSREADY], it & 1);
       tc_fence_after();
       if (elect_one()) {
@@ -551,19 +565,21 @@ attn_bwd_kv_sm100_kernel(const __grid_constant__ CUtensorMap tm_kv, const __grid
       if (elect_one()) {
         issue_product<NPL, true>(sDS, sQ, tDK, tDK + 64, it > 0 ? 1u : 0u);
         umma_commit(&bars[KB_QFREE0 + s]);
+        umma_commit(&bars[KB_PSFREE]);
         if (it == ntiles - 1) umma_commit(&bars[KB_DONE]);
       }
       __syncwarp();
+      if (STAGES == 1 && it + 1 < ntiles) issue_scores(it + 1);   // one Q / dO stage: its reload needs dK(it) done
     }
   } else {
-    // ===================== P^T / dS^T threads: one key row, 32 query columns each =====================
+    // ===================== P^T / dS^T threads: one key row, BWD_COLS query columns each =====================
     const int quarter = warp & 3;
-    const int half = (warp - 2) >> 2;             // query columns [32*half, 32*half + 32) of the tile
+    const int cg = (warp - 2) >> 2;               // query columns [BWD_COLS * cg, +BWD_COLS) of the tile
     const int r = quarter * 32 + lane;
     const int kj = k0 + r;
-    const int tid = threadIdx.x - 64;             // 0..255
+    const int tid = threadIdx.x - 64;             // 0 .. 128 * BWD_NCG - 1
     const uint32_t lane_off = (uint32_t)(quarter * 32) << 16;
-    const uint32_t col0 = (uint32_t)(half * 32);
+    const uint32_t col0 = (uint32_t)(cg * BWD_COLS);
     const float sl2 = scale * LOG2E;
     for (int it = 0; it < ntiles; ++it) {
       const int q0 = (it0 + it) * B_ROWS;
@@ -573,43 +589,40 @@ attn_bwd_kv_sm100_kernel(const __grid_constant__ CUtensorMap tm_kv, const __grid
         sNl[pb * B_ROWS + tid] = qi < T ? -lse[((long)b * H + h) * T + qi] * LOG2E : -INFINITY;
         sDel[pb * B_ROWS + tid] = qi < T ? delta[((long)b * H + h) * T + qi] : 0.f;
       }
-      named_bar_sync(1, 256);
-      mbar_wait(&bars[KB_SREADY], it & 1);   // also: dV / dK of the previous tile are complete (commit order)
+      named_bar_sync(1, 128 * BWD_NCG);
+      mbar_wait(&bars[KB_SREADY], it & 1);
       tc_fence_after();
+      float p[BWD_COLS], dp[BWD_COLS];
+      ld_combined16<NPL>(tST + lane_off + col0, tST + 64 + lane_off + col0, p);
+      ld_combined16<NPL>(tDPT + lane_off + col0, tDPT + 64 + lane_off + col0, dp);
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&bars[KB_SFREE]);            // the tensor core may start the next tile's scores
       const bool diag = q0 < k0 + A_ROWS;     // some (key, query) pair of this tile is masked
-      float ds[32];
       auto tile_body = [&](auto diag_c) {     // two instantiations: the mask costs 2 instructions per element
         constexpr bool DIAG = decltype(diag_c)::value;
 #pragma unroll
-        for (int g = 0; g < 2; ++g) {
-          float p[16], dp[16];
-          const uint32_t c = col0 + g * 16;
-          ld_combined16<NPL>(tST + lane_off + c, tST + 64 + lane_off + c, p);
-          ld_combined16<NPL>(tDPT + lane_off + c, tDPT + 64 + lane_off + c, dp);
-#pragma unroll
-          for (int i = 0; i < 16; ++i) {
-            const int ql = (int)c + i;
-            float pv = ex2f(fmaf(p[i], sl2, sNl[pb * B_ROWS + ql]));
-            if (DIAG && kj > q0 + ql) pv = 0.f;
-            p[i] = pv;
-            ds[g * 16 + i] = pv * (dp[i] - sDel[pb * B_ROWS + ql]) * scale;
-          }
-          store_split8<NPL>(sPT, r, (int)(c >> 3), reinterpret_cast<const float(&)[8]>(p[0]));
-          store_split8<NPL>(sPT, r, (int)(c >> 3) + 1, reinterpret_cast<const float(&)[8]>(p[8]));
+        for (int i = 0; i < BWD_COLS; ++i) {
+          const int ql = (int)col0 + i;
+          float pv = ex2f(fmaf(p[i], sl2, sNl[pb * B_ROWS + ql]));
+          if (DIAG && kj > q0 + ql) pv = 0.f;
+          p[i] = pv;
+          dp[i] = pv * (dp[i] - sDel[pb * B_ROWS + ql]) * scale;    // dS^T
         }
       };
       if (diag) tile_body(std::true_type{});
       else tile_body(std::false_type{});
-      tc_fence_before();
+      if (it > 0) mbar_wait(&bars[KB_PSFREE], (it - 1) & 1);   // dV / dK of the previous tile have consumed the buffers
+      store_split8<NPL>(sPT, r, (int)(col0 >> 3), reinterpret_cast<const float(&)[8]>(p[0]));
+      store_split8<NPL>(sPT, r, (int)(col0 >> 3) + 1, reinterpret_cast<const float(&)[8]>(p[8]));
       if constexpr (SHARED_PS) {
         fence_proxy_async();
         __syncwarp();
         if (lane == 0) mbar_arrive(&bars[KB_PSREADY]);
         mbar_wait(&bars[KB_PTDONE], it & 1);   // dV has consumed P^T: the buffer may take dS^T
       }
-#pragma unroll
-      for (int g = 0; g < 4; ++g)
-        store_split8<NPL>(sDS, r, (int)(col0 >> 3) + g, reinterpret_cast<const float(&)[8]>(ds[8 * g]));
+      store_split8<NPL>(sDS, r, (int)(col0 >> 3), reinterpret_cast<const float(&)[8]>(dp[0]));
+      store_split8<NPL>(sDS, r, (int)(col0 >> 3) + 1, reinterpret_cast<const float(&)[8]>(dp[8]));
       fence_proxy_async();
       __syncwarp();
       if (lane == 0) mbar_arrive(&bars[SHARED_PS ? KB_DSREADY : KB_PSREADY]);
@@ -621,23 +634,19 @@ attn_bwd_kv_sm100_kernel(const __grid_constant__ CUtensorMap tm_kv, const __grid
 #pragma unroll 1
     for (int which = 0; which < 2; ++which) {
       const uint32_t tacc = which == 0 ? tDK : tDV;
+      float v[BWD_COLS];
+      ld_combined16<NPL>(tacc + lane_off + col0, tacc + 64 + lane_off + col0, v);
 #pragma unroll
-      for (int g = 0; g < 2; ++g) {
-        float v[16];
-        const uint32_t c = col0 + g * 16;
-        ld_combined16<NPL>(tacc + lane_off + c, tacc + 64 + lane_off + c, v);
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          const uint32_t a = stage_addr(sPT, r, (int)(c >> 2) + q);
-          asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(a), "f"(v[4 * q]), "f"(v[4 * q + 1]),
-                       "f"(v[4 * q + 2]), "f"(v[4 * q + 3])
-                       : "memory");
-        }
+      for (int q = 0; q < 4; ++q) {
+        const uint32_t a = stage_addr(sPT, r, (int)(col0 >> 2) + q);
+        asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(a), "f"(v[4 * q]), "f"(v[4 * q + 1]),
+                     "f"(v[4 * q + 2]), "f"(v[4 * q + 3])
+                     : "memory");
       }
-      named_bar_sync(1, 256);
-      stage_writeout(sPT, tid, 256, dqkv, planes, plane_stride, nplanes, (long)grow0 + k0, rows_valid, 3L * E,
+      named_bar_sync(1, 128 * BWD_NCG);
+      stage_writeout(sPT, tid, 128 * BWD_NCG, dqkv, planes, plane_stride, nplanes, (long)grow0 + k0, rows_valid, 3L * E,
                      (long)(which + 1) * E + h * AD);
-      named_bar_sync(1, 256);
+      named_bar_sync(1, 128 * BWD_NCG);
     }
     tc_fence_before();
   }
@@ -653,21 +662,20 @@ attn_bwd_kv_sm100_kernel(const __grid_constant__ CUtensorMap tm_kv, const __grid
 // ---------------------------------------------------------------------------------------------------------------
 // backward, dQ of one tile of 128 queries (rows = queries).  Per 64-key tile:
 //   S = Q K^T, dP = dO V^T  ->  dS = exp(S scale - lse) (dP - delta) scale,   dQ += dS K   (K tile reused MN-major)
-// TMEM (512 allocated): S | dP | dQ, each main + corr of 64 columns.
-enum { QB_QFULL = 0, QB_SREADY, QB_DSREADY, QB_DONE, QB_KVFULL0, QB_KVFULL1, QB_KVFREE0, QB_KVFREE1, QB_COUNT };
+// TMEM (512 allocated): S | dP | dQ, each main + corr of 64 columns.  Same pipeline as above.
+enum { QB_QFULL = 0, QB_SREADY, QB_SFREE, QB_DSREADY, QB_DSFREE, QB_DONE, QB_KVFULL0, QB_KVFULL1, QB_KVFREE0, QB_KVFREE1,
+       QB_COUNT };
 
 template <int NPL>
-__global__ void __launch_bounds__(320, 1)
+__global__ void __launch_bounds__(BWD_THREADS, 1)
 attn_bwd_q_sm100_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_do,
                         const __grid_constant__ CUtensorMap tm_kv, const float* __restrict__ lse,
                         const float* __restrict__ delta, float* __restrict__ dqkv, uint16_t* __restrict__ planes,
                         long plane_stride, int nplanes, int T, int H, float scale) {
   using F = Fmt<NPL>;
   constexpr int STAGES = NPL == 2 ? 2 : 1;
-  extern __shared__ uint8_t smem_raw[];
-  const uint32_t raw = smem_u32(smem_raw);
-  const uint32_t sQ = (raw + 1023u) & ~1023u;
-  uint8_t* smem = smem_raw + (sQ - raw);
+  extern __shared__ __align__(1024) uint8_t smem[];
+  const uint32_t sQ = smem_u32(smem);
   const uint32_t sdO = sQ + F::A_TILE;
   const uint32_t sK0 = sdO + F::A_TILE;                      // stage s: K at sK0 + s * 2 * B_TILE, V right behind it
   const uint32_t sDS = sK0 + STAGES * 2 * F::B_TILE;
@@ -683,12 +691,13 @@ attn_bwd_q_sm100_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_c
   const int nkt = (kv_len + B_ROWS - 1) / B_ROWS;
   const int grow0 = b * T;
   constexpr uint32_t TMEM_COLS = 512;
+  if ((sQ & 1023u) != 0) __trap();
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tm_q);
     tma_prefetch_desc(&tm_do);
     tma_prefetch_desc(&tm_kv);
-    for (int i = 0; i < QB_COUNT; ++i) mbar_init(&bars[i], i == QB_DSREADY ? 8 : 1);
+    for (int i = 0; i < QB_COUNT; ++i) mbar_init(&bars[i], (i == QB_DSREADY || i == QB_SFREE) ? 4 * BWD_NCG : 1);
     mbar_fence_init();
   }
   if (warp == 1) tmem_alloc(tmem_slot, TMEM_COLS);
@@ -717,11 +726,11 @@ attn_bwd_q_sm100_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_c
       __syncwarp();
     }
   } else if (warp == 1) {
-    mbar_wait(&bars[QB_QFULL], 0);
-    for (int j = 0; j < nkt; ++j) {
+    auto issue_scores = [&](int j) {
       const int s = j % STAGES;
       const uint32_t sKt = sK0 + s * 2 * F::B_TILE, sVt = sKt + F::B_TILE;
       mbar_wait(&bars[QB_KVFULL0 + s], (j / STAGES) & 1);
+      if (j > 0) mbar_wait(&bars[QB_SFREE], (j - 1) & 1);
       tc_fence_after();
       if (elect_one()) {
         issue_product<NPL, false>(sQ, sKt, tS, tS + 64, 0u);
@@ -729,75 +738,81 @@ attn_bwd_q_sm100_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_c
         umma_commit(&bars[QB_SREADY]);
       }
       __syncwarp();
+    };
+    mbar_wait(&bars[QB_QFULL], 0);
+    issue_scores(0);
+    for (int j = 0; j < nkt; ++j) {
+      const int s = j % STAGES;
+      const uint32_t sKt = sK0 + s * 2 * F::B_TILE;
+      if (STAGES == 2 && j + 1 < nkt) issue_scores(j + 1);
       mbar_wait(&bars[QB_DSREADY], j & 1);
       tc_fence_after();
       if (elect_one()) {
         issue_product<NPL, true>(sDS, sKt, tDQ, tDQ + 64, j > 0 ? 1u : 0u);
         umma_commit(&bars[QB_KVFREE0 + s]);
+        umma_commit(&bars[QB_DSFREE]);
         if (j == nkt - 1) umma_commit(&bars[QB_DONE]);
       }
       __syncwarp();
+      if (STAGES == 1 && j + 1 < nkt) issue_scores(j + 1);
     }
   } else {
     const int quarter = warp & 3;
-    const int half = (warp - 2) >> 2;             // key columns [32*half, +32) of the tile
+    const int cg = (warp - 2) >> 2;               // key columns [BWD_COLS * cg, +BWD_COLS) of the tile
     const int r = quarter * 32 + lane;
     const int qi = q0 + r;
     const int tid = threadIdx.x - 64;
     const uint32_t lane_off = (uint32_t)(quarter * 32) << 16;
-    const uint32_t col0 = (uint32_t)(half * 32);
+    const uint32_t col0 = (uint32_t)(cg * BWD_COLS);
     const float sl2 = scale * LOG2E;
     const float nl = qi < T ? -lse[((long)b * H + h) * T + qi] * LOG2E : -INFINITY;
     const float del = qi < T ? delta[((long)b * H + h) * T + qi] : 0.f;
     for (int j = 0; j < nkt; ++j) {
       const int k0 = j * B_ROWS;
-      mbar_wait(&bars[QB_SREADY], j & 1);     // also: dQ MMAs of the previous tile are complete -> dS buffer is free
+      mbar_wait(&bars[QB_SREADY], j & 1);
       tc_fence_after();
+      float p[BWD_COLS], dp[BWD_COLS];
+      ld_combined16<NPL>(tS + lane_off + col0, tS + 64 + lane_off + col0, p);
+      ld_combined16<NPL>(tDP + lane_off + col0, tDP + 64 + lane_off + col0, dp);
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&bars[QB_SFREE]);
       const bool diag = k0 + B_ROWS - 1 > q0;
       auto tile_body = [&](auto diag_c) {
         constexpr bool DIAG = decltype(diag_c)::value;
 #pragma unroll
-        for (int g = 0; g < 2; ++g) {
-          float p[16], dp[16];
-          const uint32_t c = col0 + g * 16;
-          ld_combined16<NPL>(tS + lane_off + c, tS + 64 + lane_off + c, p);
-          ld_combined16<NPL>(tDP + lane_off + c, tDP + 64 + lane_off + c, dp);
-#pragma unroll
-          for (int i = 0; i < 16; ++i) {
-            float pv = ex2f(fmaf(p[i], sl2, nl));
-            if (DIAG && k0 + (int)c + i > qi) pv = 0.f;
-            p[i] = pv * (dp[i] - del) * scale;
-          }
-          store_split8<NPL>(sDS, r, (int)(c >> 3), reinterpret_cast<const float(&)[8]>(p[0]));
-          store_split8<NPL>(sDS, r, (int)(c >> 3) + 1, reinterpret_cast<const float(&)[8]>(p[8]));
+        for (int i = 0; i < BWD_COLS; ++i) {
+          float pv = ex2f(fmaf(p[i], sl2, nl));
+          if (DIAG && k0 + (int)col0 + i > qi) pv = 0.f;
+          p[i] = pv * (dp[i] - del) * scale;
         }
       };
       if (diag) tile_body(std::true_type{});
       else tile_body(std::false_type{});
-      tc_fence_before();
+      if (j > 0) mbar_wait(&bars[QB_DSFREE], (j - 1) & 1);     // dQ of the previous tile has consumed the dS buffer
+      store_split8<NPL>(sDS, r, (int)(col0 >> 3), reinterpret_cast<const float(&)[8]>(p[0]));
+      store_split8<NPL>(sDS, r, (int)(col0 >> 3) + 1, reinterpret_cast<const float(&)[8]>(p[8]));
       fence_proxy_async();
       __syncwarp();
       if (lane == 0) mbar_arrive(&bars[QB_DSREADY]);
     }
     mbar_wait(&bars[QB_DONE], 0);
     tc_fence_after();
-#pragma unroll
-    for (int g = 0; g < 2; ++g) {
-      float v[16];
-      const uint32_t c = col0 + g * 16;
-      ld_combined16<NPL>(tDQ + lane_off + c, tDQ + 64 + lane_off + c, v);
+    {
+      float v[BWD_COLS];
+      ld_combined16<NPL>(tDQ + lane_off + col0, tDQ + 64 + lane_off + col0, v);
 #pragma unroll
       for (int q = 0; q < 4; ++q) {
-        const uint32_t a = stage_addr(sDS, r, (int)(c >> 2) + q);
+        const uint32_t a = stage_addr(sDS, r, (int)(col0 >> 2) + q);
         asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(a), "f"(v[4 * q]), "f"(v[4 * q + 1]),
                      "f"(v[4 * q + 2]), "f"(v[4 * q + 3])
                      : "memory");
       }
     }
     tc_fence_before();
-    named_bar_sync(1, 256);
-    stage_writeout(sDS, tid, 256, dqkv, planes, plane_stride, nplanes, (long)grow0 + q0, min(A_ROWS, T - q0), 3L * E,
-                   (long)h * AD);
+    named_bar_sync(1, 128 * BWD_NCG);
+    stage_writeout(sDS, tid, 128 * BWD_NCG, dqkv, planes, plane_stride, nplanes, (long)grow0 + q0, min(A_ROWS, T - q0),
+                   3L * E, (long)h * AD);
   }
 
   tc_fence_before();
@@ -853,8 +868,8 @@ int attention_bwd_t(const bf16* qkv, long qkv_ps, const float* out, const float*
   if ((rc = tensor_map_3d(&tq64, qm, B_ROWS, NPL, 64))) return rc;
   if ((rc = tensor_map_3d(&tdo128, dm, A_ROWS, NPL, 64))) return rc;
   if ((rc = tensor_map_3d(&tdo64, dm, B_ROWS, NPL, 64))) return rc;
-  const size_t smem_kv = 2 * F::A_TILE + STAGES * 2 * F::B_TILE + (NPL == 3 ? 1 : 2) * F::A_TILE + 1024 + 1024 + 256;
-  const size_t smem_q = 3 * F::A_TILE + STAGES * 2 * F::B_TILE + 1024 + 128;
+  const size_t smem_kv = 2 * F::A_TILE + STAGES * 2 * F::B_TILE + (NPL == 3 ? 1 : 2) * F::A_TILE + 1024 + 256;
+  const size_t smem_q = 3 * F::A_TILE + STAGES * 2 * F::B_TILE + 256;
   static bool once = false;
   if (!once) {
     if (set_smem((const void*)attn_bwd_kv_sm100_kernel<NPL>, smem_kv)) return -1;
@@ -868,11 +883,11 @@ int attention_bwd_t(const bf16* qkv, long qkv_ps, const float* out, const float*
   dim3 grid(H, B, (T + A_ROWS - 1) / A_ROWS);
   const float scale = 1.0f / sqrtf((float)AD);
   uint16_t* pl = reinterpret_cast<uint16_t*>(dqkv_planes);
-  attn_bwd_kv_sm100_kernel<NPL><<<grid, 320, smem_kv, s>>>(*tq128, *tq64, *tdo64, lse, delta, dqkv, pl, plane_stride,
+  attn_bwd_kv_sm100_kernel<NPL><<<grid, BWD_THREADS, smem_kv, s>>>(*tq128, *tq64, *tdo64, lse, delta, dqkv, pl, plane_stride,
                                                            nplanes, T, H, scale);
   OOB_CUDA_OK(cudaGetLastError());
   count_launch();
-  attn_bwd_q_sm100_kernel<NPL><<<grid, 320, smem_q, s>>>(*tq128, *tdo128, *tq64, lse, delta, dqkv, pl, plane_stride,
+  attn_bwd_q_sm100_kernel<NPL><<<grid, BWD_THREADS, smem_q, s>>>(*tq128, *tdo128, *tq64, lse, delta, dqkv, pl, plane_stride,
                                                          nplanes, T, H, scale);
   OOB_CUDA_OK(cudaGetLastError());
   count_launch();

@@ -35,6 +35,7 @@ int oob_gemm_timing_end(double* total_ms, double* total_flops, double* executed_
   return gemm_timing_end(total_ms, total_flops, executed_flops, launches);
 }
 const char* oob_last_error(void) { return g_err; }
+long oob_tensor_map_encodes(void) { return tensor_map_encodes(); }
 long oob_ln_bwd_partials_floats(int n_embd) { return (long)LN_BWD_MAX_GRID * 2 * n_embd; }
 long oob_colsum_partials_floats(int cols) { return (long)COLSUM_MAX_PARTS * cols; }
 

@@ -203,7 +203,15 @@ class DataParallelEngine:
                 run_interruptible(lambda g=g: dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=g), aborted)
             else:
                 dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=g)
-        return bool(flag.item())      # device -> host read: the only synchronisation an elastic step adds
+        agreed = bool(flag.item())    # device -> host read: the only synchronisation an elastic step adds
+        # an all-reduce released by ncclCommAbort leaves garbage behind: a communicator that turned out to contain a
+        # lost rank while we were waiting cannot have produced a vote
+        lost_now = set(self.engine._lost_ranks)
+        for per_layer in self._dp_process_groups.values():
+            for pg in per_layer.values():
+                if pg.group in groups and lost_now & set(pg.ranks):
+                    return False
+        return agreed
 
     def do_allreduce(self):
         """engine.py:404-412: every local layer reduces over the groups that contain this rank."""
@@ -504,6 +512,7 @@ class OobleckEngine:
         self._rank = 0
         self._world_size = num_nodes * num_gpus_per_node
         self.step_seconds: list[float] = []
+        self.step_end_times: list[float] = []     # time.perf_counter() at the end of every completed step
         self._reconfiguration = None
         self._step_aborted = False
 
@@ -513,10 +522,16 @@ class OobleckEngine:
                                    self._hf_training_args, args.model.model_tag, margs)
         self._dataset = dataset if dataset is not None else SyntheticTokenDataset(
             seq_len=n_positions, vocab_size=self._model.model_args.vocab_size)
+        # Without injected templates (the planner is control plane) stages are balanced on per-layer costs: measured
+        # on the GPU at instantiate_pipelines() time when this engine runs CUDA layers (planning/profiler.py), from the
+        # FLOP model otherwise.  ``layer_costs`` is kept for inspection (bench.py prints it).
+        self.layer_costs: list[float] | None = None
+        self.layer_costs_source = "FLOP model"
+        self._templates_injected = templates is not None
         if templates is None:
-            costs = layer_cost_model(self._model, args.job.microbatch_size)
-            templates = [balanced_template(costs, n, num_gpus_per_node)
-                         for n in range(1, num_nodes + 1) if n <= len(costs)]
+            self.layer_costs = layer_cost_model(self._model, args.job.microbatch_size)
+            templates = [balanced_template(self.layer_costs, n, num_gpus_per_node)
+                         for n in range(1, num_nodes + 1) if n <= len(self.layer_costs)]
         self._pipeline_templates = templates
 
     # -- distributed -------------------------------------------------------------------------------------------------
@@ -639,6 +654,13 @@ class OobleckEngine:
 
     def instantiate_pipelines(self, global_num_microbatch: int, plan: list[PipelineTemplate] | None = None):
         """engine.py:600-643."""
+        if (not self._templates_injected and plan is None and self._layer_cls is None and torch.cuda.is_available()
+                and os.environ.get("OOB_MEASURED_BALANCE", "1") == "1" and self._num_nodes > 1):
+            from ..planning.profiler import measured_layer_costs
+            self.layer_costs = measured_layer_costs(self._model, self._args.job.microbatch_size)
+            self.layer_costs_source = "measured (CUDA events, fwd + bwd ms per layer kind, rank 0, broadcast)"
+            self._pipeline_templates = [balanced_template(self.layer_costs, n, self._num_gpus_per_node)
+                                        for n in range(1, self._num_nodes + 1) if n <= len(self.layer_costs)]
         plan = plan or self.choose_plan()
         num_microbatches = self.distribute_microbatches(plan, global_num_microbatch)
         ranks_list, used = [], 0
@@ -738,7 +760,11 @@ class OobleckEngine:
             try:
                 t0 = time.perf_counter()
                 if self._guarded_train_step():
-                    self.step_seconds.append(time.perf_counter() - t0)
+                    if self._agent_pipe is not None and torch.cuda.is_available() and \
+                            self._pipeline.device.type == "cuda":
+                        torch.cuda.synchronize()      # elastic runs: a step counts when its kernels have finished
+                    self.step_end_times.append(time.perf_counter())
+                    self.step_seconds.append(self.step_end_times[-1] - t0)
                     done += 1
             except StopIteration:
                 self._pipeline.reset_iterator()                      # engine.py:660-663

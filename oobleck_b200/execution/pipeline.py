@@ -95,11 +95,12 @@ def _my_rank() -> int:
     return dist.get_rank() if dist.is_initialized() else 0
 
 
-# forward / backward passes of consecutive micro-batches on two CUDA streams (OobleckPipeline.train).  Applied to
-# single-stage pipelines only: with several stages 1F1B already interleaves the two directions across GPUs, and that is
-# the configuration the NVLink-ring transports have been validated in.  Measured on GPT-2-XL, N=1: +2.4 % tokens/s
-# (the step is power-capped: the extra concurrency costs ~100 MHz of SM clock).
+# forward / backward passes of consecutive micro-batches on two CUDA streams (OobleckPipeline.train).  Measured on
+# GPT-2-XL, N=1: +2.4 % tokens/s (the step is power-capped: the extra concurrency costs ~100 MHz of SM clock).
+# Round 1 applied it to single-stage pipelines only; FB_OVERLAP_PP extends it to the stages of a multi-stage pipeline
+# (in the 1F1B steady state every stage alternates one forward and one backward: the same overlap applies).
 FB_OVERLAP = os.environ.get("OOB_FB_OVERLAP", "1") == "1"
+FB_OVERLAP_PP = os.environ.get("OOB_FB_OVERLAP_PP", "1") == "1"
 
 
 class PipelineExecution:
@@ -188,6 +189,14 @@ class PipelineExecution:
         ws = getattr(self._layers[0], "workspace", None)
         if ws is not None and hasattr(ws, "join"):
             ws.join()     # weight-gradient kernels run on a side stream; the ctx slot is recycled after this pass
+        if self.pipeline.device.type == "cuda":
+            # the stage inputs were allocated under the forward stream (received activations, H2D copies) but this
+            # pass reads them on the current stream: tell the allocator, or the block may be handed out again -- to
+            # a forward-stream allocation -- while these kernels still read it (send_gradients drops the last reference)
+            cur = torch.cuda.current_stream()
+            for t in self.pipeline.pipe_buffers["inputs"][buffer_id] or ():
+                if isinstance(t, torch.Tensor) and t.is_cuda:
+                    t.record_stream(cur)
         if grad is not None:
             # gradient w.r.t. the stage input: parked on the input tensor like autograd would (send_gradients reads
             # ``buffer.grad``, :395-401).  Copied out of the stage's ping-pong buffer because the transfer is async.
@@ -389,8 +398,10 @@ class OobleckPipeline:
         # ordered by three kinds of events only -- forward(b) -> backward(b), backward(b) -> next occupant of pipe
         # buffer b, end of step -> optimizer.  The GPU then fills the short last waves / small kernels of one pass
         # with CTAs of the other.  Issue order (the reference's 1F1B program) is unchanged.
+        single_stage = self.is_first_stage() and self.is_last_stage()
         overlap = (FB_OVERLAP and self.device.type == "cuda" and torch.cuda.is_available()
-                   and self.is_first_stage() and self.is_last_stage())
+                   and (single_stage or FB_OVERLAP_PP))
+        prof = getattr(self, "profile", None)   # bench.py: CUDA-event pairs around every forward / backward pass
         if overlap:
             if getattr(self, "_fwd_stream", None) is None:
                 self._fwd_stream = torch.cuda.Stream()
@@ -403,25 +414,43 @@ class OobleckPipeline:
             for cmd in step_cmds:
                 if type(cmd) not in instruction_map:
                     raise RuntimeError(f"{self.__class__.__name__} does not understand instruction {repr(cmd)}")
+                timed = prof is not None and type(cmd) in (ForwardPass, BackwardPass)
                 if not overlap:
+                    if timed:
+                        e0 = torch.cuda.Event(enable_timing=True)
+                        e0.record()
                     instruction_map[type(cmd)](**cmd.kwargs)
+                    if timed:
+                        e1 = torch.cuda.Event(enable_timing=True)
+                        e1.record()
+                        prof.append((type(cmd).__name__, e0, e1))
                     continue
                 b = cmd.kwargs.get("buffer_id")
                 if type(cmd) in forward_family:
                     with torch.cuda.stream(fwd):
                         if b in bwd_done:               # the previous occupant of this pipe buffer has been consumed
                             fwd.wait_event(bwd_done.pop(b))
+                        if timed:
+                            e0 = torch.cuda.Event(enable_timing=True)
+                            e0.record(fwd)
                         instruction_map[type(cmd)](**cmd.kwargs)
                         if type(cmd) is ForwardPass:
-                            fwd_done[b] = torch.cuda.Event()
+                            fwd_done[b] = torch.cuda.Event(enable_timing=timed)
                             fwd_done[b].record(fwd)
+                            if timed:
+                                prof.append(("ForwardPass", e0, fwd_done[b]))
                 else:
                     if type(cmd) in (BackwardPass, RecvGrad) and b in fwd_done:
                         main.wait_event(fwd_done.pop(b))
+                    if timed:
+                        e0 = torch.cuda.Event(enable_timing=True)
+                        e0.record(main)
                     instruction_map[type(cmd)](**cmd.kwargs)
                     if type(cmd) is BackwardPass:
-                        bwd_done[b] = torch.cuda.Event()
+                        bwd_done[b] = torch.cuda.Event(enable_timing=timed)
                         bwd_done[b].record(main)
+                        if timed:
+                            prof.append(("BackwardPass", e0, bwd_done[b]))
         if overlap:
             main.wait_stream(fwd)                       # losses, activations still in flight -> optimizer / caller
         for name, pipe_buffers in self.pipe_buffers.items():      # :483-485

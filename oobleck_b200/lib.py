@@ -68,6 +68,7 @@ _SIGNATURES = {
     "oob_version": (C.c_int, []),
     "oob_last_error": (C.c_char_p, []),
     "oob_launch_count": (C.c_long, []),
+    "oob_tensor_map_encodes": (C.c_long, []),
     "oob_gemm_timing_begin": (_I, []),
     "oob_gemm_timing_end": (_I, [C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_double),
                                  C.POINTER(C.c_long)]),

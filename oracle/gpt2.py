@@ -100,7 +100,7 @@ class BlockLayer(nn.Module):
         v = v.view(B, T, H, hd).transpose(1, 2)
         att = torch.matmul(q, k.transpose(-1, -2)) / (hd ** 0.5)
         causal = torch.tril(torch.ones(T, T, dtype=torch.bool, device=x.device))
-        att = torch.where(causal, att, torch.full([], torch.finfo(att.dtype).min, device=x.device))
+        att = torch.where(causal, att, torch.full([], torch.finfo(att.dtype).min, dtype=att.dtype, device=x.device))
         att = F.softmax(att, dim=-1)
         o = torch.matmul(att, v).transpose(1, 2).contiguous().view(B, T, E)
         a = torch.addmm(self.c_proj_b, o.view(-1, E), self.c_proj_w).view(B, T, E)

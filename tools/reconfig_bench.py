@@ -1,18 +1,28 @@
-"""Reconfiguration latency on real GPUs (the second half of BASELINE.json's metric).
+"""Reconfiguration latency after a REAL kill (the second half of BASELINE.json's metric; SURVEY 8d: "wall time from the
+lost-node message arriving on the worker pipe to the first completed post-reconfiguration train step").
 
-    python tools/reconfig_bench.py --gpus 4 --model gpt2          # 2 replicas x 2 stages, lose the last GPU
+    python bench.py --reconfig --gpus 8 --replicas 2 [--model gpt2-xl]      # or: python tools/reconfig_bench.py ...
 
-Scenario supported by the reference's semantics (SURVEY 7 hard part 5: a lone pipeline cannot survive a loss without a
-replica): `gpus/2` -stage replicas x 2; after 2 training steps the last rank leaves; the survivors run the reference's
-re-planning policy, rebuild pipelines (no world teardown), copy the moved layers from the surviving replica over NCCL,
-and train on.  Reported: seconds from the loss notification to (a) pipelines rebuilt + states copied, (b) first completed
-post-reconfiguration train step.
+This process plays the agent, with the reference's own fake-agent protocol (tests/execution/test_engine.py:650-657,
+1037-1053): it spawns one worker per GPU -- each runs exactly ``worker_main``'s call sequence (elastic/worker.py:23-34)
+on ``OobleckEngine(local_rank, num_nodes, 1, pipe, args)`` -- sends ``DistributionInfo`` down every pipe and re-broadcasts
+rank 0's TCPStore port.  When every worker has started training step ``--kill-step`` it SIGKILLs the worker of the last
+rank (mid-step: its pipeline neighbours are left spinning on NVLink flags, its data-parallel partners would wait in
+NCCL), then announces the lost IP to the survivors and re-broadcasts the port once more.
+
+The survivors' listener threads release the GPU (host-mapped abort words for the P2P kernels, ncclCommAbort for the
+communicators that contained the victim), the training threads drop the step in flight, re-plan with the reference's
+policy (2 x 4 stages -> 4 + 3), rebuild pipelines and links without touching the world group, receive the layers they
+now own (parameters + Adam moments) from the surviving replica, and train on.  Prints ONE JSON line.
 """
+from __future__ import annotations
+
 import argparse
 import json
 import os
-import socket
+import signal
 import sys
+import threading
 import time
 
 import torch
@@ -20,87 +30,172 @@ import torch.multiprocessing as mp
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
-from bench import MODELS  # noqa: E402
 
 
-def log(rank, msg, t0=[None]):
-    if t0[0] is None:
-        t0[0] = time.perf_counter()
-    print(f"[rank {rank} +{time.perf_counter() - t0[0]:7.2f}s] {msg}", file=sys.stderr, flush=True)
+def _ips(world):
+    return [f"127.0.0.{r + 1}" for r in range(world)]
 
 
-def worker(rank, world, port, model, q):
-    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world),
-                      LOCAL_RANK=str(rank))
-    import torch.distributed as dist
+def worker(rank, world, pipe, q, started, model, replicas, steps, kill_step):
+    from unittest.mock import patch
+    os.environ["TORCH_NCCL_ASYNC_ERROR_HANDLING"] = "0"   # a dead peer is handled by the engine, not by the NCCL watchdog
+    os.environ.setdefault("NCCL_DEBUG", "WARN")
+    os.environ.setdefault("OOB_P2P_TIMEOUT_S", "60")
+    try:
+        from bench import MODELS, VOCAB
+        from oobleck_b200.execution.dataloader import SyntheticTokenDataset
+        from oobleck_b200.execution.engine import (JobArguments, ModelArguments, OobleckArguments, OobleckEngine,
+                                                   layer_cost_model)
+        from oobleck_b200.execution.p2p import NvlinkRingTransport
+        from oobleck_b200.planning.pipeline_template import balanced_template
+        torch.cuda.set_device(rank)
+        ips = _ips(world)
+        patch("socket.gethostbyname", return_value=ips[rank]).start()      # one "node" per GPU (test_engine.py:676)
+        real_store = torch.distributed.TCPStore
+        patch("torch.distributed.TCPStore", lambda host_name, *a, **kw: real_store("127.0.0.1", *a, **kw)).start()
 
-    from oobleck_b200.execution.dataloader import SyntheticTokenDataset
-    from oobleck_b200.execution.engine import (JobArguments, ModelArguments, OobleckArguments, OobleckEngine,
-                                               layer_cost_model)
-    from oobleck_b200.execution.p2p import NvlinkRingTransport
-    from oobleck_b200.planning.pipeline_template import balanced_template
-    torch.cuda.set_device(rank)
-    cfg = MODELS[model]
-    ma = cfg["model_args"]
-    mb, gb = cfg["microbatch"], 16 * cfg["microbatch"]
-    args = OobleckArguments(job=JobArguments(microbatch_size=mb, global_microbatch_size=gb, steps=1),
-                            model=ModelArguments(model_name="gpt2", model_tag=model, model_args=dict(ma)))
-    ds = SyntheticTokenDataset(num_samples=4096, seq_len=ma["n_positions"], vocab_size=ma.get("vocab_size", 50257))
-    eng = OobleckEngine(rank, world, 1, None, args, dataset=ds, transport_cls=NvlinkRingTransport)
-    costs = layer_cost_model(eng._model, mb)
-    half = world // 2
-    eng._pipeline_templates = [balanced_template(costs, n) for n in range(1, half + 1)]
-    log(rank, "engine built")
-    eng.initialize_distributed("nccl")
-    eng.instantiate_pipelines(gb // mb, plan=[eng._pipeline_templates[-1]] * 2)
-    log(rank, "pipelines instantiated")
-    for i in range(2):
-        eng._train_step()
+        cfg = MODELS[model]
+        ma = dict(cfg["model_args"])
+        mb = cfg["microbatch"]
+        stages = world // replicas
+        gb = mb * 8 * world                 # 8 micro-batches per GPU and step: enough for a 1F1B steady state
+        oargs = OobleckArguments(job=JobArguments(microbatch_size=mb, global_microbatch_size=gb, steps=steps),
+                                 model=ModelArguments(model_name="gpt2", model_tag=model, model_args=ma))
+        ds = SyntheticTokenDataset(num_samples=max(2334, gb * (steps + 4)), seq_len=ma["n_positions"],
+                                   vocab_size=ma.get("vocab_size", VOCAB))
+        # worker_main: ctor -> initialize_distributed -> instantiate_pipelines -> train
+        eng = OobleckEngine(0, world, 1, pipe, oargs, dataset=ds, transport_cls=NvlinkRingTransport)
+        costs = layer_cost_model(eng._model, mb)
+        eng._pipeline_templates = [balanced_template(costs, n, 1) for n in range(1, world + 1)]
+        eng._templates_injected = True
+        eng.initialize_distributed()
+        plan_t = next(t for t in eng._pipeline_templates if t._num_nodes == stages)
+        eng.instantiate_pipelines(gb // mb, plan=[plan_t] * replicas)
+
+        orig = eng._guarded_train_step
+        count = {"n": 0}
+
+        def hook():
+            if count["n"] == kill_step:
+                started.put(rank)       # the agent kills the victim once everybody is inside this step
+            count["n"] += 1
+            return orig()
+        eng._guarded_train_step = hook
+        t_train0 = time.perf_counter()
+        eng.train()
         torch.cuda.synchronize()
-        log(rank, f"train step {i} done")
-    dist.barrier()
-    log(rank, "barrier passed; rank %d leaves now" % (world - 1))
-    lost = world - 1
-    if rank == lost:
-        q.put((rank, None))
-        time.sleep(20)   # keep the process (and its CUDA context / IPC exports) out of the way, like a dead node
-        return
-    t0 = time.perf_counter()
-    eng._reconfiguration.on_reconfigure([lost])
-    torch.cuda.synchronize()
-    t1 = time.perf_counter()
-    log(rank, f"reconfigured in {t1 - t0:.3f}s: {[p._ranks for p in eng._reconfiguration._pipelines]}")
-    eng._train_step()
-    torch.cuda.synchronize()
-    t2 = time.perf_counter()
-    log(rank, f"first post-reconfiguration step done at {t2 - t0:.3f}s")
-    q.put((rank, {"rebuild_s": t1 - t0, "first_step_done_s": t2 - t0,
-                  "new_ranks": [p._ranks for p in eng._reconfiguration._pipelines],
-                  "my_layers": len(eng._pipeline.execution._layers)}))
-    time.sleep(3)
+        rc = eng._reconfiguration
+        t_note = rc.last_notification_time
+        first_after = next((t for t in eng.step_end_times if t_note is not None and t > t_note), None)
+        # replicas of a layer must hold identical parameters after the move (bit for bit: same NCCL reduction on both)
+        sums = {l.layer_id: float(l.flat_param.double().sum()) for l in eng._pipeline.execution._layers}
+        q.put((rank, {
+            "pipelines": [p._ranks for p in rc._pipelines],
+            "notify_to_rebuilt_s": rc.last_reconfiguration_seconds,
+            "notify_to_first_step_s": (first_after - t_note) if first_after is not None else None,
+            "steps_completed": len(eng.step_seconds),
+            "step_s_before": eng.step_seconds[:kill_step], "step_s_after": eng.step_seconds[kill_step:],
+            "loss": float(eng._pipeline.execution.total_loss) if eng._pipeline.is_last_stage() else None,
+            "param_sums": sums, "train_wall_s": time.perf_counter() - t_train0}))
+    except Exception:  # noqa: BLE001
+        import traceback
+        q.put((rank, traceback.format_exc()))
+        raise
 
 
-def main():
-    ap = argparse.ArgumentParser()
-    ap.add_argument("--gpus", type=int, default=4)
-    ap.add_argument("--model", default="gpt2")
-    a = ap.parse_args()
-    with socket.socket() as s:
-        s.bind(("127.0.0.1", 0))
-        port = s.getsockname()[1]
+def main(args=None):
+    if args is None or not hasattr(args, "kill_step"):
+        ap = argparse.ArgumentParser()
+        ap.add_argument("--gpus", type=int, default=8)
+        ap.add_argument("--replicas", type=int, default=2)
+        ap.add_argument("--model", default="gpt2-xl")
+        ap.add_argument("--steps", type=int, default=5)
+        ap.add_argument("--kill-step", type=int, default=2)
+        ap.add_argument("--reconfig", action="store_true")
+        known, _ = ap.parse_known_args()
+        if args is not None:                      # called from bench.py: keep its --gpus / --replicas / --model / --steps
+            for k in ("gpus", "replicas", "model"):
+                setattr(known, k, getattr(args, k))
+            known.steps = max(getattr(args, "steps", 5), known.kill_step + 2)
+        args = known
+    from oobleck_b200.execution.engine import DistributionInfo
+    world = args.gpus
+    assert world % args.replicas == 0 and args.replicas >= 2, "a lost stage needs a surviving replica (SURVEY 7.5)"
+    victim = world - 1
+    ips = _ips(world)
     ctx = mp.get_context("spawn")
-    q = ctx.Queue()
-    procs = [ctx.Process(target=worker, args=(r, a.gpus, port, a.model, q)) for r in range(a.gpus)]
+    q, started = ctx.Queue(), ctx.Queue()
+    pipes = [ctx.Pipe(duplex=True) for _ in range(world)]
+    procs = [ctx.Process(target=worker, args=(r, world, pipes[r][1], q, started, args.model, args.replicas, args.steps,
+                                              args.kill_step)) for r in range(world)]
     for p in procs:
         p.start()
-    res = dict(q.get(timeout=240) for _ in range(a.gpus))
-    for p in procs:
+    marks = {}
+
+    def rebroadcast(ps):
+        port = ps[0][0].recv()
+        for pipe, _ in ps:
+            pipe.send(port)
+
+    def agent():
+        for pipe, _ in pipes:
+            pipe.send(DistributionInfo(list(ips), world))
+        rebroadcast(pipes)
+        for _ in range(world):
+            started.get(timeout=1800)
+        time.sleep(0.3)                                   # let the step get going: kill lands mid-step
+        marks["kill"] = time.perf_counter()
+        os.kill(procs[victim].pid, signal.SIGKILL)
+        procs[victim].join(timeout=30)
+        marks["announce"] = time.perf_counter()
+        survivors = [p for i, p in enumerate(pipes) if i != victim]
+        for pipe, _ in survivors:
+            pipe.send(ips[victim])
+        rebroadcast(survivors)
+
+    t = threading.Thread(target=agent, daemon=True)
+    t.start()
+    results = {}
+    for _ in range(world - 1):
+        r = q.get(timeout=3000)
+        results[r[0]] = r[1]
+    t.join(timeout=60)
+    for i, p in enumerate(procs):
         p.join(timeout=60)
-    alive = {k: v for k, v in res.items() if v}
-    print(json.dumps({"metric": "reconfiguration_latency_s", "model": a.model, "gpus": a.gpus,
-                      "rebuild_s_max": max(v["rebuild_s"] for v in alive.values()),
-                      "first_step_done_s_max": max(v["first_step_done_s"] for v in alive.values()),
-                      "new_ranks": next(iter(alive.values()))["new_ranks"], "per_rank": alive}))
+    errors = {r: v for r, v in results.items() if isinstance(v, str)}
+    if errors:
+        print(json.dumps({"metric": "reconfiguration_latency_s", "error": errors}), flush=True)
+        sys.exit(1)
+    worst_first = max(v["notify_to_first_step_s"] for v in results.values())
+    worst_rebuilt = max(v["notify_to_rebuilt_s"] for v in results.values())
+    # consistency: every replica of a layer ends with the same parameter checksum
+    by_layer = {}
+    for v in results.values():
+        for lid, s in v["param_sums"].items():
+            by_layer.setdefault(lid, set()).add(s)
+    out = {
+        "metric": "reconfiguration_latency_s", "value": worst_first, "unit": "s", "higher_is_better": False,
+        "n_gpus": world, "definition": "lost-node message received on the worker pipe -> first completed "
+                                       "post-reconfiguration train step, max over the survivors (SURVEY 8d)",
+        "config": {"workload": f"{args.model}: {args.replicas} replicas x {world // args.replicas} stages, rank {victim} "
+                               f"SIGKILLed inside training step {args.kill_step}", "model": args.model},
+        "notify_to_pipelines_rebuilt_and_states_copied_s": worst_rebuilt,
+        "agent_kill_to_announce_s": marks["announce"] - marks["kill"],
+        "pipelines_after": next(iter(results.values()))["pipelines"],
+        "step_s_before": statistics_of([x for v in results.values() for x in v["step_s_before"][1:]]),
+        "step_s_after": statistics_of([x for v in results.values() for x in v["step_s_after"][1:]]),
+        "replicas_identical_after": all(len(s) == 1 for s in by_layer.values()),
+        "per_rank": {str(r): {k: v[k] for k in ("notify_to_rebuilt_s", "notify_to_first_step_s", "steps_completed")}
+                     for r, v in sorted(results.items())},
+    }
+    print(json.dumps(out), flush=True)
+
+
+def statistics_of(xs):
+    if not xs:
+        return None
+    xs = sorted(xs)
+    return {"median": xs[len(xs) // 2], "max": xs[-1], "n": len(xs)}
 
 
 if __name__ == "__main__":
