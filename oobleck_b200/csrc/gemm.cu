@@ -132,12 +132,13 @@ static int launchp_t(const CUtensorMap& ta, const CUtensorMap& tb, const GemmPar
   }
   GemmParams p = p_in;
   const int stage = gemmp_stage_bytes<BN, TWO_CTA, BK>(p.nsplit);
-  // epilogue transposition tiles: 4 warps x 32 rows x slab fp32; 32-column slabs (full 128-B lines per store) unless
-  // they would cost a ring stage
-  int overhead = 1024 + 256 + 4 * 32 * 32 * 4;
+  // epilogue transposition tiles: one per epilogue warp, 32 rows x slab fp32; 32-column slabs (full 128-B lines per
+  // store) unless they would cost a ring stage
+  constexpr int EPI_WARPS = 4 * GEMM_EPI_GROUPS;
+  int overhead = 1024 + 256 + EPI_WARPS * 32 * 32 * 4;
   p.slab = 32;
-  if ((max_smem - overhead) / stage < (max_smem - (overhead - 4 * 32 * 16 * 4)) / stage) {
-    overhead -= 4 * 32 * 16 * 4;
+  if ((max_smem - overhead) / stage < (max_smem - (overhead - EPI_WARPS * 32 * 16 * 4)) / stage) {
+    overhead -= EPI_WARPS * 32 * 16 * 4;
     p.slab = 16;
   }
   int stages = (max_smem - overhead) / stage;

@@ -58,7 +58,12 @@ struct GemmParams {
 };
 
 constexpr int GEMM_BM = 128;
-constexpr int GEMM_THREADS = 192;
+// warp 0 producer, warp 1 MMA, then GEMM_EPI_GROUPS x 4 epilogue warps: each group of 4 covers the 128 TMEM lanes
+// (a warp may only touch lanes 32 * (warp % 4) ..) and takes BN / GEMM_EPI_GROUPS of the tile's columns.  Round 1 ran one
+// group: 1.5 eligible warps per scheduler, "No Eligible" 76 % of the cycles, the fused epilogues cost as much as the
+// whole main loop (profiles/r01_ncu_gemm_fwdfc_v5.txt, r01_gemm_sweep12_compact_epilogue.log).
+constexpr int GEMM_EPI_GROUPS = 2;
+constexpr int GEMM_THREADS = 64 + 128 * GEMM_EPI_GROUPS;
 
 // K-block geometry.  One smem row holds BK contraction elements (K-major) or BK output elements (MN-major) and is
 // exactly one swizzle span: BK = 64 -> 128 B rows / SWIZZLE_128B, BK = 32 -> 64 B rows / SWIZZLE_64B (half-size

@@ -35,7 +35,7 @@ gemm_bf16x3_persistent_kernel(const __grid_constant__ CUtensorMap tma_a, const _
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   // after the ring: one transposition tile per epilogue warp (32 rows x p.slab fp32), then the barriers
   float* stage_out = reinterpret_cast<float*>(smem + (size_t)num_stages * stage_bytes);
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(stage_out + 4 * 32 * p.slab);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(stage_out + 4 * GEMM_EPI_GROUPS * 32 * p.slab);
   uint64_t* empty_bar = full_bar + num_stages;
   uint64_t* tmem_full_bar = empty_bar + num_stages;   // [2] chunk accumulator ready
   uint64_t* tmem_empty_bar = tmem_full_bar + 2;        // [2] chunk accumulator drained
@@ -55,7 +55,8 @@ gemm_bf16x3_persistent_kernel(const __grid_constant__ CUtensorMap tma_a, const _
   const int chunk_kb = p.chunk_kb > 0 ? p.chunk_kb : GEMM_CHUNK_ELEMS / BK;
   const int num_chunks = (num_kb + chunk_kb - 1) / chunk_kb;
   constexpr uint32_t TMEM_COLS = 512;
-  constexpr uint32_t kEpiArrivals = TWO_CTA ? 8 : 4;
+  constexpr uint32_t kEpiArrivals = (TWO_CTA ? 8 : 4) * GEMM_EPI_GROUPS;
+  constexpr int CG = BN / GEMM_EPI_GROUPS;            // columns per epilogue warp
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tma_a);
@@ -182,26 +183,26 @@ gemm_bf16x3_persistent_kernel(const __grid_constant__ CUtensorMap tma_a, const _
       }
     }
   } else {
-    // ===================== epilogue (warps 2..5) =====================
+    // ===================== epilogue (warps 2 ..) =====================
     const int quarter = warp & 3;
+    const int cgrp = (warp - 2) >> 2;                    // which CG-column slice of the tile this warp owns
     const bool has_corr = nsplit > 1;
-    const uint32_t t_lane = tmem_base + ((uint32_t)(quarter * 32) << 16);
+    const uint32_t t_lane = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(cgrp * CG);
     int gc = 0, ti = 0;
     for (int t = unit; t < num_tiles; t += num_units, ++ti) {
       const int m0 = (t % tiles_m) * TILE_M + (int)rank * GEMM_BM;
-      const int n0 = (t / tiles_m) * BN;
-      const int row = m0 + quarter * 32 + lane;
+      const int n0 = (t / tiles_m) * BN + cgrp * CG;
       const int cb = ti & 1;
-      float racc[BN];
+      float racc[CG];
 #pragma unroll
-      for (int j = 0; j < BN; ++j) racc[j] = 0.f;
+      for (int j = 0; j < CG; ++j) racc[j] = 0.f;
       for (int c = 0; c < num_chunks; ++c, ++gc) {
         const int buf = gc & 1;
         mbar_wait(&tmem_full_bar[buf], (gc >> 1) & 1);
         tc_fence_after();
         const bool last_chunk = (c == num_chunks - 1);
 #pragma unroll
-        for (int g = 0; g < BN / 32; ++g) {
+        for (int g = 0; g < CG / 32; ++g) {
           uint32_t v[32];
           tmem_ld_32x32(t_lane + (uint32_t)(buf * BN + g * 32), v);
           tmem_ld_wait();
@@ -232,11 +233,11 @@ gemm_bf16x3_persistent_kernel(const __grid_constant__ CUtensorMap tma_a, const _
         const int row0 = m0 + quarter * 32;
         if (p.slab == 32) {
 #pragma unroll
-          for (int g = 0; g < BN / 32; ++g)
+          for (int g = 0; g < CG / 32; ++g)
             if (n0 + g * 32 < p.N) epilogue_slab<32>(&racc[g * 32], my_stage, p.epi, row0, n0 + g * 32, p.M, p.N, lane);
         } else {
 #pragma unroll
-          for (int g = 0; g < BN / 16; ++g)
+          for (int g = 0; g < CG / 16; ++g)
             if (n0 + g * 16 < p.N) epilogue_slab<16>(&racc[g * 16], my_stage, p.epi, row0, n0 + g * 16, p.M, p.N, lane);
         }
       }

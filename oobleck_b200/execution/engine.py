@@ -147,6 +147,9 @@ class DataParallelEngine:
                 for fsdp_index, rank in enumerate(ranks):
                     ranks_grid[layer_index].setdefault(fsdp_index, []).append(rank)
         self._ranks_grid = ranks_grid
+        self._comm_stream = None
+        self._pending: list = []
+        self._overlapped: set[int] = set()
         # One communicator per DISTINCT rank set, created in first-use order (identical on every rank).  The reference
         # calls new_group once per (layer, fsdp_index) (:390-392); the mapping below is otherwise the same.
         my_rank = _rank()
@@ -213,13 +216,46 @@ class DataParallelEngine:
                     return False
         return agreed
 
+    def _groups_of(self, layer):
+        process_groups = {fi: pg for fi, pg in self._dp_process_groups[layer.layer_id].items() if pg.rank_index() >= 0}
+        if process_groups and any(pg.size() > 1 for pg in process_groups.values()):
+            return process_groups
+        return None
+
+    def layer_ready(self, layer):
+        """Hook of ``PipelineExecution.backward_pass`` for the step's last micro-batch (non-elastic CUDA runs): the
+        layer's gradient is complete once this backward and its side-stream weight-gradient kernels have run, so its
+        SUM all-reduce starts now on the communication stream and overlaps the backward of the layers before it and
+        the pipeline flush.  (The reference reduces layer by layer after the whole step, blocking:
+        engine.py:404-412, layer.py:290-291.)  One bucket per layer: the flat gradient is already contiguous."""
+        pgs = self._groups_of(layer)
+        if pgs is None:
+            return
+        import ctypes as C
+
+        from .. import lib as L
+        if self._comm_stream is None:
+            self._comm_stream = torch.cuda.Stream()
+        cs = self._comm_stream
+        cs.wait_stream(torch.cuda.current_stream())
+        L.call("oob_side_join", C.c_void_p(cs.cuda_stream))     # this layer's wgrad / bias-sum kernels
+        with torch.cuda.stream(cs):
+            self._pending.extend(layer.reduce_gradients(pgs, async_op=True))
+        self._overlapped.add(layer.layer_id)
+
     def do_allreduce(self):
-        """engine.py:404-412: every local layer reduces over the groups that contain this rank."""
+        """engine.py:404-412: every local layer reduces over the groups that contain this rank (SUM, never averaged).
+        Layers whose reduction was started early by ``layer_ready`` are only waited for."""
         for layer in self.engine._pipeline.execution._layers:
-            process_groups = {fi: pg for fi, pg in self._dp_process_groups[layer.layer_id].items()
-                              if pg.rank_index() >= 0}
-            if process_groups and any(pg.size() > 1 for pg in process_groups.values()):
-                layer.reduce_gradients(process_groups)
+            if layer.layer_id in self._overlapped:
+                continue
+            pgs = self._groups_of(layer)
+            if pgs is not None:
+                layer.reduce_gradients(pgs)
+        for w in self._pending:
+            w.wait()                          # the compute stream waits for the NCCL stream; the host does not block
+        self._pending.clear()
+        self._overlapped.clear()
 
 
 # ---- reconfiguration -----------------------------------------------------------------------------------------------
@@ -384,6 +420,7 @@ class ReconfigurationEngine:
             if all(layer is not l for l in new_pipeline.execution._layers):
                 layer.remove_tensors()
         self.engine._pipeline = new_pipeline
+        self.engine._install_dp_overlap()
 
     # -- mechanism ---------------------------------------------------------------------------------------------------
     def _reinstantiate(self, num_instances_set, new_ranks_list) -> OobleckPipeline:
@@ -628,6 +665,15 @@ class OobleckEngine:
                 pass
 
     # -- planning stand-ins ------------------------------------------------------------------------------------------
+    def _install_dp_overlap(self):
+        """Overlapped all-reduce only where it is safe: CUDA layers, replicas exist, and no agent pipe (an elastic step
+        must not exchange gradients before its vote -- ``_guarded_train_step``)."""
+        ex = self._pipeline.execution
+        overlap = (self._agent_pipe is None and self._pipeline.device.type == "cuda"
+                   and os.environ.get("OOB_DP_OVERLAP", "1") == "1"
+                   and any(self._dp_engine._groups_of(l) is not None for l in ex._layers))
+        ex.grad_ready_hook = self._dp_engine.layer_ready if overlap else None
+
     def distribute_microbatches(self, templates: list[PipelineTemplate], global_num_microbatch: int) -> list[int]:
         """Integer stand-in for ``PipelineInstantiator._distribute_batch`` (instantiator.py:254-329, pyomo MINLP,
         control plane): proportional to each pipeline's GPU count, remainder to the largest pipelines first."""
@@ -684,6 +730,7 @@ class OobleckEngine:
         self._pipeline.initialize_execution(self._model)
         assert self._pipeline.communication is not None and self._pipeline.execution is not None
         self._dp_engine = DataParallelEngine(self, pipelines)
+        self._install_dp_overlap()
         self._reconfiguration = ReconfigurationEngine(self, pipelines)
         self._step_aborted = False
 

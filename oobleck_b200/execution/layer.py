@@ -363,9 +363,14 @@ class Layer:
         return None
 
     # -- data parallel -----------------------------------------------------------------------------------------------
-    def reduce_gradients(self, process_groups: dict) -> None:
+    def reduce_gradients(self, process_groups: dict, async_op: bool = False):
         """layer.py:272-291: SUM all-reduce of the flat gradient over the cross-replica group(s); never averaged.
-        With one GPU per stage there is exactly one (fsdp_index -> group) entry."""
+        With one GPU per stage there is exactly one (fsdp_index -> group) entry.  ``async_op``: return the NCCL work
+        handles instead of waiting (the caller overlaps the reduction with the rest of the backward pass)."""
         assert len(process_groups) == 1, "sharded DP groups need the FSDP path (out of scope this round)"
+        works = []
         for _, pg in process_groups.items():
-            torch.distributed.all_reduce(self.flat_grad, group=getattr(pg, "group", pg))
+            w = torch.distributed.all_reduce(self.flat_grad, group=getattr(pg, "group", pg), async_op=async_op)
+            if async_op:
+                works.append(w)
+        return works

@@ -116,6 +116,8 @@ class PipelineExecution:
         self._training_args = training_args
         self._loss: torch.Tensor | None = None       # loss of the micro-batch being processed
         self.total_loss: torch.Tensor | None = None  # running sum over micro-batches (never reset, :196-201)
+        self._bwd_seen = 0                           # backward passes so far in this step
+        self.grad_ready_hook = None                  # DataParallelEngine.layer_ready when replicas exist
 
         optimizer_cls, scheduler_cls = pipeline._optimizer_factory()
         self._optimizer = optimizer_cls(
@@ -184,8 +186,14 @@ class PipelineExecution:
             grad_tensors = self.pipeline.communication.grad_recv_buf
             assert len(output_tensors) == len(grad_tensors)      # pipeline.py:233
             grad = HiddenGrad(grad_tensors[0])
+        # the step's LAST micro-batch: a layer's accumulated gradient is final as soon as its backward is enqueued, so
+        # the data-parallel engine may start that layer's all-reduce under the backward of the layers before it
+        self._bwd_seen = getattr(self, "_bwd_seen", 0) + 1
+        hook = self.grad_ready_hook if self._bwd_seen == self.pipeline.train_schedule.micro_batches else None
         for layer in reversed(self._layers):
             grad = layer.backward(buffer_id, grad)
+            if hook is not None:
+                hook(layer)
         ws = getattr(self._layers[0], "workspace", None)
         if ws is not None and hasattr(ws, "join"):
             ws.join()     # weight-gradient kernels run on a side stream; the ctx slot is recycled after this pass
@@ -410,6 +418,7 @@ class OobleckPipeline:
             fwd_done: dict[int, torch.cuda.Event] = {}
             bwd_done: dict[int, torch.cuda.Event] = {}
         forward_family = (LoadMicroBatch, RecvActivation, ForwardPass, SendActivation)
+        self.execution._bwd_seen = 0
         for step_cmds in self.train_schedule:
             for cmd in step_cmds:
                 if type(cmd) not in instruction_map:

