@@ -27,7 +27,7 @@ AGENT_IPS = ["127.0.0.1", "127.0.0.2", "127.0.0.3", "127.0.0.4"]
 M, MB, STEPS_BEFORE, STEPS_TOTAL = 4, 1, 2, 4
 
 
-def worker(rank, pipe, q, ready):
+def worker(rank, pipe, q, ready, mode):
     torch.set_num_threads(1)
     try:
         from oracle_layer import OracleLayer
@@ -46,14 +46,19 @@ def worker(rank, pipe, q, ready):
         args = OobleckArguments(job=JobArguments(microbatch_size=MB, global_microbatch_size=MB * M, steps=STEPS_TOTAL),
                                 model=ModelArguments(model_name="gpt2", model_tag="t", model_args=dict(MARGS)))
         ds = SyntheticTokenDataset(num_samples=256, seq_len=32, vocab_size=211, pin_memory=False)
-        templates = [even_template(4, 1), even_template(4, 2)]
+        if mode == "replicas":
+            templates = [even_template(4, 1), even_template(4, 2)]
+            plan = [templates[1], templates[1]]                              # ranks [0, 1] and [2, 3]
+        else:   # one 4-stage pipeline without a replica: survives through the peer shadows (BASELINE config 5 shape)
+            templates = [even_template(4, 3), even_template(4, 4)]
+            plan = [templates[1]]
         # worker_main's call sequence: ctor(local_rank, num_nodes, gpus_per_node, pipe, args) -> initialize_distributed
         # -> instantiate_pipelines -> train
         eng = OobleckEngine(0, len(AGENT_IPS), 1, pipe, args, dataset=ds, layer_cls=OracleLayer, templates=templates,
-                            backend="gloo", comm_timeout_s=20)
+                            backend="gloo", comm_timeout_s=20, peer_shadow=(mode == "lone"))
         eng.initialize_distributed()
         assert eng._rank == rank and eng._world_size == 4 and eng._rank_map[AGENT_IPS[rank]] == [rank]
-        eng.instantiate_pipelines(M, plan=[templates[1], templates[1]])      # ranks [0, 1] and [2, 3]
+        eng.instantiate_pipelines(M, plan=plan)
         assert eng._reconfiguration._reconfiguration_listener is not None    # engine.py:50-53
 
         orig_step = eng._guarded_train_step
@@ -72,10 +77,11 @@ def worker(rank, pipe, q, ready):
         eng.train()
 
         new_ranks = [p._ranks for p in eng._reconfiguration._pipelines]
-        assert new_ranks == [[2], [0, 1]], new_ranks
+        assert new_ranks == ([[2], [0, 1]] if mode == "replicas" else [[0, 1, 2]]), new_ranks
         assert eng._dist_info.agent_ips == AGENT_IPS[:3] and eng._dist_info.world_size == 3
         layers = eng._pipeline.execution._layers
-        assert sorted(l.layer_id for l in layers) == {0: [0, 1], 1: [2, 3], 2: [0, 1, 2, 3]}[rank]
+        want = {0: [0, 1], 1: [2, 3], 2: [0, 1, 2, 3]} if mode == "replicas" else {0: [0, 1], 1: [2], 2: [3]}
+        assert sorted(l.layer_id for l in layers) == want[rank]
         out = {l.layer_id: (l.flat_param.numpy().copy(), l.exp_avg.numpy().copy(), l.opt_step) for l in layers}
         q.put((rank, out, eng._reconfiguration.last_reconfiguration_seconds, len(eng.step_seconds)))
     except Exception:  # noqa: BLE001
@@ -120,12 +126,17 @@ def never_failed_reference():
 
 
 @pytest.mark.timeout(600)
-def test_engine_driven_through_agent_pipe_survives_a_dead_node():
+@pytest.mark.parametrize("mode", ["replicas", "lone"])
+def test_engine_driven_through_agent_pipe_survives_a_dead_node(mode):
+    """``lone``: the same death in a single 4-stage pipeline.  The reference raises "No alive ranks for the layer"
+    (engine.py:263-269, its test at tests/execution/test_engine.py:1015-1019); with peer shadows the survivors re-split
+    into 3 stages -- layers 1 and 2 move between survivors, layer 3 (parameters AND Adam moments) comes out of the mirror
+    its neighbour kept -- and the run still matches the never-failed oracle."""
     from oobleck_b200.execution.engine import DistributionInfo
     ctx = mp.get_context("spawn")
     q, ready = ctx.Queue(), ctx.Queue()
     pipes = [ctx.Pipe(duplex=True) for _ in AGENT_IPS]
-    procs = [ctx.Process(target=worker, args=(r, pipes[r][1], q, ready)) for r in range(4)]
+    procs = [ctx.Process(target=worker, args=(r, pipes[r][1], q, ready, mode)) for r in range(4)]
     for p in procs:
         p.start()
 

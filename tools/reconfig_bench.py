@@ -13,7 +13,10 @@ NCCL), then announces the lost IP to the survivors and re-broadcasts the port on
 The survivors' listener threads release the GPU (host-mapped abort words for the P2P kernels, ncclCommAbort for the
 communicators that contained the victim), the training threads drop the step in flight, re-plan with the reference's
 policy (2 x 4 stages -> 4 + 3), rebuild pipelines and links without touching the world group, receive the layers they
-now own (parameters + Adam moments) from the surviving replica, and train on.  Prints ONE JSON line.
+now own (parameters + Adam moments) from the surviving replica, and train on.  With ``--replicas 1`` (BASELINE config 5:
+one 8-stage pipeline -> the 7-stage template) there is no replica: the stage state comes from the peer shadows
+(``PeerShadow``: every stage mirrors its successor's parameters and moments over NVLink after each step).
+Prints ONE JSON line.
 """
 from __future__ import annotations
 
@@ -64,7 +67,8 @@ def worker(rank, world, pipe, q, started, model, replicas, steps, kill_step):
         ds = SyntheticTokenDataset(num_samples=max(2334, gb * (steps + 4)), seq_len=ma["n_positions"],
                                    vocab_size=ma.get("vocab_size", VOCAB))
         # worker_main: ctor -> initialize_distributed -> instantiate_pipelines -> train
-        eng = OobleckEngine(0, world, 1, pipe, oargs, dataset=ds, transport_cls=NvlinkRingTransport)
+        eng = OobleckEngine(0, world, 1, pipe, oargs, dataset=ds, transport_cls=NvlinkRingTransport,
+                            peer_shadow=(replicas == 1))   # a lone pipeline survives through its neighbours' mirrors
         costs = layer_cost_model(eng._model, mb)
         eng._pipeline_templates = [balanced_template(costs, n, 1) for n in range(1, world + 1)]
         eng._templates_injected = True
@@ -120,7 +124,8 @@ def main(args=None):
         args = known
     from oobleck_b200.execution.engine import DistributionInfo
     world = args.gpus
-    assert world % args.replicas == 0 and args.replicas >= 2, "a lost stage needs a surviving replica (SURVEY 7.5)"
+    assert world % args.replicas == 0 and world // args.replicas >= 1
+    assert args.replicas >= 2 or world >= 3, "a lone pipeline needs >= 3 stages to lose one and keep a mirror"
     victim = world - 1
     ips = _ips(world)
     ctx = mp.get_context("spawn")
