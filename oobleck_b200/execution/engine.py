@@ -183,44 +183,21 @@ class DataParallelEngine:
     def engine(self):
         return self._engine()
 
-    def vote(self, ok: bool, device, lost: set[int], aborted) -> bool:
-        """Elastic runs only: the commit point of a step.  Before any gradient is exchanged every rank tells its
-        cross-replica partners whether its own pipeline finished this step's micro-batches and no loss notification is
-        pending (MIN all-reduce of one flag per distinct communicator; every rank votes exactly once per step, so
-        nobody waits for a partner that will not come).  One 0 anywhere and every replica drops the step -- instead
-        of waiting in a gradient all-reduce for a partner whose pipeline was cut short, or reducing with its half-built
-        gradients.  Communicators that contain a rank this process already knows is lost are skipped; a partner that is
-        dead without our knowing makes the vote itself fail (gloo: peer reset; NCCL: the listener aborts that
-        communicator), which also counts as 0."""
-        groups = []
-        for per_layer in self._dp_process_groups.values():
-            for pg in per_layer.values():
-                if pg.rank_index() >= 0 and pg.size() > 1 and pg.group is not None and pg.group not in groups \
-                        and not (lost & set(pg.ranks)):
-                    groups.append(pg.group)
-        if not groups:
-            return ok
-        flag = torch.tensor([1 if ok else 0], dtype=torch.int32, device=device)
-        for g in groups:
-            if flag.device.type == "cpu":
-                run_interruptible(lambda g=g: dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=g), aborted)
-            else:
-                dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=g)
-        agreed = bool(flag.item())    # device -> host read: the only synchronisation an elastic step adds
-        # an all-reduce released by ncclCommAbort leaves garbage behind: a communicator that turned out to contain a
-        # lost rank while we were waiting cannot have produced a vote
-        lost_now = set(self.engine._lost_ranks)
-        for per_layer in self._dp_process_groups.values():
-            for pg in per_layer.values():
-                if pg.group in groups and lost_now & set(pg.ranks):
-                    return False
-        return agreed
-
     def _groups_of(self, layer):
         process_groups = {fi: pg for fi, pg in self._dp_process_groups[layer.layer_id].items() if pg.rank_index() >= 0}
         if process_groups and any(pg.size() > 1 for pg in process_groups.values()):
             return process_groups
         return None
+
+    def touches(self, ranks: set[int]) -> bool:
+        """Does any communicator this rank reduces gradients over contain one of ``ranks``?"""
+        if not ranks:
+            return False
+        for layer in self.engine._pipeline.execution._layers:
+            for pg in (self._groups_of(layer) or {}).values():
+                if ranks & set(pg.ranks):
+                    return True
+        return False
 
     def layer_ready(self, layer):
         """Hook of ``PipelineExecution.backward_pass`` for the step's last micro-batch (non-elastic CUDA runs): the
@@ -489,6 +466,7 @@ class ReconfigurationEngine:
                 layer.remove_tensors()
         self.engine._pipeline = new_pipeline
         self.engine._install_dp_overlap()
+        self.engine._make_job_group()
         if self.engine._peer_shadow:
             self.engine._shadow = PeerShadow(self.engine, new_pipeline)
             self.engine._shadow.refresh()
@@ -670,6 +648,8 @@ class OobleckEngine:
         self._store_port: int | None = None
         self._reconfigured = False
         self._lost_ranks: set[int] = set()
+        self._job_group = None
+        self._job_ranks: list[int] = []
         self._notified = False           # a loss notification has arrived and has not been applied yet
         self._args = args
         self._hf_training_args = TrainingArguments(per_device_train_batch_size=args.job.microbatch_size,
@@ -868,6 +848,7 @@ class OobleckEngine:
         self._install_dp_overlap()
         self._reconfiguration = ReconfigurationEngine(self, pipelines)
         self._step_aborted = False
+        self._make_job_group()
         self._shadow = PeerShadow(self, self._pipeline) if self._peer_shadow and dist.is_initialized() else None
         if self._shadow is not None:
             self._shadow.refresh()          # step-0 state: a rank may be lost before the first optimizer step
@@ -884,40 +865,54 @@ class OobleckEngine:
     def _guarded_train_step(self) -> bool:
         """One ``_train_step`` that survives the loss of a peer (elastic runs: an agent pipe exists).
 
-            1. unless a loss notification is already pending: run the pipeline's micro-batches; a transport abort or a
-               torch.distributed error on a dead neighbour marks the attempt as failed instead of propagating;
-            2. vote (``DataParallelEngine.vote``): the step is committed only if every replica finished and nobody has
-               a notification pending;
-            3. committed: gradient all-reduce + optimizer, exactly ``_train_step``.
-               dropped : gradients are zeroed, the queued reconfiguration is applied (waiting for the agent's message if
-               the failure was noticed first), and the caller runs the step again on the new pipelines.
+            1. unless a loss notification is already pending: run the pipeline's micro-batches, then drain the device;
+               a wait on a neighbour that gave up (``transport.aborted()``: the peer is lost, or dropped the step) or a
+               torch.distributed error marks the attempt as failed instead of propagating;
+            2. vote: ONE MIN all-reduce of that flag over every rank of the job (``_job_group``).  The step is committed
+               only if every rank finished its micro-batches and nobody has a notification pending; a dead rank makes
+               the vote itself fail for everybody (gloo: peer reset; NCCL: released by the listener's abort).  Either
+               all surviving ranks commit the step or all of them drop it;
+            3. committed: gradient all-reduce + optimizer, exactly ``_train_step`` (+ the peer-shadow refresh).
+               dropped  : gradients are zeroed, the queued reconfiguration is applied (waiting for the agent's message
+               if the failure was noticed first), and the caller runs the step again on the new pipelines.
 
         Parameters are only written by ``optimizer_step``, the last action of a committed step, so a dropped step leaves
         the model exactly as the previous step left it.  Returns False for a dropped step."""
         if self._agent_pipe is None:
             self._train_step()
             return True
+        on_gpu = torch.cuda.is_available() and self._pipeline.device.type == "cuda"
         failure: Exception | None = None
         ok = not self._notified
         global_step = self._pipeline._global_step
         if ok:
             try:
                 self._pipeline.train()
+                if on_gpu:
+                    torch.cuda.synchronize()      # every wait of this step has either seen its data or given up
                 transport = getattr(self._pipeline.communication, "transport", None)
                 if transport is not None and hasattr(transport, "aborted") and transport.aborted():
-                    raise PipelineAborted("an inter-stage link was aborted")
+                    raise PipelineAborted("an inter-stage transfer was abandoned")
             except (PipelineAborted, RuntimeError) as e:
                 ok, failure = False, e
         _dbg(f"step: pipeline ok={ok} failure={type(failure).__name__ if failure else None}; voting")
         try:
-            agreed = self._dp_engine.vote(ok, self._pipeline.device, set(self._lost_ranks), lambda: False)
+            agreed = self._vote(ok)
         except (PipelineAborted, RuntimeError) as e:
             _dbg(f"step: vote failed: {str(e)[:120]}")
             agreed = False
         _dbg(f"step: agreed={agreed}")
         if agreed:
-            self._dp_engine.do_allreduce()
-            self._pipeline.execution.optimizer_step()
+            try:
+                self._dp_engine.do_allreduce()
+                if on_gpu:
+                    torch.cuda.synchronize()
+                if self._dp_engine.touches(self._lost_ranks):
+                    raise PipelineAborted("a gradient all-reduce ran into a lost rank")   # never apply its output
+                self._pipeline.execution.optimizer_step()
+            except (PipelineAborted, RuntimeError) as e:
+                agreed, failure = False, e
+        if agreed:
             if self._shadow is not None:
                 try:
                     self._shadow.refresh()
@@ -927,13 +922,43 @@ class OobleckEngine:
         self._pipeline._global_step = global_step      # the dropped step never happened
         try:
             self._pipeline.execution._optimizer.zero_grad()
-            if torch.cuda.is_available() and self._pipeline.device.type == "cuda":
+            if on_gpu:
                 torch.cuda.synchronize()
         except RuntimeError:
             pass                      # a poisoned stream: everything on it is rebuilt below anyway
         if not self._reconfiguration.poll() and not self._wait_for_notification():
             raise failure if failure is not None else PipelineAborted("step dropped but no loss was announced")
         return False
+
+    def _make_job_group(self):
+        """Elastic runs: the communicator of the per-step vote -- every rank that currently trains."""
+        self._job_ranks = sorted(r for p in self._reconfiguration._pipelines for r in p._ranks)
+        self._job_group = None
+        if self._agent_pipe is None or not dist.is_initialized() or len(self._job_ranks) <= 1:
+            return
+        key = tuple(self._job_ranks)
+        if key not in _COMMUNICATORS:
+            _COMMUNICATORS[key] = _new_member_group(key, self._comm_timeout)
+        self._job_group = _COMMUNICATORS[key]
+
+    def _vote(self, ok: bool) -> bool:
+        if self._job_group is None:
+            return ok
+        device = self._pipeline.device
+        flag = torch.tensor([1 if ok else 0], dtype=torch.int32, device=device)
+        if device.type == "cpu":
+            # gloo cannot abort a collective: once the listener has announced a loss this rank stops waiting for partners
+            # that left the vote (NCCL: the listener aborts the communicator instead)
+            run_interruptible(lambda: dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=self._job_group),
+                              lambda: self._notified)
+        else:
+            dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=self._job_group)
+        agreed = bool(flag.item())
+        # an all-reduce released by ncclCommAbort leaves garbage behind: a communicator that turned out to contain a
+        # lost rank while we were waiting cannot have produced a vote
+        if self._lost_ranks & set(self._job_ranks):
+            return False
+        return agreed
 
     def _wait_for_notification(self, timeout: float = 60.0) -> bool:
         """A failure was noticed before the agent's lost-node message arrived: wait for the listener to queue it, then

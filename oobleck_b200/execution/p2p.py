@@ -161,9 +161,9 @@ class NvlinkRingTransport(DistTransport):
                 L.load().oob_p2p_abort(link.mine, None)
 
     def aborted(self) -> bool:
-        """Host-side read of the mailboxes' control words: did any wait of this transport give up?"""
-        if self._abort:
-            return True
+        """Host-side read of the mailboxes' control words: did any wait of this transport really give up (abort request
+        honoured, or watchdog)?  Call it after the device has drained.  A bare abort request with no kernel waiting is
+        not a fault: the data of the step is complete."""
         st = C.c_int(0)
         for link in list(self.links.values()):
             if link.mine and L.load().oob_p2p_status(link.mine, C.byref(st)) == 0 and st.value != 0:
