@@ -93,31 +93,32 @@ __device__ __forceinline__ void ld_combined16(uint32_t t_main, uint32_t t_corr, 
 // One split product D[128 x 64] (+)= A[128 x 64] . op(B[64 x 64]) issued by a single thread.
 //   B_MN = false: D[m][n] = sum_k A[m][k] B[n][k]   (B K-major: its rows are the n index)
 //   B_MN = true : D[m][n] = sum_k A[m][k] B[k][n]   (B MN-major: its rows are the contraction index)
-// `acc` = 0 starts fresh accumulators.  Descriptor offsets are compile-time constants (gemm_sm100.cuh: every extra
-// dependent instruction of the issuing lane costs tensor-pipe time).
+// `acc` = 0 starts fresh accumulators.  The "corr" accumulator must sit right behind "main" (t_main + 64): the leading
+// product A0.B0 and the first correction A0.B1 are ONE instruction with N = 128 -- planes 0 and 1 of a B tile are
+// adjacent in shared memory, so [B0 | B1] is simply a B operand of 128 rows (K-major) or of two N-atoms one plane apart
+// (MN-major), and its two halves land in the main and corr columns.  An N = 64 instruction occupies the tensor pipe for
+// 32 clk, less than the single issuing lane needs per instruction (descriptors travel vector -> uniform registers):
+// the first version, 3 x N = 64 per k-step, was issue-bound.  Descriptor offsets are compile-time constants.
 template <int NPL, bool B_MN>
 __device__ __forceinline__ void issue_product(uint32_t sa, uint32_t sb, uint32_t t_main, uint32_t t_corr, uint32_t acc) {
   constexpr int F16 = Fmt<NPL>::FP16 ? 0 : 1;   // instruction-descriptor format code: 0 = F16, 1 = BF16
-  constexpr uint32_t idesc = make_idesc_f16kind(A_ROWS, B_ROWS, 0, B_MN ? 1 : 0, F16, F16);
+  constexpr uint32_t idesc64 = make_idesc_f16kind(A_ROWS, B_ROWS, 0, B_MN ? 1 : 0, F16, F16);
+  constexpr uint32_t idesc128 = make_idesc_f16kind(A_ROWS, 2 * B_ROWS, 0, B_MN ? 1 : 0, F16, F16);
   constexpr uint32_t B_KSTEP = B_MN ? 16 * ROWB : 32;   // 16 contraction rows, or 16 elements inside the row
-  constexpr int PA[6] = {0, 0, 1, 1, 0, 2};
-  constexpr int PB[6] = {0, 1, 0, 1, 2, 0};
+  // remaining corrections after A0.[B0|B1]:  fp16 pair: A1.B0      bf16 x 3: A1.B0, A1.B1, A0.B2, A2.B0
+  constexpr int NREST = Fmt<NPL>::FP16 ? 1 : 4;
+  constexpr int PA[4] = {1, 1, 0, 2};
+  constexpr int PB[4] = {0, 1, 2, 0};
   const uint64_t a_base = make_smem_desc(sa, 0, 8 * ROWB, SWZ_128B);
   const uint64_t b_base = make_smem_desc(sb, B_MN ? B_PLANE : 0, 8 * ROWB, SWZ_128B);
-  uint32_t am = acc, ac = acc;
+  (void)t_corr;
 #pragma unroll
   for (int k = 0; k < 4; ++k) {
-    umma_bf16(t_main, a_base + ((k * 32) >> 4), b_base + ((k * B_KSTEP) >> 4), idesc, am);
-    am = 1u;
-  }
+    umma_bf16(t_main, a_base + ((k * 32) >> 4), b_base + ((k * B_KSTEP) >> 4), idesc128, k == 0 ? acc : 1u);
 #pragma unroll
-  for (int k = 0; k < 4; ++k) {
-#pragma unroll
-    for (int q = 1; q < Fmt<NPL>::NPROD; ++q) {
-      umma_bf16(t_corr, a_base + ((PA[q] * A_PLANE + k * 32) >> 4), b_base + ((PB[q] * B_PLANE + k * B_KSTEP) >> 4),
-                idesc, ac);
-      ac = 1u;
-    }
+    for (int q = 0; q < NREST; ++q)
+      umma_bf16(t_main + 64, a_base + ((PA[q] * A_PLANE + k * 32) >> 4),
+                b_base + ((PB[q] * B_PLANE + k * B_KSTEP) >> 4), idesc64, 1u);
   }
 }
 
@@ -581,15 +582,25 @@ attn_bwd_kv_sm100_kernel(const __grid_constant__ CUtensorMap tm_kv, const __grid
     const uint32_t lane_off = (uint32_t)(quarter * 32) << 16;
     const uint32_t col0 = (uint32_t)(cg * BWD_COLS);
     const float sl2 = scale * LOG2E;
+    // per-query softmax statistics: fetched one tile ahead (the global-load latency hides under the previous tile's
+    // arithmetic), handed over through shared memory double-buffered by tile parity
+    float nl_next = -INFINITY, del_next = 0.f;
+    auto fetch_stats = [&](int it) {
+      const int qi = (it0 + it) * B_ROWS + tid;
+      const bool in = tid < B_ROWS && it < ntiles && qi < T;
+      nl_next = in ? -lse[((long)b * H + h) * T + qi] * LOG2E : -INFINITY;
+      del_next = in ? delta[((long)b * H + h) * T + qi] : 0.f;
+    };
+    fetch_stats(0);
     for (int it = 0; it < ntiles; ++it) {
       const int q0 = (it0 + it) * B_ROWS;
       const int pb = it & 1;
-      if (tid < B_ROWS) {   // per-query softmax statistics of this tile (double-buffered by tile parity)
-        const int qi = q0 + tid;
-        sNl[pb * B_ROWS + tid] = qi < T ? -lse[((long)b * H + h) * T + qi] * LOG2E : -INFINITY;
-        sDel[pb * B_ROWS + tid] = qi < T ? delta[((long)b * H + h) * T + qi] : 0.f;
+      if (tid < B_ROWS) {
+        sNl[pb * B_ROWS + tid] = nl_next;
+        sDel[pb * B_ROWS + tid] = del_next;
       }
       named_bar_sync(1, 128 * BWD_NCG);
+      fetch_stats(it + 1);
       mbar_wait(&bars[KB_SREADY], it & 1);
       tc_fence_after();
       float p[BWD_COLS], dp[BWD_COLS];

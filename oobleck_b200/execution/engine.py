@@ -314,6 +314,7 @@ class ReconfigurationEngine:
         t0 = engine._pipeline_templates[0]
         self._min_num_ranks = t0._num_nodes * t0._num_gpus_per_node          # engine.py:46-49
         self.last_reconfiguration_seconds: float | None = None
+        self.last_breakdown: dict | None = None
         self.last_notification_time: float | None = None
         # lost-rank lists received by the listener thread, applied by the training thread at its next safe point
         self._pending: "queue.Queue[tuple[list[int], float]]" = queue.Queue()
@@ -449,18 +450,21 @@ class ReconfigurationEngine:
         def get_pipeline_template(ranks, templates):
             return next((t for t in templates if t._num_nodes * t._num_gpus_per_node == len(ranks)), None)
 
+        t_phase = [time.perf_counter()]
         old_rank_grids = [copy.deepcopy(pipeline.rank_grid) for pipeline in self._pipelines]
         new_ranks_list = self.plan_new_ranks(lost_ranks)
         new_num_instances_set: dict[PipelineTemplate, int] = defaultdict(int)
         for ranks in new_ranks_list:
             new_num_instances_set[get_pipeline_template(ranks, self.engine._pipeline_templates)] += 1
         new_pipeline = self._reinstantiate(new_num_instances_set, new_ranks_list)
+        t_phase.append(time.perf_counter())
         new_rank_grids = []
         remaining = list(new_ranks_list)
         for template, num_instance in new_num_instances_set.items():
             for _ in range(num_instance):
                 new_rank_grids.append(template.get_rank_grid(remaining.pop(0)))
         self._copy_model_states(old_rank_grids, new_rank_grids, new_pipeline)
+        t_phase.append(time.perf_counter())
         for layer in self.engine._pipeline.execution._layers:        # engine.py:176-178
             if all(layer is not l for l in new_pipeline.execution._layers):
                 layer.remove_tensors()
@@ -470,6 +474,10 @@ class ReconfigurationEngine:
         if self.engine._peer_shadow:
             self.engine._shadow = PeerShadow(self.engine, new_pipeline)
             self.engine._shadow.refresh()
+        t_phase.append(time.perf_counter())
+        self.last_breakdown = {"plan_and_rebuild_pipelines_s": t_phase[1] - t_phase[0],
+                               "copy_model_states_s": t_phase[2] - t_phase[1],
+                               "communicators_and_shadows_s": t_phase[3] - t_phase[2]}
 
     # -- mechanism ---------------------------------------------------------------------------------------------------
     def _reinstantiate(self, num_instances_set, new_ranks_list) -> OobleckPipeline:

@@ -120,6 +120,7 @@ class Layer:
     """Constructor keeps the reference's positional order (layer.py:71-78)."""
 
     device_type = "cuda"
+    supports_deferred_init = True     # accepts init_values=False (see __init__)
 
     @classmethod
     def make_workspace(cls, model, microbatch_size: int, device) -> "StageWorkspace":
@@ -129,7 +130,7 @@ class Layer:
     def __init__(self, layer_id: int, layer: StageLayerSpec, process_group=None, pre_stream=None, post_stream=None, *,
                  microbatch_size: int, num_pipe_buffers: int, workspace: StageWorkspace | None = None,
                  nsplit: int = 3, device: torch.device | None = None, seq_len: int | None = None,
-                 bwd_fp16: bool | None = None):
+                 bwd_fp16: bool | None = None, init_values: bool = True):
         L.load()  # fail loudly if the CUDA extension is missing
         if not torch.cuda.is_available():
             raise L.OobleckB200Error("oobleck_b200.Layer needs a CUDA device (there is no CPU path)")
@@ -151,7 +152,10 @@ class Layer:
         n = layer.num_params
         self.numel = n
         self.plane_stride = _round8(n)
-        flat = layer.init_flat().to(self.device)
+        # ``init_values=False``: the layer is built to RECEIVE its state (reconfiguration moves parameters and moments
+        # into it); generating 30-80 M random numbers per layer on the host was most of the rebuild time
+        flat = layer.init_flat().to(self.device) if init_values else \
+            torch.empty(n, dtype=torch.float32, device=self.device)
         flat.requires_grad_(False)
         flat.grad = torch.zeros(n, dtype=torch.float32, device=self.device)
         self._param_handle = _ParamHandle(flat, process_group)
@@ -180,7 +184,8 @@ class Layer:
         # AdamW step count of THIS layer's moments: travels with exp_avg / exp_avg_sq through reconfigurations so the
         # bias correction matches the moments (optimizer.py)
         self.opt_step = 0
-        self.refresh_planes()
+        if init_values:
+            self.refresh_planes()
 
         E, V = layer.n_embd, layer.vocab_size
         self.dims = OobDims(self.mb, self.T, E, layer.n_head, V, (V + 63) // 64 * 64, layer.layer_norm_epsilon, nsplit,

@@ -543,8 +543,12 @@ class OobleckPipeline:
                     except TypeError:   # layer classes with the reference's two-argument signature
                         layers.append(layer_cls.create_layer_from_layer(existing_layer, pg))
                     continue
+            extra = {}
+            if existing_pipeline is not None and getattr(layer_cls, "supports_deferred_init", False):
+                extra["init_values"] = False      # a layer that appears during a reconfiguration receives its state
             layers.append(layer_cls(layer_id, model.layers[layer_id], pg, None, None, microbatch_size=mb,
-                                    num_pipe_buffers=num_pipe_buffers, workspace=workspace, nsplit=self._nsplit))
+                                    num_pipe_buffers=num_pipe_buffers, workspace=workspace, nsplit=self._nsplit,
+                                    **extra))
         self.execution = PipelineExecution(pipeline=self, layers=layers, shard_id=shard_id,
                                            dataloader=self._dataloader, training_args=self._training_args)
         self.pipe_buffers: dict[str, list] = {

@@ -6,9 +6,9 @@ lost-node message arriving on the worker pipe to the first completed post-reconf
 This process plays the agent, with the reference's own fake-agent protocol (tests/execution/test_engine.py:650-657,
 1037-1053): it spawns one worker per GPU -- each runs exactly ``worker_main``'s call sequence (elastic/worker.py:23-34)
 on ``OobleckEngine(local_rank, num_nodes, 1, pipe, args)`` -- sends ``DistributionInfo`` down every pipe and re-broadcasts
-rank 0's TCPStore port.  When every worker has started training step ``--kill-step`` it SIGKILLs the worker of the last
-rank (mid-step: its pipeline neighbours are left spinning on NVLink flags, its data-parallel partners would wait in
-NCCL), then announces the lost IP to the survivors and re-broadcasts the port once more.
+rank 0's TCPStore port.  When every worker has started training step ``--kill-step`` the worker of the last rank dies by
+SIGKILL (its pipeline neighbours are left spinning on NVLink flags, everybody else runs into a vote that cannot complete);
+the agent notices the death, announces the lost IP to the survivors and re-broadcasts the port once more.
 
 The survivors' listener threads release the GPU (host-mapped abort words for the P2P kernels, ncclCommAbort for the
 communicators that contained the victim), the training threads drop the step in flight, re-plan with the reference's
@@ -39,8 +39,21 @@ def _ips(world):
     return [f"127.0.0.{r + 1}" for r in range(world)]
 
 
+def _die_with_parent():
+    """Workers must not outlive the agent process (a killed benchmark would leave them spinning on the GPUs)."""
+    parent = os.getppid()
+
+    def watch():
+        while True:
+            time.sleep(1.0)
+            if os.getppid() != parent:
+                os._exit(1)
+    threading.Thread(target=watch, daemon=True).start()
+
+
 def worker(rank, world, pipe, q, started, model, replicas, steps, kill_step):
     from unittest.mock import patch
+    _die_with_parent()
     os.environ["TORCH_NCCL_ASYNC_ERROR_HANDLING"] = "0"   # a dead peer is handled by the engine, not by the NCCL watchdog
     os.environ.setdefault("NCCL_DEBUG", "WARN")
     os.environ.setdefault("OOB_P2P_TIMEOUT_S", "60")
@@ -81,7 +94,12 @@ def worker(rank, world, pipe, q, started, model, replicas, steps, kill_step):
 
         def hook():
             if count["n"] == kill_step:
-                started.put(rank)       # the agent kills the victim once everybody is inside this step
+                started.put(rank)
+                if rank == world - 1:
+                    # the victim dies here, with SIGKILL: its peers are inside this step -- pipeline neighbours spinning
+                    # on NVLink flags it will never write, everybody else on their way into the vote
+                    time.sleep(0.05)
+                    os.kill(os.getpid(), signal.SIGKILL)
             count["n"] += 1
             return orig()
         eng._guarded_train_step = hook
@@ -95,7 +113,7 @@ def worker(rank, world, pipe, q, started, model, replicas, steps, kill_step):
         sums = {l.layer_id: float(l.flat_param.double().sum()) for l in eng._pipeline.execution._layers}
         q.put((rank, {
             "pipelines": [p._ranks for p in rc._pipelines],
-            "notify_to_rebuilt_s": rc.last_reconfiguration_seconds,
+            "notify_to_rebuilt_s": rc.last_reconfiguration_seconds, "breakdown": rc.last_breakdown,
             "notify_to_first_step_s": (first_after - t_note) if first_after is not None else None,
             "steps_completed": len(eng.step_seconds),
             "step_s_before": eng.step_seconds[:kill_step], "step_s_after": eng.step_seconds[kill_step:],
@@ -148,10 +166,11 @@ def main(args=None):
         rebroadcast(pipes)
         for _ in range(world):
             started.get(timeout=1800)
-        time.sleep(0.3)                                   # let the step get going: kill lands mid-step
         marks["kill"] = time.perf_counter()
-        os.kill(procs[victim].pid, signal.SIGKILL)
-        procs[victim].join(timeout=30)
+        procs[victim].join(timeout=60)                    # the victim SIGKILLs itself inside this step (see worker)
+        if procs[victim].is_alive():
+            os.kill(procs[victim].pid, signal.SIGKILL)
+            procs[victim].join(timeout=30)
         marks["announce"] = time.perf_counter()
         survivors = [p for i, p in enumerate(pipes) if i != victim]
         for pipe, _ in survivors:
@@ -190,7 +209,8 @@ def main(args=None):
         "step_s_before": statistics_of([x for v in results.values() for x in v["step_s_before"][1:]]),
         "step_s_after": statistics_of([x for v in results.values() for x in v["step_s_after"][1:]]),
         "replicas_identical_after": all(len(s) == 1 for s in by_layer.values()),
-        "per_rank": {str(r): {k: v[k] for k in ("notify_to_rebuilt_s", "notify_to_first_step_s", "steps_completed")}
+        "per_rank": {str(r): {k: v[k] for k in ("notify_to_rebuilt_s", "breakdown", "notify_to_first_step_s",
+                                                "steps_completed")}
                      for r, v in sorted(results.items())},
     }
     print(json.dumps(out), flush=True)
