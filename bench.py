@@ -195,7 +195,9 @@ def cpu_pipeline_sample(model: str, gpus: int, replicas: int, steps: int, warmup
         depth //= 2
         need = 24.0 * (12 * depth * E * E + 2 * E * V)
         depth_note = f" (host RAM {avail / 2**30:.0f} GiB: depth reduced to {depth} of {ma['num_hidden_layers']} blocks)"
-    seq = min(REF_SEQ, ma["n_positions"])
+    # the sample is REF_SEQ tokens per step in total: P micro-batches of REF_SEQ / P tokens, so that a step costs about
+    # the same host time at every N (1F1B over P CPU stages of cores / P threads each) and K + W steps fit the run
+    seq = max(16, min(REF_SEQ, ma["n_positions"]) // max(1, P // replicas))
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = free_port()

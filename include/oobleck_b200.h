@@ -218,6 +218,22 @@ int oob_p2p_send(const void* src, long bytes, void* my_mailbox, void* peer_mailb
 int oob_p2p_recv(void* dst, long bytes, void* my_mailbox, void* peer_mailbox, int nslots, long slot_bytes,
                  long offset_in_slot, unsigned seq, int first, int last, void* stream);
 
+/* ==== pipeline-template search (csrc/planning/template_search.cpp) ================================================
+ * Dependency-free rebuild of PipelineTemplateGenerator::create_pipeline_templates
+ * (oobleck/csrc/planning/pipeline_template.cpp:82-339; cost algebra execution_result.h:60-205): for every node count
+ * in [min_nodes, max_nodes] the stage / GPU split minimising the 1F1B iteration-time estimate.
+ * allreduce_in_node: [num_layers][allreduce_stride] seconds, column g = all-reduce over g GPUs of one node (NULL = 0).
+ * out: per template { num_nodes, num_stages, then per stage { first_layer, end_layer, num_gpus } }.
+ * Returns 0, -2 on bad arguments (non-positive layer times included), -3 when `out` is too small. */
+typedef struct {
+  double forward, backward;       /* milliseconds (any unit, consistently) */
+  long long mem_params;           /* bytes of parameters (the planner budgets 6x this) */
+  long long mem_activations;      /* bytes of activations */
+} oob_layer_profile;
+int oob_plan_pipeline_templates(const oob_layer_profile* layers, int num_layers, const double* allreduce_in_node,
+                                int allreduce_stride, int num_gpus_per_node, int min_nodes, int max_nodes, int* out,
+                                int out_capacity, double* iteration_time, int* num_templates);
+
 #ifdef __cplusplus
 }
 #endif

@@ -405,15 +405,32 @@ __device__ __forceinline__ float block_reduce(float v, float* sh, bool is_max) {
   return r;
 }
 
+// Number of positions that contribute to the mean: t < T - 1 and 0 <= label < V.  HF's GPT-2 loss (what the reference
+// runs) is CrossEntropyLoss(ignore_index=-100, reduction="mean"): padded / masked labels produce no loss, no gradient,
+// and do not count in the divisor; an id outside the vocabulary is treated the same way instead of reading out of
+// bounds.  Every CTA recounts (the label array is a few KB and L2-resident), so no extra launch or scratch is needed.
+__device__ __forceinline__ float count_valid_targets(const long long* __restrict__ labels, int rows, int T, int V,
+                                                     float* sh) {
+  float n = 0.f;
+  for (int r = threadIdx.x; r < rows; r += blockDim.x) {
+    if (r % T < T - 1) {
+      const long long y = labels[r + 1];
+      n += (y >= 0 && y < V) ? 1.f : 0.f;
+    }
+  }
+  return block_reduce(n, sh, false);
+}
+
 __global__ void __launch_bounds__(512)
-cross_entropy_kernel(const float* __restrict__ logits, long ldl, const long long* __restrict__ labels, int T, int V,
-                     float grad_scale, float* __restrict__ row_loss, bf16* __restrict__ dplanes, long ldp,
+cross_entropy_kernel(const float* __restrict__ logits, long ldl, const long long* __restrict__ labels, int rows, int T,
+                     int V, float grad_scale_user, float* __restrict__ row_loss, bf16* __restrict__ dplanes, long ldp,
                      long plane_stride, int nplanes) {
   __shared__ float sh[32];
   const int row = blockIdx.x;
   const int t = row % T;
   const float* lr = logits + (long)row * ldl;
-  const bool has_target = t < T - 1;
+  const long long target = t < T - 1 ? labels[row + 1] : -1;
+  const bool has_target = target >= 0 && target < V;
   const int vpad = (int)ldp;
   if (!has_target) {
     if (threadIdx.x == 0) row_loss[row] = 0.f;
@@ -425,7 +442,9 @@ cross_entropy_kernel(const float* __restrict__ logits, long ldl, const long long
     }
     return;
   }
-  const long long target = labels[row + 1];
+  const float nvalid = count_valid_targets(labels, rows, T, V, sh);
+  __syncthreads();
+  const float grad_scale = (1.0f / fmaxf(nvalid, 1.f)) * grad_scale_user;
   float mx = -INFINITY;
   for (int c = threadIdx.x; c < V; c += blockDim.x) mx = fmaxf(mx, lr[c]);
   mx = block_reduce(mx, sh, true);
@@ -464,14 +483,17 @@ cross_entropy_kernel(const float* __restrict__ logits, long ldl, const long long
 }
 
 // loss = sum(row_loss) * scale, deterministic single-CTA reduction
-__global__ void __launch_bounds__(1024) loss_reduce_kernel(const float* __restrict__ row_loss, int rows, float scale,
+__global__ void __launch_bounds__(1024) loss_reduce_kernel(const float* __restrict__ row_loss,
+                                                           const long long* __restrict__ labels, int rows, int T, int V,
                                                            float* __restrict__ loss, float* __restrict__ total) {
   __shared__ float sh[32];
+  const float nvalid = count_valid_targets(labels, rows, T, V, sh);
+  __syncthreads();
   float s = 0.f;
   for (int i = threadIdx.x; i < rows; i += blockDim.x) s += row_loss[i];
   s = block_reduce(s, sh, false);
   if (threadIdx.x == 0) {
-    const float l = s * scale;
+    const float l = s * (1.0f / fmaxf(nvalid, 1.f));
     *loss = l;
     if (total) *total += l;
   }
@@ -483,12 +505,11 @@ int cross_entropy(const float* logits, long ldl, const long long* labels, int B,
   const int rows = B * T;
   OOB_CHECK(T >= 2, "cross_entropy: sequence length must be >= 2");
   OOB_CHECK(dplanes == nullptr || (ldp % 8 == 0 && plane_stride % 8 == 0), "cross_entropy: plane strides must be multiples of 8");
-  const float scale = 1.0f / (float)((long)B * (T - 1));
-  cross_entropy_kernel<<<rows, 512, 0, s>>>(logits, ldl, labels, T, V, scale * grad_scale, row_loss, dplanes, ldp,
+  cross_entropy_kernel<<<rows, 512, 0, s>>>(logits, ldl, labels, rows, T, V, grad_scale, row_loss, dplanes, ldp,
                                             plane_stride, nplanes);
   OOB_CUDA_OK(cudaGetLastError());
   count_launch();
-  loss_reduce_kernel<<<1, 1024, 0, s>>>(row_loss, rows, scale, loss, total_loss);
+  loss_reduce_kernel<<<1, 1024, 0, s>>>(row_loss, labels, rows, T, V, loss, total_loss);
   OOB_CUDA_OK(cudaGetLastError());
   count_launch();
   return 0;

@@ -825,11 +825,20 @@ class OobleckEngine:
         """engine.py:600-643."""
         if (not self._templates_injected and plan is None and self._layer_cls is None and torch.cuda.is_available()
                 and os.environ.get("OOB_MEASURED_BALANCE", "1") == "1" and self._num_nodes > 1):
-            from ..planning.profiler import measured_layer_costs
-            self.layer_costs = measured_layer_costs(self._model, self._args.job.microbatch_size)
+            from ..planning.profiler import measured_layer_results
+            results = measured_layer_results(self._model, self._args.job.microbatch_size)
+            self.layer_costs = [r._forward + r._backward for r in results.get()]
             self.layer_costs_source = "measured (CUDA events, fwd + bwd ms per layer kind, rank 0, broadcast)"
-            self._pipeline_templates = [balanced_template(self.layer_costs, n, self._num_gpus_per_node)
-                                        for n in range(1, self._num_nodes + 1) if n <= len(self.layer_costs)]
+            if os.environ.get("OOB_TEMPLATE_SOURCE", "planner") == "planner":
+                # the reference's flow (engine.py:453-500): profile -> PipelineTemplateGenerator.create_pipeline_templates
+                from ..planning.pipeline_template import PipelineTemplateGenerator
+                self._pipeline_templates = PipelineTemplateGenerator().create_pipeline_templates(
+                    results, (1, min(self._num_nodes, len(self.layer_costs))), self._num_gpus_per_node)
+                self.layer_costs_source += " -> template search (csrc/planning/template_search.cpp)"
+            else:
+                self._pipeline_templates = [balanced_template(self.layer_costs, n, self._num_gpus_per_node)
+                                            for n in range(1, self._num_nodes + 1) if n <= len(self.layer_costs)]
+                self.layer_costs_source += " -> min-max contiguous partition"
         plan = plan or self.choose_plan()
         num_microbatches = self.distribute_microbatches(plan, global_num_microbatch)
         ranks_list, used = [], 0

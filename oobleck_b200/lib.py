@@ -61,6 +61,11 @@ class OobHeadCtx(C.Structure):
     _fields_ = [(n, C.c_void_p) for n in ["lnf_planes", "mean", "rstd", "logits", "dlogits_planes", "row_loss", "loss"]]
 
 
+class LayerProfile(C.Structure):           # oob_layer_profile
+    _fields_ = [("forward", C.c_double), ("backward", C.c_double), ("mem_params", C.c_longlong),
+                ("mem_activations", C.c_longlong)]
+
+
 ACT_NONE, ACT_GELU, ACT_DGELU = 0, 1, 2
 
 _P, _L, _I, _F = C.c_void_p, C.c_long, C.c_int, C.c_float
@@ -68,6 +73,9 @@ _SIGNATURES = {
     "oob_version": (C.c_int, []),
     "oob_last_error": (C.c_char_p, []),
     "oob_launch_count": (C.c_long, []),
+    "oob_plan_pipeline_templates": (C.c_int, [C.POINTER(LayerProfile), C.c_int, C.POINTER(C.c_double), C.c_int, C.c_int,
+                                              C.c_int, C.c_int, C.POINTER(C.c_int), C.c_int, C.POINTER(C.c_double),
+                                              C.POINTER(C.c_int)]),
     "oob_tensor_map_encodes": (C.c_long, []),
     "oob_gemm_timing_begin": (_I, []),
     "oob_gemm_timing_end": (_I, [C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_double),

@@ -1,6 +1,5 @@
-"""Bookkeeping stand-in for the reference's C++ planner objects (oobleck/csrc/planning/*, bound through
-pipeline_template.pyi).  The planner itself (divide-and-conquer template search) is control plane and out of
-scope; the hot path only needs the *shape* of its result:
+"""The reference's C++ planner objects (oobleck/csrc/planning/*, bound through pipeline_template.pyi) with the same
+class names and attributes.  The hot path needs the *shape* of the planner's result:
 
 * ``StageExecutionResult._layer_indices / _num_gpus``     (execution_result.h:60-112)
 * ``PipelineTemplate.get_stages() / get_rank_grid(ranks)`` (pipeline_template.h:20-90)
@@ -8,10 +7,44 @@ scope; the hot path only needs the *shape* of its result:
 so that ``OobleckPipeline`` can be constructed exactly as ``HeterogeneousPipelinesExecutionPlan.instantiate``
 does (planning/instantiator.py:135-152).  ``even_template`` / ``balanced_template`` build templates without the
 planner for benchmarks and tests.
+
+``LayerExecutionResult(s)`` and ``PipelineTemplateGenerator.create_pipeline_templates`` are the dependency-free rebuild of
+the template search itself: the divide-and-conquer of pipeline_template.cpp:82-339 with the cost algebra
+of execution_result.h:60-205, in C++ behind the C ABI (csrc/planning/template_search.cpp; the reference's build needs
+cppcoro and oneTBB, neither of which exists here), fed by ``planning/profiler.py``'s measured latencies.
 """
 from __future__ import annotations
 
 from typing import Sequence
+
+
+class LayerExecutionResult:
+    """pipeline_template.pyi:1-16 / execution_result.h:15-38."""
+
+    def __init__(self, layer_index: int, forward: float, backward: float, allreduce_in_node: dict[int, float],
+                 allreduce_across_nodes: dict[int, float], mem_required: tuple[int, int]):
+        self._index = layer_index
+        self._forward = float(forward)
+        self._backward = float(backward)
+        self._allreduce_in_node = dict(allreduce_in_node)
+        self._allreduce_across_nodes = dict(allreduce_across_nodes)
+        self._mem_required = (int(mem_required[0]), int(mem_required[1]))
+
+
+class LayerExecutionResults:
+    """pipeline_template.pyi:18-21."""
+
+    def __init__(self, data: list[LayerExecutionResult]):
+        self._data = list(data)
+
+    def get(self) -> list[LayerExecutionResult]:
+        return self._data
+
+    def at(self, index: int) -> LayerExecutionResult:
+        return self._data[index]
+
+    def size(self) -> int:
+        return len(self._data)
 
 
 class StageExecutionResult:
@@ -19,6 +52,7 @@ class StageExecutionResult:
         self._layer_indices = list(layer_indices)
         self._num_gpus = num_gpus
         self._size = len(self._layer_indices)
+        self._mem_required = 0
 
     def num_layers(self) -> int:
         return len(self._layer_indices)
@@ -91,3 +125,49 @@ def balanced_template(layer_costs: Sequence[float], num_stages: int, num_gpus_pe
         j = i
     stages = [StageExecutionResult(range(a, b), 1) for a, b in reversed(bounds)]
     return PipelineTemplate(stages, best[num_stages][n], n, num_stages, num_gpus_per_node)
+
+
+class PipelineTemplateGenerator:
+    """pipeline_template.pyi:53-62: ``create_pipeline_templates(layer_execution_results, (min_nodes, max_nodes),
+    num_gpus_per_node) -> list[PipelineTemplate]``, one template per feasible node count, stages chosen by the
+    divide-and-conquer search (``oob_plan_pipeline_templates``)."""
+
+    def create_pipeline_templates(self, layer_execution_results: LayerExecutionResults, num_nodes: tuple[int, int],
+                                  num_gpus_per_node: int) -> list[PipelineTemplate]:
+        import ctypes as C
+
+        from .. import lib as L
+        lib = L.load()
+        n = layer_execution_results.size()
+        prof = (L.LayerProfile * n)()
+        stride = num_gpus_per_node + 1
+        ar = (C.c_double * (n * stride))()
+        for i, r in enumerate(layer_execution_results.get()):
+            prof[i].forward, prof[i].backward = r._forward, r._backward
+            prof[i].mem_params, prof[i].mem_activations = r._mem_required
+            for g, v in r._allreduce_in_node.items():
+                if 0 <= int(g) < stride:
+                    ar[i * stride + int(g)] = float(v)
+        min_nodes, max_nodes = num_nodes
+        cap = max(1, max_nodes - min_nodes + 1) * (2 + 3 * n)
+        out = (C.c_int * cap)()
+        times = (C.c_double * max(1, max_nodes - min_nodes + 1))()
+        count = C.c_int(0)
+        rc = lib.oob_plan_pipeline_templates(prof, n, ar, stride, num_gpus_per_node, min_nodes, max_nodes, out, cap, times,
+                                             C.byref(count))
+        if rc != 0:
+            raise L.OobleckB200Error(f"oob_plan_pipeline_templates failed ({rc}): layer times must be positive")
+        templates, pos = [], 0
+        for t in range(count.value):
+            nodes, nstages = out[pos], out[pos + 1]
+            pos += 2
+            stages = []
+            for _ in range(nstages):
+                begin, end, gpus = out[pos], out[pos + 1], out[pos + 2]
+                pos += 3
+                st = StageExecutionResult(range(begin, end), gpus)
+                st._mem_required = sum(6 * layer_execution_results.at(i)._mem_required[0]
+                                       + layer_execution_results.at(i)._mem_required[1] for i in range(begin, end))
+                stages.append(st)
+            templates.append(PipelineTemplate(stages, times[t], n, nodes, num_gpus_per_node))
+        return templates

@@ -60,9 +60,9 @@ def measure_layer_costs(model, microbatch: int, device: torch.device | None = No
     return out
 
 
-def measured_layer_costs(model, microbatch: int, device: torch.device | None = None) -> list[float]:
-    """fwd + bwd milliseconds per ``model.layers`` entry.  Measured on global rank 0 and broadcast when a process group
-    exists (profiler.py:108-116), so every rank derives the same pipeline templates from it."""
+def _measured_table(model, microbatch: int, device: torch.device | None = None):
+    """[kind][fwd, bwd] milliseconds, measured on global rank 0 and broadcast when a process group exists
+    (profiler.py:108-116), so every rank derives the same pipeline templates from it."""
     rank = dist.get_rank() if dist.is_initialized() else 0
     kinds = ["embed", "block", "head"]
     table = torch.zeros(len(kinds), 2, dtype=torch.float64)
@@ -76,5 +76,20 @@ def measured_layer_costs(model, microbatch: int, device: torch.device | None = N
         t = table.to(dev)
         dist.broadcast(t, 0)
         table = t.cpu()
-    cost = {k: float(table[i, 0] + table[i, 1]) for i, k in enumerate(kinds)}
-    return [cost[l.kind] for l in model.layers]
+    return {k: (float(table[i, 0]), float(table[i, 1])) for i, k in enumerate(kinds)}
+
+
+def measured_layer_costs(model, microbatch: int, device: torch.device | None = None) -> list[float]:
+    """fwd + bwd milliseconds per ``model.layers`` entry."""
+    t = _measured_table(model, microbatch, device)
+    return [t[l.kind][0] + t[l.kind][1] for l in model.layers]
+
+
+def measured_layer_results(model, microbatch: int, device: torch.device | None = None):
+    """The planner's input (``LayerExecutionResults``, what ``get_profile_results`` returns in the reference): measured
+    forward / backward per layer, the memory model of ``StageLayerSpec`` for (parameters, activations)."""
+    from .pipeline_template import LayerExecutionResult, LayerExecutionResults
+    t = _measured_table(model, microbatch, device)
+    return LayerExecutionResults([
+        LayerExecutionResult(i, t[l.kind][0], t[l.kind][1], {}, {}, (4 * l.num_params, l.activation_bytes(microbatch)))
+        for i, l in enumerate(model.layers)])

@@ -309,6 +309,35 @@ def test_cross_entropy():
     assert (got[:, V:] == 0).all()
 
 
+def test_cross_entropy_ignored_labels():
+    """HF GPT-2's loss is CrossEntropyLoss(ignore_index=-100, mean over the targets that count): padded labels (and ids
+    outside the vocabulary) give no loss, no gradient, and do not enter the divisor."""
+    B, T, V = 3, 17, 1000
+    Vp = (V + 63) // 64 * 64
+    torch.manual_seed(1)
+    logits = torch.randn(B * T, Vp, device=DEV) * 2
+    labels = torch.randint(0, V, (B, T), device=DEV)
+    labels[0, 5:9] = -100
+    labels[2, 1] = -100
+    labels[1, 16] = V + 7            # out of range: ignored, never dereferenced
+    row_loss = torch.empty(B * T, device=DEV)
+    loss, total = torch.zeros(1, device=DEV), torch.zeros(1, device=DEV)
+    dp = ops.new_planes(B * T, Vp)
+    L.call("oob_cross_entropy", P(logits), Vp, P(labels), B, T, V, P(row_loss), P(loss), P(total), P(dp), Vp,
+           dp.stride(0), 3, 1.0, S())
+    l64 = logits[:, :V].double().view(B, T, V).requires_grad_(True)
+    tgt = labels[:, 1:].clone()
+    tgt[tgt >= V] = -100
+    ref = torch.nn.functional.cross_entropy(l64[:, :-1].reshape(-1, V), tgt.reshape(-1), ignore_index=-100)
+    ref.backward()
+    assert abs(loss.item() - ref.item()) < 1e-5 * abs(ref.item())
+    got = ops.planes_to_float(dp)
+    assert rel_err(got[:, :V], l64.grad.view(B * T, V)) < 5e-6
+    ignored = (tgt.reshape(-1) == -100)
+    rows = torch.arange(B * T, device=DEV).view(B, T)[:, :-1].reshape(-1)[ignored]
+    assert (got[rows] == 0).all() and (row_loss[rows] == 0).all()
+
+
 def test_adamw_matches_torch():
     n = 100003
     p0, g = torch.randn(n, device=DEV), torch.randn(n, device=DEV)
