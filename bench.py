@@ -134,6 +134,7 @@ def _cpu_worker(rank, world, port, model, replicas, seq, steps, warmup, threads,
                                                    layer_cost_model)
         from oobleck_b200.planning.pipeline_template import balanced_template
         from oracle.layer import OracleLayer
+        OracleLayer.fast_init = True
         cfg = MODELS[model]
         ma = dict(cfg["model_args"])
         ma["num_hidden_layers"] = depth
@@ -173,7 +174,7 @@ def _cpu_worker(rank, world, port, model, replicas, seq, steps, warmup, threads,
         raise
 
 
-def cpu_pipeline_sample(model: str, gpus: int, replicas: int, steps: int, warmup: int, timeout: float = 3000.0):
+def cpu_pipeline_sample(model: str, gpus: int, replicas: int, steps: int, warmup: int, timeout: float = 800.0):
     """Spawn the P gloo processes of the CPU arm and return (seconds per step list, tokens per step, description)."""
     import torch.multiprocessing as mp
     cfg = MODELS[model]
@@ -201,15 +202,29 @@ def cpu_pipeline_sample(model: str, gpus: int, replicas: int, steps: int, warmup
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = free_port()
-    procs = [ctx.Process(target=_cpu_worker, args=(r, P, port, model, replicas, seq, steps, warmup, threads, depth, q))
-             for r in range(P)]
+    procs = [ctx.Process(target=_cpu_worker, args=(r, P, port, model, replicas, seq, steps, warmup, threads, depth, q),
+                         daemon=True) for r in range(P)]
     for p in procs:
         p.start()
-    status, payload, tokens = q.get(timeout=timeout)
+    # bounded wait: a CPU sample that does not come back must never take the whole benchmark down with it
+    import queue as _queue
+    t0 = time.perf_counter()
+    msg = None
+    while msg is None:
+        try:
+            msg = q.get(timeout=2.0)
+        except _queue.Empty:
+            if time.perf_counter() - t0 > timeout:
+                msg = ("error", f"CPU sample exceeded its {timeout:.0f} s budget", 0)
+            elif any(p.exitcode not in (None, 0) for p in procs):
+                msg = ("error", "a CPU worker died: exit codes " + str([p.exitcode for p in procs]), 0)
+    status, payload, tokens = msg
     for p in procs:
-        p.join(timeout=120)
+        p.join(timeout=5 if status != "ok" else 120)
+        if p.is_alive():
+            p.terminate()
     if status != "ok":
-        raise RuntimeError("CPU arm failed:\n" + str(payload))
+        raise RuntimeError("CPU arm failed: " + str(payload))
     sample = (f"real 1F1B train step (pipeline.train + all-reduce + AdamW) of the oracle port over {P} gloo process(es) x "
               f"{threads} threads: full depth ({depth + 2} stage layers{depth_note}), micro-batch 1 x {seq} tokens, "
               f"{tokens // seq} micro-batches per step; nothing extrapolated")
@@ -244,8 +259,14 @@ def run_reference(args, cfg):
 
 
 def cpu_baseline_sample(model: str):
-    """Bounded CPU sample for the N=1 line of our arm: one warm-up + two timed steps of the same CPU pipeline."""
-    times, tokens, info = cpu_pipeline_sample(model, 1, 1, steps=2, warmup=1)
+    """Bounded CPU sample for the N=1 line of our arm: one warm-up + two timed steps of the same CPU pipeline, with a hard
+    wall-clock budget (the GPU numbers of the line must never be lost to a slow host)."""
+    budget = float(os.environ.get("OOB_CPU_BASELINE_BUDGET_S", "240"))
+    try:
+        times, tokens, info = cpu_pipeline_sample(model, 1, 1, steps=2, warmup=1, timeout=budget)
+    except RuntimeError as e:
+        return {"value": None, "unit": "tokens/s", "cores": os.cpu_count(), "kind": "port",
+                "sample": f"not measured: {str(e)[:200]}"}
     return {"value": tokens * len(times) / sum(times), "unit": "tokens/s", "cores": info["cores"], "kind": "port",
             "sample": f"{len(times)} x ({info['sample']})"}
 
@@ -526,9 +547,11 @@ def run_ours(args, cfg):
 # dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of the dominant GEMM shape in the DEFAULT build (fp16 pairs
 # everywhere, pair-only plane buffers): forward FC 2048 x 6400 x 1600, bias + GELU epilogue writing the fp32
 # pre-activation and the two fp16 planes of GELU(x).  Source: profiles/ (see GEMM_TRAFFIC_NOTE).
-GEMM_TRAFFIC_BYTES = None
-GEMM_TRAFFIC_NOTE = ("bytes/launch from ncu --set full of the forward-FC launch in the default (pair-only) build; "
-                     "`achieved` aggregates all GEMM shapes")
+GEMM_TRAFFIC_BYTES = 54.50e6 + 57.77e6
+GEMM_TRAFFIC_NOTE = ("bytes/launch (dram read 54.5 MB + write 57.8 MB) from ncu --set full of the forward-FC launch in the "
+                     "default pair-only build, profiles/r02_ncu_gemm_fwdfc_pair_2groups.txt; algorithmic bytes of that "
+                     "launch: 54 MB of operand planes + 105 MB of outputs (part of the output is still in L2 when the "
+                     "kernel ends); `achieved` aggregates all GEMM shapes")
 
 
 def main():

@@ -49,6 +49,9 @@ class OracleLayer:
     def optimizer_factory():
         return OracleAdamW, WarmupLR
 
+    fast_init = False      # bench.py's CPU arm: constant weights (timing does not depend on the values; drawing 1.5 G
+                           # normal deviates on the host costs more than the sample itself)
+
     def __init__(self, layer_id, spec, process_group=None, pre_stream=None, post_stream=None, *, microbatch_size,
                  num_pipe_buffers, workspace=None, nsplit=3):
         self.layer_id = layer_id
@@ -57,7 +60,7 @@ class OracleLayer:
         d = og.GPT2Dims(n_embd=spec.n_embd, n_head=spec.n_head, n_layer=spec.n_layer, n_positions=spec.n_positions,
                         vocab_size=spec.vocab_size, layer_norm_epsilon=spec.layer_norm_epsilon)
         self.module = {"embed": og.EmbeddingLayer, "block": og.BlockLayer, "head": og.HeadLayer}[spec.kind](d)
-        flat = spec.init_flat()
+        flat = torch.full((spec.num_params,), 0.01) if self.fast_init else spec.init_flat()
         og.load_flat_(self.module, flat)
         flat.grad = torch.zeros_like(flat)
         self._param_handle = _Handle(flat)
