@@ -641,6 +641,10 @@ class OobleckEngine:
                  transport_cls=None, device_resident: bool = False, listen: bool = True, backend: str | None = None,
                  comm_timeout_s: float | None = None, peer_shadow: bool | None = None):
         self._agent_pipe = pipe
+        if pipe is not None:
+            # elastic run: a dead peer is this engine's business (listener thread: abort + reconfigure), not the NCCL
+            # watchdog's, which would tear the whole process down on the first remote error
+            os.environ.setdefault("TORCH_NCCL_ASYNC_ERROR_HANDLING", "0")
         # mirror every stage's state on its neighbour (PeerShadow): off by default -- it only matters for pipelines
         # without a replica -- OOB_PEER_SHADOW=1 or peer_shadow=True turns it on
         self._peer_shadow = (os.environ.get("OOB_PEER_SHADOW", "0") == "1") if peer_shadow is None else bool(peer_shadow)
