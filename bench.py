@@ -73,6 +73,20 @@ def workload_config(model: str, cfg: dict, gpus: int, replicas: int) -> dict:
             "parallelism": (f"pp{stages}" if replicas == 1 else f"dp{replicas} x pp{stages}")}
 
 
+def usable_cores() -> int:
+    """Host threads the CPU arm may really use: the affinity mask, a cgroup CPU quota if one is set, at most 64 (the
+    oracle's eager torch ops stop scaling long before that; 128 OpenMP threads on a shared, hyper-threaded host made
+    the round-2 sample run for minutes)."""
+    n = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    try:
+        quota, period = open("/sys/fs/cgroup/cpu.max").read().split()
+        if quota != "max":
+            n = min(n, max(1, int(int(quota) / int(period))))
+    except (OSError, ValueError):
+        pass
+    return max(1, min(n, int(os.environ.get("OOB_CPU_ARM_MAX_THREADS", "64"))))
+
+
 def free_port() -> int:
     with socket.socket() as s:
         s.bind(("127.0.0.1", 0))
@@ -126,6 +140,11 @@ def _cpu_worker(rank, world, port, model, replicas, seq, steps, warmup, threads,
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world),
                       LOCAL_RANK=str(rank))
     torch.set_num_threads(threads)
+    t_start = time.perf_counter()
+
+    def note(msg):
+        if rank == 0 and os.environ.get("OOB_CPU_ARM_VERBOSE", "1") == "1":
+            print(f"[cpu arm +{time.perf_counter() - t_start:6.1f}s] {msg}", file=sys.stderr, flush=True)
     try:
         import torch.distributed as dist
 
@@ -148,7 +167,9 @@ def _cpu_worker(rank, world, port, model, replicas, seq, steps, warmup, threads,
         eng.initialize_distributed("gloo")
         t = balanced_template(layer_cost_model(eng._model, 1), stages, 1)
         eng._pipeline_templates = [t]
+        note(f"engine built ({threads} threads, depth {depth}, {seq} tokens per micro-batch)")
         eng.instantiate_pipelines(M, plan=[t] * replicas)
+        note("pipelines instantiated (oracle layers materialised)")
         times = []
         for it in range(warmup + steps):
             if world > 1:
@@ -162,6 +183,7 @@ def _cpu_worker(rank, world, port, model, replicas, seq, steps, warmup, threads,
             dt = torch.tensor([time.perf_counter() - t0], dtype=torch.float64)
             if world > 1:
                 dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+            note(f"step {it} took {float(dt):.2f} s")
             if it >= warmup:
                 times.append(float(dt))
         if rank == 0:
@@ -179,7 +201,7 @@ def cpu_pipeline_sample(model: str, gpus: int, replicas: int, steps: int, warmup
     import torch.multiprocessing as mp
     cfg = MODELS[model]
     ma = cfg["model_args"]
-    cores = os.cpu_count() or 1
+    cores = usable_cores()
     P = gpus
     threads = max(1, cores // P)
     depth = ma["num_hidden_layers"]
@@ -265,7 +287,7 @@ def cpu_baseline_sample(model: str):
     try:
         times, tokens, info = cpu_pipeline_sample(model, 1, 1, steps=2, warmup=1, timeout=budget)
     except RuntimeError as e:
-        return {"value": None, "unit": "tokens/s", "cores": os.cpu_count(), "kind": "port",
+        return {"value": None, "unit": "tokens/s", "cores": usable_cores(), "kind": "port",
                 "sample": f"not measured: {str(e)[:200]}"}
     return {"value": tokens * len(times) / sum(times), "unit": "tokens/s", "cores": info["cores"], "kind": "port",
             "sample": f"{len(times)} x ({info['sample']})"}
@@ -316,7 +338,7 @@ def parity_check(args, cfg, world: int, rank: int, local_rank: int, transport_cl
     verdict = torch.zeros(1, device="cuda")
     if rank == 0:
         from oracle import gpt2 as og
-        torch.set_num_threads(min(os.cpu_count() or 1, 64))
+        torch.set_num_threads(usable_cores())
         d = og.GPT2Dims(n_embd=ma["n_embd"], n_head=ma["n_head"], n_layer=depth, n_positions=T, vocab_size=vocab)
         olayers = og.build_layers(d)
         for ol, spec in zip(olayers, eng._model.layers):
