@@ -27,6 +27,29 @@ AGENT_IPS = ["127.0.0.1", "127.0.0.2", "127.0.0.3", "127.0.0.4"]
 M, MB, STEPS_BEFORE, STEPS_TOTAL = 4, 1, 2, 4
 
 
+def scenario(mode):
+    """(world, model args, global micro-batches, templates factory, initial plan, pipelines expected after the loss)"""
+    from oobleck_b200.planning.pipeline_template import even_template
+    if mode == "replicas":
+        t = [even_template(4, 1), even_template(4, 2)]
+        return 4, MARGS, 4, t, [t[1], t[1]], [[2], [0, 1]]
+    if mode == "lone":        # one 4-stage pipeline without a replica: survives through the peer shadows
+        t = [even_template(4, 3), even_template(4, 4)]
+        return 4, MARGS, 4, t, [t[1]], [[0, 1, 2]]
+    big = dict(MARGS, num_hidden_layers=6)          # 8 stage layers
+    if mode == "replicas8":   # BASELINE config 4's shape: 2 replicas x 4 stages on 8 ranks -> 4 + 3
+        t = [even_template(8, 3), even_template(8, 4)]
+        return 8, big, 8, t, [t[1], t[1]], [[4, 5, 6], [0, 1, 2, 3]]
+    if mode == "lone8":       # BASELINE config 5's shape: one 8-stage pipeline -> the 7-stage template
+        t = [even_template(8, 7), even_template(8, 8)]
+        return 8, big, 8, t, [t[1]], [[0, 1, 2, 3, 4, 5, 6]]
+    raise ValueError(mode)
+
+
+def ips_of(world):
+    return [f"127.0.0.{i + 1}" for i in range(world)]
+
+
 def worker(rank, pipe, q, ready, mode):
     torch.set_num_threads(1)
     try:
@@ -35,6 +58,9 @@ def worker(rank, pipe, q, ready, mode):
         from oobleck_b200.execution.dataloader import SyntheticTokenDataset
         from oobleck_b200.execution.engine import JobArguments, ModelArguments, OobleckArguments, OobleckEngine
         from oobleck_b200.planning.pipeline_template import even_template
+        world, margs, M, templates, plan, pipelines_after = scenario(mode)
+        AGENT_IPS = ips_of(world)
+        victim = world - 1
         # every worker believes it runs on its own node: the reference's tests patch the same call (test_engine.py:676)
         patch("socket.gethostbyname", return_value=AGENT_IPS[rank]).start()
         real_tcpstore = torch.distributed.TCPStore
@@ -44,20 +70,14 @@ def worker(rank, pipe, q, ready, mode):
         patch("torch.distributed.TCPStore", local_store).start()
 
         args = OobleckArguments(job=JobArguments(microbatch_size=MB, global_microbatch_size=MB * M, steps=STEPS_TOTAL),
-                                model=ModelArguments(model_name="gpt2", model_tag="t", model_args=dict(MARGS)))
+                                model=ModelArguments(model_name="gpt2", model_tag="t", model_args=dict(margs)))
         ds = SyntheticTokenDataset(num_samples=256, seq_len=32, vocab_size=211, pin_memory=False)
-        if mode == "replicas":
-            templates = [even_template(4, 1), even_template(4, 2)]
-            plan = [templates[1], templates[1]]                              # ranks [0, 1] and [2, 3]
-        else:   # one 4-stage pipeline without a replica: survives through the peer shadows (BASELINE config 5 shape)
-            templates = [even_template(4, 3), even_template(4, 4)]
-            plan = [templates[1]]
         # worker_main's call sequence: ctor(local_rank, num_nodes, gpus_per_node, pipe, args) -> initialize_distributed
         # -> instantiate_pipelines -> train
         eng = OobleckEngine(0, len(AGENT_IPS), 1, pipe, args, dataset=ds, layer_cls=OracleLayer, templates=templates,
-                            backend="gloo", comm_timeout_s=20, peer_shadow=(mode == "lone"))
+                            backend="gloo", comm_timeout_s=20, peer_shadow=mode.startswith("lone"))
         eng.initialize_distributed()
-        assert eng._rank == rank and eng._world_size == 4 and eng._rank_map[AGENT_IPS[rank]] == [rank]
+        assert eng._rank == rank and eng._world_size == world and eng._rank_map[AGENT_IPS[rank]] == [rank]
         eng.instantiate_pipelines(M, plan=plan)
         assert eng._reconfiguration._reconfiguration_listener is not None    # engine.py:50-53
 
@@ -66,7 +86,7 @@ def worker(rank, pipe, q, ready, mode):
 
         def step_hook():
             if count["n"] == STEPS_BEFORE:
-                if rank == 3:
+                if rank == victim:
                     q.put((rank, "gone", None, None))
                     q.close(); q.join_thread()          # noqa: E702
                     os._exit(0)                         # the node dies: no goodbye, no barrier
@@ -77,11 +97,13 @@ def worker(rank, pipe, q, ready, mode):
         eng.train()
 
         new_ranks = [p._ranks for p in eng._reconfiguration._pipelines]
-        assert new_ranks == ([[2], [0, 1]] if mode == "replicas" else [[0, 1, 2]]), new_ranks
-        assert eng._dist_info.agent_ips == AGENT_IPS[:3] and eng._dist_info.world_size == 3
+        assert new_ranks == pipelines_after, new_ranks
+        assert eng._dist_info.agent_ips == AGENT_IPS[:victim] and eng._dist_info.world_size == world - 1
         layers = eng._pipeline.execution._layers
-        want = {0: [0, 1], 1: [2, 3], 2: [0, 1, 2, 3]} if mode == "replicas" else {0: [0, 1], 1: [2], 2: [3]}
-        assert sorted(l.layer_id for l in layers) == want[rank]
+        # ownership follows the template of the pipeline this rank ended up in
+        mine = next(p for p in eng._reconfiguration._pipelines if rank in p._ranks)
+        stage = mine._template.get_stages()[mine._ranks.index(rank)]
+        assert sorted(l.layer_id for l in layers) == list(stage._layer_indices)
         out = {l.layer_id: (l.flat_param.numpy().copy(), l.exp_avg.numpy().copy(), l.opt_step) for l in layers}
         q.put((rank, out, eng._reconfiguration.last_reconfiguration_seconds, len(eng.step_seconds)))
     except Exception:  # noqa: BLE001
@@ -90,15 +112,16 @@ def worker(rank, pipe, q, ready, mode):
         raise
 
 
-def never_failed_reference():
+def never_failed_reference(margs=MARGS, M=M):
     """Single process, all layers: steps 0..STEPS_BEFORE-1 on global batches 0.., then the sampler restarts (the new
     loaders start a fresh epoch-0 iterator) and the remaining steps consume global batches 0.. again."""
     from oobleck_b200.execution.dataloader import OobleckSampler, SyntheticTokenDataset
     from oobleck_b200.module.model import OobleckModel
     from oracle import gpt2 as og
     from oracle import optim as oo
-    model = OobleckModel("gpt2", {"input_ids": None, "attention_mask": None, "labels": None}, None, "t", dict(MARGS))
-    layers = og.build_layers(og.GPT2Dims(n_embd=64, n_head=1, n_layer=2, n_positions=32, vocab_size=211))
+    model = OobleckModel("gpt2", {"input_ids": None, "attention_mask": None, "labels": None}, None, "t", dict(margs))
+    layers = og.build_layers(og.GPT2Dims(n_embd=64, n_head=1, n_layer=margs["num_hidden_layers"], n_positions=32,
+                                         vocab_size=211))
     flats = [spec.init_flat() for spec in model.layers]
     for l, f in zip(layers, flats):
         og.load_flat_(l, f)
@@ -126,17 +149,20 @@ def never_failed_reference():
 
 
 @pytest.mark.timeout(600)
-@pytest.mark.parametrize("mode", ["replicas", "lone"])
+@pytest.mark.parametrize("mode", ["replicas", "lone", "replicas8", "lone8"])
 def test_engine_driven_through_agent_pipe_survives_a_dead_node(mode):
     """``lone``: the same death in a single 4-stage pipeline.  The reference raises "No alive ranks for the layer"
     (engine.py:263-269, its test at tests/execution/test_engine.py:1015-1019); with peer shadows the survivors re-split
     into 3 stages -- layers 1 and 2 move between survivors, layer 3 (parameters AND Adam moments) comes out of the mirror
     its neighbour kept -- and the run still matches the never-failed oracle."""
     from oobleck_b200.execution.engine import DistributionInfo
+    world, margs, M_, _, _, _ = scenario(mode)
+    AGENT_IPS = ips_of(world)
+    victim = world - 1
     ctx = mp.get_context("spawn")
     q, ready = ctx.Queue(), ctx.Queue()
     pipes = [ctx.Pipe(duplex=True) for _ in AGENT_IPS]
-    procs = [ctx.Process(target=worker, args=(r, pipes[r][1], q, ready, mode)) for r in range(4)]
+    procs = [ctx.Process(target=worker, args=(r, pipes[r][1], q, ready, mode)) for r in range(world)]
     for p in procs:
         p.start()
 
@@ -149,32 +175,33 @@ def test_engine_driven_through_agent_pipe_survives_a_dead_node(mode):
         for pipe, _ in pipes:
             pipe.send(DistributionInfo(list(AGENT_IPS), len(AGENT_IPS)))
         broadcast_rank0_port(pipes)
-        for _ in range(3):                             # the three survivors are inside the step the dead node misses
+        for _ in range(world - 1):                     # the survivors are inside the step the dead node misses
             ready.get(timeout=300)
-        procs[3].join(timeout=60)                      # the node is really gone
-        for pipe, _ in pipes[:3]:
-            pipe.send(AGENT_IPS[3])                    # test_engine.py:1045-1047
-        broadcast_rank0_port(pipes[:3])
+        procs[victim].join(timeout=60)                 # the node is really gone
+        for pipe, _ in pipes[:victim]:
+            pipe.send(AGENT_IPS[victim])               # test_engine.py:1045-1047
+        broadcast_rank0_port(pipes[:victim])
 
     t = threading.Thread(target=agent, daemon=True)
     t.start()
     results = {}
-    for _ in range(4):
+    for _ in range(world):
         r = q.get(timeout=500)
         results[r[0]] = r
     t.join(timeout=60)
     for p in procs:
         p.join(timeout=60)
-    assert results[3][1] == "gone"
-    for r in (0, 1, 2):
+    assert results[victim][1] == "gone"
+    survivors = range(victim)
+    for r in survivors:
         assert not isinstance(results[r][1], str), results[r][1]
         assert results[r][3] == STEPS_TOTAL            # every survivor completed all steps (one of them twice started)
         assert results[r][2] is not None and results[r][2] < 60
-    flats, ms = never_failed_reference()
-    for r in (0, 1, 2):
+    flats, ms = never_failed_reference(margs, M_)
+    for r in survivors:
         for lid, (param, exp_avg, opt_step) in results[r][1].items():
             assert opt_step == STEPS_TOTAL             # moved layers brought their AdamW step count along
             # summation order differs (replicas reduce, one process accumulates): Adam turns 1e-8 gradient noise into ~1e-7 steps
             torch.testing.assert_close(torch.from_numpy(param), flats[lid], rtol=1e-4, atol=2e-6)
             torch.testing.assert_close(torch.from_numpy(exp_avg), ms[lid], rtol=1e-3, atol=1e-7)
-    print("reconfiguration seconds (notification -> pipelines rebuilt):", {r: results[r][2] for r in (0, 1, 2)})
+    print("reconfiguration seconds (notification -> pipelines rebuilt):", {r: results[r][2] for r in survivors})
