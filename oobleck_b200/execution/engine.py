@@ -207,7 +207,9 @@ class DataParallelEngine:
         engine.py:404-412, layer.py:290-291.)  One bucket per layer: the flat gradient is already contiguous."""
         pgs = self._groups_of(layer)
         if pgs is None:
-            return
+            if not getattr(layer, "sharded", False):
+                return
+            pgs = {}       # no replica, but the stage shards the layer: its reduce-scatter starts now all the same
         import ctypes as C
 
         from .. import lib as L
@@ -231,6 +233,10 @@ class DataParallelEngine:
                 layer.reduce_gradients(pgs)
         for w in self._pending:
             w.wait()                          # the compute stream waits for the NCCL stream; the host does not block
+        if self._overlapped and self._comm_stream is not None:
+            # collectives that were already waited for on the communication stream itself (a sharded layer's
+            # reduce-scatter, which its cross-replica all-reduce consumes there)
+            torch.cuda.current_stream().wait_stream(self._comm_stream)
         self._pending.clear()
         self._overlapped.clear()
 
@@ -798,7 +804,8 @@ class OobleckEngine:
         ex = self._pipeline.execution
         overlap = (self._agent_pipe is None and self._pipeline.device.type == "cuda"
                    and os.environ.get("OOB_DP_OVERLAP", "1") == "1"
-                   and any(self._dp_engine._groups_of(l) is not None for l in ex._layers))
+                   and any(self._dp_engine._groups_of(l) is not None or getattr(l, "sharded", False)
+                           for l in ex._layers))
         ex.grad_ready_hook = self._dp_engine.layer_ready if overlap else None
 
     def distribute_microbatches(self, templates: list[PipelineTemplate], global_num_microbatch: int) -> list[int]:

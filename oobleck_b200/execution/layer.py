@@ -9,8 +9,10 @@ Replaces oobleck/execution/layer.py:40-291.  The reference wraps a deep-copied f
 * per pipe-buffer activation contexts that the hand-written forward fills and the hand-written backward consumes
   (no autograd graph, no checkpoint recompute -- layer.py:93-94 re-runs every block forward in backward).
 
-FSDP sharding inside a stage (layer.py:96-142, 167-225) is out of scope for this round: every BASELINE config runs
-one GPU per stage, which is the reference's ``NO_SHARD`` branch (layer.py:100-102).
+A stage that owns several GPUs shards this state across them (layer.py:96-142, 167-225 -- FSDP ``FULL_SHARD``): see
+``sharding.py`` for the B200 schedule of it (one in-place all-gather and one reduce-scatter per layer and STEP).  Every
+BASELINE config runs one GPU per stage, the reference's ``NO_SHARD`` branch (layer.py:100-102), which allocates exactly
+what it did before sharding existed.
 """
 from __future__ import annotations
 
@@ -23,6 +25,7 @@ import torch
 
 from .. import lib as L
 from ..module.model import StageLayerSpec
+from .sharding import ShardedFlatState, shard_param
 
 
 from ..lib import OobBlockCtx, OobBwdScratch, OobDims, OobHeadCtx, OobLayerParams  # noqa: E402
@@ -110,10 +113,15 @@ class HiddenGrad:
 class _ParamHandle:
     """Just enough of FSDP's FlatParamHandle for the callers that reach through ``layer._param_handle``."""
 
-    def __init__(self, flat_param: torch.Tensor, process_group):
+    def __init__(self, flat_param: torch.Tensor, process_group, sharded: bool = False):
         self.flat_param = flat_param
         self.process_group = process_group
-        self._sharding_strategy = "NO_SHARD"   # layer.py:100-102 when the per-layer group has one rank
+        # layer.py:100-102: FULL_SHARD when the per-layer group has more than one rank
+        self._sharding_strategy = "FULL_SHARD" if sharded else "NO_SHARD"
+
+    @property
+    def uses_sharded_strategy(self) -> bool:
+        return self._sharding_strategy != "NO_SHARD"
 
 
 class Layer:
@@ -121,6 +129,7 @@ class Layer:
 
     device_type = "cuda"
     supports_deferred_init = True     # accepts init_values=False (see __init__)
+    supports_sharding = True          # accepts columns=<shard columns of the rank grid> (sharding.py)
 
     @classmethod
     def make_workspace(cls, model, microbatch_size: int, device) -> "StageWorkspace":
@@ -130,7 +139,7 @@ class Layer:
     def __init__(self, layer_id: int, layer: StageLayerSpec, process_group=None, pre_stream=None, post_stream=None, *,
                  microbatch_size: int, num_pipe_buffers: int, workspace: StageWorkspace | None = None,
                  nsplit: int = 3, device: torch.device | None = None, seq_len: int | None = None,
-                 bwd_fp16: bool | None = None, init_values: bool = True):
+                 bwd_fp16: bool | None = None, init_values: bool = True, columns: int = 1):
         L.load()  # fail loudly if the CUDA extension is missing
         if not torch.cuda.is_available():
             raise L.OobleckB200Error("oobleck_b200.Layer needs a CUDA device (there is no CPU path)")
@@ -140,8 +149,6 @@ class Layer:
         self.device = device or torch.device("cuda", torch.cuda.current_device())
         self._rank_index = process_group.rank_index() if hasattr(process_group, "rank_index") else 0
         self._group_size = process_group.size() if hasattr(process_group, "size") else 1
-        if self._group_size != 1:
-            raise NotImplementedError("intra-stage FSDP sharding (layer.py:96-225) is out of scope this round")
         self.pre_stream, self.post_stream = pre_stream, post_stream
         self.nsplit = nsplit
         self.mb = microbatch_size
@@ -154,13 +161,13 @@ class Layer:
         self.plane_stride = _round8(n)
         # ``init_values=False``: the layer is built to RECEIVE its state (reconfiguration moves parameters and moments
         # into it); generating 30-80 M random numbers per layer on the host was most of the rebuild time
-        flat = layer.init_flat().to(self.device) if init_values else \
-            torch.empty(n, dtype=torch.float32, device=self.device)
-        flat.requires_grad_(False)
-        flat.grad = torch.zeros(n, dtype=torch.float32, device=self.device)
-        self._param_handle = _ParamHandle(flat, process_group)
-        self.exp_avg = torch.zeros(n, dtype=torch.float32, device=self.device)
-        self.exp_avg_sq = torch.zeros(n, dtype=torch.float32, device=self.device)
+        st = self._state = ShardedFlatState(n, process_group, max(columns, self._group_size), self.device)
+        if init_values:     # deterministic: every holder of a sharded layer starts from the same full vector
+            st.install_full_(layer.init_flat())
+        else:
+            st.stale = st.sharded   # the shard arrives from another rank; the rest is gathered on first use
+        self._param_handle = _ParamHandle(st.param_shard, process_group, st.sharded)
+        self.exp_avg, self.exp_avg_sq = st.exp_avg, st.exp_avg_sq
         # forward GEMMs read fp16 x 2 planes (3 tensor-core products, fp32-grade for bounded-range operands); the
         # bf16 x 3 planes stay for the backward GEMMs: 5-plane buffers (include/oobleck_b200.h)
         self.fwd_fp16 = 1 if nsplit == 3 else 0
@@ -199,42 +206,93 @@ class Layer:
 
     @property
     def flat_grad(self) -> torch.Tensor:
+        """Gradient of ``flat_param``: the whole vector, or -- sharded -- this rank's reduce-scattered shard."""
         return self._param_handle.flat_param.grad
+
+    @property
+    def sharded(self) -> bool:
+        return self._state.sharded
+
+    @property
+    def full_param(self) -> torch.Tensor:
+        """The ``numel`` parameters the kernels read (== ``flat_param`` unless the stage shards the layer)."""
+        return self._state.compute_param
+
+    @property
+    def full_grad(self) -> torch.Tensor:
+        """The ``numel`` gradients the kernels accumulate into, local to this rank."""
+        return self._state.compute_grad
 
     def planes_ptr(self) -> int:
         return self.planes.data_ptr() if self.planes is not None and self.planes.numel() else 0
 
-    def _params_struct(self) -> OobLayerParams:
-        return OobLayerParams(self.flat_param.data_ptr(), self.planes_ptr(), self.plane_stride,
-                              self.flat_grad.data_ptr())
+    def optimizer_planes_ptr(self) -> int:
+        """Planes the fused AdamW refreshes while it writes the parameters: only when the whole vector is updated
+        here.  A sharded layer splits its planes after the next all-gather instead (``unshard_params``)."""
+        return 0 if self._state.sharded else self.planes_ptr()
 
-    def refresh_planes(self) -> None:
+    def _params_struct(self) -> OobLayerParams:
+        return OobLayerParams(self._state.full_param.data_ptr(), self.planes_ptr(), self.plane_stride,
+                              self._state.full_grad.data_ptr())
+
+    def _split_planes(self) -> None:
         if not self.nplanes:
             return
-        L.call("oob_split_planes", C.c_void_p(self.flat_param.data_ptr()), C.c_void_p(self.planes.data_ptr()),
+        L.call("oob_split_planes", C.c_void_p(self._state.full_param.data_ptr()), C.c_void_p(self.planes.data_ptr()),
                self.numel, self.plane_stride, self.nplanes, _stream())
 
+    def refresh_planes(self) -> None:
+        """``flat_param`` was written from outside (a received state): make the copies the kernels read current.  A
+        sharded layer only notes that its gathered copy is out of date; the gather itself is a collective and runs
+        when every holder reaches its next forward."""
+        if self._state.sharded:
+            self._state.stale = True
+            return
+        self._split_planes()
+
     def load_flat_(self, flat: torch.Tensor) -> None:
-        """Install explicit weights (parity tests, reconfiguration copies)."""
+        """Install explicit weights -- the WHOLE vector, on every holder (parity tests, reconfiguration copies)."""
         assert flat.numel() == self.numel
-        self.flat_param.copy_(flat.to(self.device, torch.float32))
-        self.refresh_planes()
+        self._state.install_full_(flat)
+        self._split_planes()
+
+    # -- sharding (layer.py:117-165) -----------------------------------------------------------------------------------
+    def unshard_params(self, state=None) -> None:
+        """layer.py:117-133.  Gathers only if the shards changed since the last gather (once per step); the reference
+        gathers before every forward and every backward."""
+        if self._state.unshard():
+            self._split_planes()
+
+    def reshard_params(self) -> None:
+        """layer.py:135-144.  Nothing to free: the gathered copy stays resident until the optimizer invalidates it
+        (sharding.py)."""
+
+    def prepare_gradient_for_optim(self) -> None:
+        """FSDP's name for "make ``flat_param.grad`` the gradient the optimizer consumes" (layer.py:276): for a sharded
+        layer, the SUM reduce-scatter of the locally accumulated gradient, unless it already ran for this step."""
+        self._state.scatter_grads()
+
+    def _shard_param(self, tensor: torch.Tensor, number: int) -> list[torch.Tensor]:   # layer.py:262-270
+        return shard_param(tensor, number)
 
     def state_tensors(self) -> list[torch.Tensor]:
         """What has to move when this layer changes owner: parameters and both Adam moments (the reference moves
-        ``flat_param`` only, engine.py:284-306, and silently restarts the moments)."""
+        ``flat_param`` only, engine.py:284-306, and silently restarts the moments).  Sharded: this rank's shards."""
         return [self.flat_param, self.exp_avg, self.exp_avg_sq]
 
     def adopt_state_(self, other: "Layer") -> None:
         """Take over parameters, gradients-in-progress, moments and step count of ``other`` (same layer id, same
         device): used when a reused layer needs more pipe buffers than it was built with."""
         assert other.numel == self.numel and other.layer_id == self.layer_id
-        self.flat_param.copy_(other.flat_param)
-        self.flat_grad.copy_(other.flat_grad)
+        assert other._state.padded == self._state.padded and other._state.k == self._state.k
+        self._state.full_param.copy_(other._state.full_param)
+        self._state.full_grad.copy_(other._state.full_grad)
         self.exp_avg.copy_(other.exp_avg)
         self.exp_avg_sq.copy_(other.exp_avg_sq)
+        self._state.stale = other._state.stale
         self.opt_step = other.opt_step
-        self.refresh_planes()
+        if not self._state.stale:
+            self._split_planes()
 
     def grow_pipe_buffers(self, num_pipe_buffers: int) -> None:
         """Re-allocate the per-slot activation contexts for a deeper schedule; parameters and optimizer state are
@@ -244,19 +302,26 @@ class Layer:
             self._alloc_contexts()
 
     def zero_grad(self) -> None:
-        self.flat_grad.zero_()
+        self._state.zero_grad()
 
     def remove_tensors(self) -> None:  # layer.py:66-69
         empty = torch.tensor([], device=self.device)
         if self.flat_param.grad is not None:
             self.flat_param.grad = None
         self.flat_param.data = empty
+        st = self._state
+        st.full_param = st.full_grad = st.grad_shard = st.reduce_buffer = st.exp_avg = st.exp_avg_sq = empty
         self.planes = self.exp_avg = self.exp_avg_sq = empty
         self.ctx_tensors, self.out = [], []
 
     @classmethod
     def create_layer_from_layer(cls, existing_layer: "Layer", process_group,
                                 num_pipe_buffers: int | None = None) -> "Layer":  # layer.py:41-64
+        if existing_layer._state.sharded or (hasattr(process_group, "size") and process_group.size() > 1):
+            old = getattr(existing_layer._param_handle.process_group, "ranks", None)
+            if old != getattr(process_group, "ranks", None):
+                raise NotImplementedError(f"layer {existing_layer.layer_id}: re-sharding a live layer over a different "
+                                          f"set of stage ranks ({old} -> {getattr(process_group, 'ranks', None)})")
         existing_layer._param_handle.process_group = process_group
         if num_pipe_buffers is not None:
             existing_layer.grow_pipe_buffers(num_pipe_buffers)   # never shrinks; weights / moments stay in place
@@ -304,12 +369,14 @@ class Layer:
         """tuple in, tuple out, like the fx shards (sharding.py:86-96)."""
         kind = self.spec.kind
         self.saved_in[buffer_id] = inputs
+        if self._state.sharded:
+            self.unshard_params()
         if kind == "embed":
             input_ids, _attention_mask, labels = inputs
             assert input_ids.dtype == torch.int64 and input_ids.is_contiguous()
             y = self.out[buffer_id]
             E = self.spec.n_embd
-            w = self.flat_param
+            w = self._state.full_param
             L.call("oob_embedding_fwd", C.c_void_p(input_ids.data_ptr()), C.c_void_p(w.data_ptr()),
                    C.c_void_p(w.data_ptr() + self.spec.vocab_size * E * 4), C.c_void_p(y.data_ptr()),
                    self.mb * self.T, self.T, E, _stream())
@@ -335,6 +402,8 @@ class Layer:
         kind = self.spec.kind
         inputs = self.saved_in[buffer_id]
         ws = self.workspace
+        if self._state.sharded:
+            self.unshard_params()     # pre_backward_hook (layer.py:159-165); a no-op unless the shards changed
         p = self._params_struct()
         if kind == "head":
             hidden = inputs[0]
@@ -361,7 +430,7 @@ class Layer:
             return HiddenGrad(dx, dxp)
         # embedding
         input_ids = inputs[0]
-        g = self.flat_grad
+        g = self._state.full_grad
         L.call("oob_embedding_bwd", C.c_void_p(input_ids.data_ptr()), C.c_void_p(grad.grad.data_ptr()),
                C.c_void_p(g.data_ptr()), C.c_void_p(g.data_ptr() + self.spec.vocab_size * E * 4), self.mb, self.T, E,
                (1.0 / self.loss_scale) if self.bwd_fp16 else 1.0, _stream())
@@ -369,13 +438,18 @@ class Layer:
 
     # -- data parallel -----------------------------------------------------------------------------------------------
     def reduce_gradients(self, process_groups: dict, async_op: bool = False):
-        """layer.py:272-291: SUM all-reduce of the flat gradient over the cross-replica group(s); never averaged.
-        With one GPU per stage there is exactly one (fsdp_index -> group) entry.  ``async_op``: return the NCCL work
-        handles instead of waiting (the caller overlaps the reduction with the rest of the backward pass)."""
-        assert len(process_groups) == 1, "sharded DP groups need the FSDP path (out of scope this round)"
+        """layer.py:272-291: SUM all-reduce of the gradient over the cross-replica group(s); never averaged.  With one
+        GPU per stage there is exactly one (fsdp_index -> group) entry and the whole flat gradient is reduced.  A
+        sharded layer first reduce-scatters over its stage (once per step) and reduces its shard; a layer that shares
+        shard columns with a sharded replica reduces column by column (``ShardedFlatState.dp_chunks``).  ``async_op``:
+        return the NCCL work handles instead of waiting (the caller overlaps the reduction with the rest of the
+        backward pass)."""
         works = []
-        for _, pg in process_groups.items():
-            w = torch.distributed.all_reduce(self.flat_grad, group=getattr(pg, "group", pg), async_op=async_op)
+        w = self._state.scatter_grads(async_op=async_op)
+        if w is not None and async_op:
+            w.wait()     # stream-side: the cross-replica reduction below (another communicator) reads the shard
+        for chunk, pg in self._state.dp_chunks(process_groups):
+            w = torch.distributed.all_reduce(chunk, group=getattr(pg, "group", pg), async_op=async_op)
             if async_op:
                 works.append(w)
         return works

@@ -32,10 +32,15 @@ class FusedAdamW:
             # the bias correction follows the layer's own moments (torch keeps ``step`` per parameter too): a layer
             # that arrives through a reconfiguration brings its count with it, a fresh optimizer does not reset it
             l.opt_step = getattr(l, "opt_step", 0) + 1
+            # a layer sharded over its stage (sharding.py): the update runs on this rank's shard of parameters,
+            # reduce-scattered gradient and moments; the planes are split after the next all-gather, not here
+            l.prepare_gradient_for_optim()
             L.call("oob_adamw_step", C.c_void_p(l.flat_param.data_ptr()), C.c_void_p(l.flat_grad.data_ptr()),
                    C.c_void_p(l.exp_avg.data_ptr()), C.c_void_p(l.exp_avg_sq.data_ptr()),
-                   C.c_void_p(l.planes_ptr()), l.plane_stride, l.nplanes, l.numel, float(g["lr"]), g["betas"][0],
-                   g["betas"][1], g["eps"], g["weight_decay"], l.opt_step, stream)
+                   C.c_void_p(l.optimizer_planes_ptr()), l.plane_stride, l.nplanes, l.flat_param.numel(),
+                   float(g["lr"]), g["betas"][0], g["betas"][1], g["eps"], g["weight_decay"], l.opt_step, stream)
+            if l.sharded:
+                l.refresh_planes()    # marks the gathered copy out of date
             self.state[l.flat_param] = {"step": l.opt_step, "exp_avg": l.exp_avg, "exp_avg_sq": l.exp_avg_sq}
 
     def zero_grad(self) -> None:

@@ -369,7 +369,7 @@ class OobleckPipeline:
     """pipeline.py:430-623."""
 
     def __init__(self, pipeline_id: int, pipeline_template, ranks: list[int], dataloader: OobleckDataLoader, step: int,
-                 training_args, *, layer_cls=None, transport_cls=None, nsplit: int = 3):
+                 training_args, *, layer_cls=None, transport_cls=None, nsplit: int = 3, stage_group_factory=None):
         self._pipeline_id = pipeline_id
         self._template = pipeline_template
         self._ranks = ranks
@@ -379,6 +379,7 @@ class OobleckPipeline:
         self._layer_cls = layer_cls
         self._transport_cls = transport_cls
         self._nsplit = nsplit
+        self._stage_group_factory = stage_group_factory    # ranks -> communicator of a multi-GPU stage (tests)
         if layer_cls is not None and hasattr(layer_cls, "device_type"):
             self.device = torch.device(layer_cls.device_type)
         else:
@@ -477,11 +478,36 @@ class OobleckPipeline:
         return FusedAdamW, WarmupLR
 
     def initialize_distributed_fsdp(self):
-        """Per-layer groups (pipeline.py:565-580) -- membership only, no communicator is created."""
+        """Per-layer groups (pipeline.py:565-580).  A layer held by one rank gets membership only; a stage of several
+        GPUs shards its layers (layer.py:100-102) and needs a communicator -- ONE per stage, shared by its layers,
+        created by its members only (the reference calls ``dist.new_group`` once per layer, on every rank).  Holders
+        are listed in rank-grid order, so shard ``j`` of a layer covers the shard columns (``fsdp_index``) where its
+        rank stands in the grid row (engine.py:374-384)."""
         me = _my_rank()
-        self._per_layer_pgs: dict[int, RankGroup] = {
-            layer_id: RankGroup(list(set(ranks)), me) for layer_id, ranks in self.rank_grid.items()}
+        self._per_layer_pgs: dict[int, RankGroup] = {}
+        widths = set()
+        for layer_id, ranks in self.rank_grid.items():
+            holders = list(dict.fromkeys(ranks))
+            widths.add(len(holders))
+            comm = None
+            if len(holders) > 1 and me in holders:
+                comm = self._stage_communicator(holders)
+            self._per_layer_pgs[layer_id] = RankGroup(holders, me, comm)
+        if len(widths) > 1:
+            # the reference wires ONE previous and ONE next rank per rank (pipeline.py:602-610): a stage narrower than
+            # its neighbour would leave sends without a receiver
+            raise NotImplementedError(f"stages of different widths inside one pipeline ({sorted(widths)} GPUs): every "
+                                      "stage of a pipeline must own the same number of GPUs")
         self.execution = None
+
+    def _stage_communicator(self, ranks: list[int]):
+        if self._stage_group_factory is not None:
+            return self._stage_group_factory(ranks)
+        from .engine import _COMMUNICATORS, _new_member_group
+        key = tuple(sorted(ranks))
+        if key not in _COMMUNICATORS:
+            _COMMUNICATORS[key] = _new_member_group(key, None)
+        return _COMMUNICATORS[key]
 
     def initialize_distributed_pipeline(self):
         """Per shard column wiring (pipeline.py:582-617): who is my previous / next stage."""
@@ -546,6 +572,11 @@ class OobleckPipeline:
             extra = {}
             if existing_pipeline is not None and getattr(layer_cls, "supports_deferred_init", False):
                 extra["init_values"] = False      # a layer that appears during a reconfiguration receives its state
+            columns = len(self.rank_grid[layer_id])
+            if columns > 1:
+                if not getattr(layer_cls, "supports_sharding", False):
+                    raise NotImplementedError(f"{layer_cls.__name__} cannot hold {columns} shard columns")
+                extra["columns"] = columns
             layers.append(layer_cls(layer_id, model.layers[layer_id], pg, None, None, microbatch_size=mb,
                                     num_pipe_buffers=num_pipe_buffers, workspace=workspace, nsplit=self._nsplit,
                                     **extra))

@@ -8,15 +8,16 @@ import torch
 
 from oobleck_b200.execution.layer import HiddenGrad
 from oobleck_b200.execution.optimizer import WarmupLR
+from oobleck_b200.execution.sharding import ShardedFlatState, shard_param
 from oracle import gpt2 as og
 from oracle import optim as oo
 
 
 class _Handle:
-    def __init__(self, flat):
+    def __init__(self, flat, process_group=None, sharded=False):
         self.flat_param = flat
-        self.process_group = None
-        self._sharding_strategy = "NO_SHARD"
+        self.process_group = process_group
+        self._sharding_strategy = "FULL_SHARD" if sharded else "NO_SHARD"
 
 
 class OracleAdamW:
@@ -30,16 +31,15 @@ class OracleAdamW:
         self._step += 1
         g = self.param_groups[0]
         for l in self.layers:
-            l.sync_grads()
+            l.prepare_gradient_for_optim()
             l.opt_step += 1
             oo.adamw_step_(l.flat_param, l.flat_param.grad, l.exp_avg, l.exp_avg_sq, l.opt_step, g["lr"], g["betas"][0],
                            g["betas"][1], g["eps"], g["weight_decay"])
-            og.load_flat_(l.module, l.flat_param)
+            l.refresh_planes()
 
     def zero_grad(self):
         for l in self.layers:
-            l.module.zero_grad()
-            l.flat_param.grad.zero_()
+            l.zero_grad()
 
 
 class OracleLayer:
@@ -52,21 +52,27 @@ class OracleLayer:
     fast_init = False      # bench.py's CPU arm: constant weights (timing does not depend on the values; drawing 1.5 G
                            # normal deviates on the host costs more than the sample itself)
 
+    supports_sharding = True   # same intra-stage sharding as the CUDA layer (oobleck_b200/execution/sharding.py)
+
     def __init__(self, layer_id, spec, process_group=None, pre_stream=None, post_stream=None, *, microbatch_size,
-                 num_pipe_buffers, workspace=None, nsplit=3):
+                 num_pipe_buffers, workspace=None, nsplit=3, columns=1):
         self.layer_id = layer_id
+        spec = getattr(spec, "spec", spec)
         self.spec = spec
         self.num_pipe_buffers = num_pipe_buffers
         d = og.GPT2Dims(n_embd=spec.n_embd, n_head=spec.n_head, n_layer=spec.n_layer, n_positions=spec.n_positions,
                         vocab_size=spec.vocab_size, layer_norm_epsilon=spec.layer_norm_epsilon)
         self.module = {"embed": og.EmbeddingLayer, "block": og.BlockLayer, "head": og.HeadLayer}[spec.kind](d)
         flat = torch.full((spec.num_params,), 0.01) if self.fast_init else spec.init_flat()
-        og.load_flat_(self.module, flat)
-        flat.grad = torch.zeros_like(flat)
-        self._param_handle = _Handle(flat)
-        self.exp_avg, self.exp_avg_sq = torch.zeros_like(flat), torch.zeros_like(flat)
+        k = process_group.size() if hasattr(process_group, "size") else 1
+        st = self._state = ShardedFlatState(spec.num_params, process_group, max(columns, k), "cpu")
+        st.install_full_(flat)
+        og.load_flat_(self.module, st.compute_param)
+        self._param_handle = _Handle(st.param_shard, process_group, st.sharded)
+        self.exp_avg, self.exp_avg_sq = st.exp_avg, st.exp_avg_sq
         self.saved = [None] * num_pipe_buffers
         self.opt_step = 0
+        self._grads_final = False     # this step's gradient went through a collective: the module's copy is outdated
 
     @classmethod
     def create_layer_from_layer(cls, existing, pg, num_pipe_buffers=None):
@@ -87,20 +93,60 @@ class OracleLayer:
         self.sync_grads()
         return self._param_handle.flat_param.grad
 
+    @property
+    def sharded(self):
+        return self._state.sharded
+
+    @property
+    def full_param(self):
+        return self._state.compute_param
+
+    @property
+    def full_grad(self):
+        self.sync_grads()
+        return self._state.compute_grad
+
     def sync_grads(self):
-        self._param_handle.flat_param.grad.copy_(og.flat_grads(self.module))
+        """autograd accumulates in the module; the flat vector follows until a collective has rewritten it"""
+        if not self._grads_final:
+            self._state.compute_grad.copy_(og.flat_grads(self.module))
+
+    def zero_grad(self):
+        self.module.zero_grad()
+        self._state.zero_grad()
+        self._grads_final = False
 
     def load_flat_(self, flat):
-        self.flat_param.copy_(flat)
-        og.load_flat_(self.module, flat)
+        self._state.install_full_(flat)
+        og.load_flat_(self.module, self._state.compute_param)
 
     def refresh_planes(self):
-        og.load_flat_(self.module, self.flat_param)
+        if self._state.sharded:
+            self._state.stale = True
+        else:
+            og.load_flat_(self.module, self._state.compute_param)
+
+    def unshard_params(self, state=None):
+        if self._state.unshard():
+            og.load_flat_(self.module, self._state.compute_param)
+
+    def reshard_params(self):
+        pass
+
+    def prepare_gradient_for_optim(self):
+        self.sync_grads()
+        if self._state.sharded:
+            self._state.scatter_grads()
+            self._grads_final = True
+
+    def _shard_param(self, tensor, number):
+        return shard_param(tensor, number)
 
     def remove_tensors(self):
         pass
 
     def __call__(self, inputs, buffer_id=0, total_loss=None):
+        self.unshard_params()
         ins = tuple(t.detach().requires_grad_(t.is_floating_point()) for t in inputs)
         outs = self.module(*ins)
         self.saved[buffer_id] = (ins, outs)
@@ -121,12 +167,7 @@ class OracleLayer:
         return HiddenGrad(x.grad) if x.is_floating_point() else None
 
     def reduce_gradients(self, process_groups):
-        self.sync_grads()
-        for _, pg in process_groups.items():
-            torch.distributed.all_reduce(self._param_handle.flat_param.grad, group=getattr(pg, "group", pg))
-        # write the reduced gradient back into the module
-        off = 0
-        for p in self.module.parameters():
-            n = p.numel()
-            p.grad = self._param_handle.flat_param.grad[off:off + n].view_as(p).clone()
-            off += n
+        self.prepare_gradient_for_optim()
+        for chunk, pg in self._state.dp_chunks(process_groups):
+            torch.distributed.all_reduce(chunk, group=getattr(pg, "group", pg))
+        self._grads_final = True

@@ -39,8 +39,14 @@ def worker(rank, world, port, mode, M, mb, steps, q):
                                 model=ModelArguments(model_name="gpt2", model_tag="t", model_args=dict(MARGS)))
         ds = SyntheticTokenDataset(num_samples=256, seq_len=128, vocab_size=1000)
         templates = [even_template(6, 2)] if mode == "pp" else [even_template(6, 1)]
-        eng = OobleckEngine(rank, world, 1, None, args, dataset=ds, templates=templates,
-                            transport_cls=NvlinkRingTransport)
+        if mode == "fsdp":    # ONE stage that owns both GPUs of a node: every layer sharded 2-way (layer.py:100-102)
+            from oobleck_b200.planning.pipeline_template import PipelineTemplate, StageExecutionResult
+            templates = [PipelineTemplate([StageExecutionResult(range(6), 2)], 0.0, 6, 1, 2)]
+            eng = OobleckEngine(rank, 1, 2, None, args, dataset=ds, templates=templates,
+                                transport_cls=NvlinkRingTransport)
+        else:
+            eng = OobleckEngine(rank, world, 1, None, args, dataset=ds, templates=templates,
+                                transport_cls=NvlinkRingTransport)
         eng.initialize_distributed("nccl")
         eng.instantiate_pipelines(M)
         totals = []
@@ -50,6 +56,14 @@ def worker(rank, world, port, mode, M, mb, steps, q):
             totals.append(float(tl) if tl is not None else None)
         torch.cuda.synchronize()
         out = {l.layer_id: l.flat_param.cpu().numpy().copy() for l in eng._pipeline.execution._layers}
+        if mode == "fsdp":
+            for l in eng._pipeline.execution._layers:
+                st = l._state
+                assert l.sharded and (st.scatters, st.gathers) == (steps, steps - 1), (st.scatters, st.gathers)
+                # the gathered copy and the planes follow the last update once the next forward asks for them
+                l.unshard_params()
+                out[l.layer_id] = (st.lo, l.flat_param.cpu().numpy().copy(), l.full_param.cpu().numpy().copy(),
+                                   l.exp_avg.cpu().numpy().copy())
         q.put((rank, out, totals, None))
         dist.barrier()
         dist.destroy_process_group()
@@ -59,7 +73,7 @@ def worker(rank, world, port, mode, M, mb, steps, q):
         raise
 
 
-def reference_run(M, mb, steps, num_pipelines):
+def reference_run(M, mb, steps, num_pipelines, grad_scale=1.0, return_moments=False):
     sys.path.insert(0, ROOT)
     from oobleck_b200.execution.dataloader import OobleckSampler, SyntheticTokenDataset
     from oobleck_b200.module.model import OobleckModel
@@ -91,8 +105,10 @@ def reference_run(M, mb, steps, num_pipelines):
                 tot[pi] += float(x[0].detach())
         losses.append(tot)
         for i, l in enumerate(layers):
-            oo.adamw_step_(flats[i], og.flat_grads(l), ms[i], vs[i], step + 1, lrs[step])
+            oo.adamw_step_(flats[i], og.flat_grads(l) * grad_scale, ms[i], vs[i], step + 1, lrs[step])
             og.load_flat_(l, flats[i])
+    if return_moments:
+        return flats, losses, ms
     return flats, losses
 
 
@@ -137,3 +153,30 @@ def test_two_replicas_nccl_allreduce():
             assert err < 1e-4, (lid, float(err))
         want = sum(t[rank] for t in losses)
         assert abs(totals[-1] - want) < 1e-4 * abs(want)
+
+
+def test_stage_sharded_over_two_gpus_nccl():
+    """one stage on 2 GPUs.  Every layer keeps half of its parameters and moments per GPU, gathers them in
+    place once per step and reduce-scatters its gradient once per step (overlapped: the hook of the last micro-batch
+    backward starts it on the communication stream).  Both shard columns run the pipeline's micro-batches and the
+    reduce-scatter SUMs (reference semantics, layer.py:202-206): the update sees twice the gradient."""
+    M, mb, steps = 4, 2, 3
+    results = run("fsdp", M, mb, steps)
+    flats, losses, ms = reference_run(M, mb, steps, 1, grad_scale=2.0, return_moments=True)
+    ref_cum = list(itertools.accumulate(sum(t) for t in losses))
+    for rank, out, totals, _ in results:
+        assert sorted(out) == list(range(6))
+        for lid, (lo, shard, full, m) in out.items():
+            n = flats[lid].numel()
+            want = torch.zeros(max(n, lo + shard.size)); want[:n] = flats[lid]
+            want_m = torch.zeros_like(want); want_m[:n] = ms[lid]
+            scale = flats[lid].abs().max()
+            assert (torch.from_numpy(shard) - want[lo:lo + shard.size]).abs().max() / scale < 1e-4, lid
+            assert (torch.from_numpy(full) - flats[lid]).abs().max() / scale < 1e-4, lid
+            assert (torch.from_numpy(m) - want_m[lo:lo + m.size]).abs().max() / ms[lid].abs().max() < 1e-3, lid
+        for got, want in zip(totals, ref_cum):
+            assert abs(got - want) < 1e-4 * abs(want)
+    a, b = results[0][1], results[1][1]
+    for lid in a:       # the two ranks hold the two halves and agree on the gathered vector bit for bit
+        assert a[lid][0] == 0 and b[lid][0] == a[lid][1].size
+        assert (a[lid][2] == b[lid][2]).all()

@@ -1,0 +1,217 @@
+"""Intra-stage sharding (reference layer.py:96-225, 262-291, engine.py:363-412) on CPU + gloo.
+
+The host logic under test is the product's (``oobleck_b200/execution/sharding.py``, the stage communicators of
+``OobleckPipeline.initialize_distributed_fsdp``, ``DataParallelEngine``'s per-``fsdp_index`` groups); stage compute is the
+oracle.  Expected values follow the reference's semantics: every shard column of a pipeline runs the pipeline's
+micro-batches (one dataloader per pipeline, engine.py:618-628) and the post-backward reduce-scatter SUMs without
+pre-division (layer.py:202-206), so a stage of ``k`` GPUs contributes ``k`` times its gradient."""
+import os
+import sys
+
+import pytest
+import torch
+import torch.distributed as dist
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+from test_pipeline_gloo import MARGS, make_engine, run_spawn  # noqa: E402
+
+
+class FakeGroup:
+    def __init__(self, ranks, me, comm="comm"):
+        self.ranks, self.me, self.group = ranks, me, comm
+
+    def size(self):
+        return len(self.ranks)
+
+    def rank_index(self):
+        return self.ranks.index(self.me)
+
+
+def test_shard_param_is_the_reference_chunking():
+    """layer.py:262-270: ``number`` chunks, missing ones zero-filled, the last zero-padded to the first's size."""
+    from oobleck_b200.execution.sharding import shard_param
+    t = torch.arange(10.0)
+    got = shard_param(t, 4)                      # torch.chunk(4) of 10 -> 3, 3, 3, 1
+    assert [c.tolist() for c in got] == [[0, 1, 2], [3, 4, 5], [6, 7, 8], [9, 0, 0]]
+    got = shard_param(torch.arange(4.0).view(2, 2), 3)     # chunk(3) of 4 -> 2, 2 : one chunk is missing
+    assert [c.tolist() for c in got] == [[0, 1], [2, 3], [0, 0]]
+    got = shard_param(torch.arange(8.0), 2)
+    assert [c.tolist() for c in got] == [[0, 1, 2, 3], [4, 5, 6, 7]]
+
+
+def test_shard_layout_nests_across_stage_widths():
+    """A layer held by 1, 2 or 4 ranks of a 4-column grid: shard boundaries are multiples of the same unit, so the
+    cross-replica groups of column c reduce the same elements whatever the width of the stage on the other side."""
+    from oobleck_b200.execution.sharding import ShardedFlatState, shard_unit
+    n, columns = 1000, 4
+    unit = shard_unit(n, columns)
+    assert unit == 256 and unit % 8 == 0 and unit * columns >= n
+    for k in (1, 2, 4):
+        for index in range(k):
+            st = ShardedFlatState(n, FakeGroup(list(range(k)), index), columns, "cpu")
+            assert st.padded == 1024 and st.per_rank == 1024 // k and st.lo == index * st.per_rank
+            assert st.compute_param.numel() == n and st.full_grad.numel() == 1024
+            if k > 1:   # the shard is a view into the gathered buffer: optimizer and gather work in place
+                st.param_shard.fill_(7.0)
+                assert torch.equal(st.full_param[st.lo:st.hi], torch.full((st.per_rank,), 7.0))
+                assert st.exp_avg.numel() == st.per_rank and st.grad_shard.numel() == st.per_rank
+            else:
+                assert st.param_shard.numel() == n and st.exp_avg.numel() == n
+            # cross-replica groups: one per column this rank owns; the slices tile its reduce buffer
+            first = index * (columns // k)
+            groups = {c: FakeGroup([0, 9], 0, comm=f"c{c}") for c in range(first, first + columns // k)}
+            chunks = st.dp_chunks(groups)
+            assert [c.numel() for c, _ in chunks] == [unit] * (columns // k)
+            base = st.reduce_buffer.data_ptr()
+            assert [(c.data_ptr() - base) // 4 for c, _ in chunks] == [i * unit for i in range(columns // k)]
+    # consecutive columns on ONE communicator are reduced in one call; single-member groups are skipped
+    st = ShardedFlatState(n, FakeGroup([0], 0), columns, "cpu")
+    same = {c: FakeGroup([0, 9], 0, comm="one") for c in range(4)}
+    assert [c.numel() for c, _ in st.dp_chunks(same)] == [1024]
+    lonely = {0: FakeGroup([0, 9], 0, comm="a"), 1: FakeGroup([0], 0, comm=None), 2: FakeGroup([0, 9], 0, comm="a"),
+              3: FakeGroup([0, 9], 0, comm="a")}
+    assert [c.numel() for c, _ in st.dp_chunks(lonely)] == [256, 512]
+    with pytest.raises(ValueError):
+        ShardedFlatState(n, FakeGroup([0, 1, 2], 0), 4, "cpu")            # 4 columns over 3 ranks
+    # NO_SHARD allocates exactly the flat vector
+    st = ShardedFlatState(n, FakeGroup([0], 0), 1, "cpu")
+    assert st.padded == n and st.param_shard is st.full_param and st.param_shard.grad is st.full_grad
+
+
+# ---- engine level --------------------------------------------------------------------------------------------------
+def weighted_reference(M_per_pipeline, weights, mb, steps):
+    """Single process, all layers.  Pipeline ``p`` consumes its sampler's micro-batches; its gradient enters the update
+    ``weights[p]`` times (the width of its stages)."""
+    from oobleck_b200.execution.dataloader import OobleckSampler, SyntheticTokenDataset
+    from oobleck_b200.module.model import OobleckModel
+    from oracle import gpt2 as og
+    from oracle import optim as oo
+    model = OobleckModel("gpt2", {"input_ids": None, "attention_mask": None, "labels": None}, None, "t", dict(MARGS))
+    layers = og.build_layers(og.GPT2Dims(n_embd=64, n_head=1, n_layer=2, n_positions=32, vocab_size=211))
+    flats = [spec.init_flat() for spec in model.layers]
+    for l, f in zip(layers, flats):
+        og.load_flat_(l, f)
+    ds = SyntheticTokenDataset(num_samples=128, seq_len=32, vocab_size=211, pin_memory=False)
+    iters = [iter(OobleckSampler(ds, mb, pi, list(M_per_pipeline), 0)) for pi in range(len(M_per_pipeline))]
+    ms, vs = [torch.zeros_like(f) for f in flats], [torch.zeros_like(f) for f in flats]
+    lrs = oo.lr_sequence(steps, warmup_min_lr=0)
+    totals = [0.0] * len(M_per_pipeline)
+    for step in range(steps):
+        grads = [torch.zeros_like(f) for f in flats]
+        for pi, m in enumerate(M_per_pipeline):
+            for l in layers:
+                l.zero_grad()
+            for _ in range(m):
+                ids = ds.input_ids[next(iters[pi])]
+                x = (ids, torch.ones_like(ids), ids)
+                for l in layers:
+                    x = l(*x)
+                x[0].backward()
+                totals[pi] += float(x[0].detach())
+            for g, l in zip(grads, layers):
+                g.add_(og.flat_grads(l), alpha=float(weights[pi]))
+        for i, l in enumerate(layers):
+            oo.adamw_step_(flats[i], grads[i], ms[i], vs[i], step + 1, lrs[step])
+            og.load_flat_(l, flats[i])
+    return flats, ms, totals
+
+
+def wide_template(num_layers, stages, gpus_per_stage, nodes, gpn):
+    from oobleck_b200.planning.pipeline_template import PipelineTemplate, StageExecutionResult
+    base, extra = divmod(num_layers, stages)
+    out, start = [], 0
+    for s in range(stages):
+        n = base + (1 if s < extra else 0)
+        out.append(StageExecutionResult(range(start, start + n), gpus_per_stage))
+        start += n
+    return PipelineTemplate(out, 0.0, num_layers, nodes, gpn)
+
+
+def worker_sharded(rank, world, port, mode, M, mb, steps, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    torch.set_num_threads(2)
+    try:
+        gpn = 2
+        wide = wide_template(4, 1, 2, 1, gpn)            # one stage on both GPUs of a node: every layer sharded 2-way
+        narrow = wide_template(4, 2, 1, 1, gpn)          # two 1-GPU stages on a node: rows [a, a], [b, b]
+        plan = {"lone": [wide], "replicas": [wide, wide], "mixed": [wide, narrow]}[mode]
+        eng = make_engine(rank % gpn, world // gpn, gpn, M, mb, steps, templates=[wide, narrow])
+        assert eng._rank == rank
+        eng.instantiate_pipelines(M, plan=plan)
+        layers = eng._pipeline.execution._layers
+        sharded_here = mode != "mixed" or rank < 2
+        for l in layers:
+            assert l.sharded == sharded_here
+            assert l._param_handle._sharding_strategy == ("FULL_SHARD" if sharded_here else "NO_SHARD")
+            assert l._state.columns == gpn
+        if sharded_here:   # ONE communicator for the stage, shared by its layers
+            assert len({id(l._state.comm) for l in layers}) == 1
+        for _ in range(steps):
+            eng._train_step()
+        out = {}
+        for l in layers:
+            st = l._state
+            # one reduce-scatter per step, one all-gather per step after the first (initial values are deterministic)
+            assert (st.scatters, st.gathers) == ((steps, steps - 1) if sharded_here else (0, 0))
+            out[l.layer_id] = (st.lo, st.param_shard.numpy().copy(), st.exp_avg.numpy().copy(), st.sharded)
+        q.put((rank, out, float(eng._pipeline.execution.total_loss) if eng._pipeline.is_last_stage() else None, None))
+        dist.barrier()
+    except Exception:  # noqa: BLE001
+        import traceback
+        q.put((rank, None, None, traceback.format_exc()))
+        raise
+
+
+def check_against(results, flats, ms):
+    seen = {}
+    for rank, out, _, _ in results:
+        for lid, (lo, shard, m, sharded) in out.items():
+            n = flats[lid].numel()
+            want_p = torch.zeros(max(n, lo + shard.size)); want_p[:n] = flats[lid]
+            want_m = torch.zeros_like(want_p); want_m[:n] = ms[lid]
+            torch.testing.assert_close(torch.from_numpy(shard), want_p[lo:lo + shard.size], rtol=1e-5, atol=1e-7)
+            torch.testing.assert_close(torch.from_numpy(m), want_m[lo:lo + m.size], rtol=1e-4, atol=1e-9)
+            seen.setdefault(lid, []).append((rank, lo, shard.size))
+    return seen
+
+
+@pytest.mark.timeout(300)
+def test_one_stage_on_two_gpus_shards_every_layer():
+    """1 node x 2 GPUs, one stage: FULL_SHARD (layer.py:100-102).  Both columns run the pipeline's 4 micro-batches;
+    the reduce-scatter sums them: the update sees 2 x the gradient."""
+    M, mb, steps = 4, 1, 3
+    results = run_spawn(worker_sharded, 2, "lone", M, mb, steps)
+    flats, ms, totals = weighted_reference([M], [2], mb, steps)
+    seen = check_against(results, flats, ms)
+    for lid, parts in seen.items():         # two disjoint halves that tile the (padded) vector
+        assert sorted(p[1] for p in parts) == [0, parts[0][2]] and 2 * parts[0][2] >= flats[lid].numel()
+    for _, _, total, _ in results:          # both columns are last stages and saw the same losses
+        assert abs(total - totals[0]) < 1e-5 * abs(totals[0])
+
+
+@pytest.mark.timeout(300)
+def test_two_sharded_replicas_reduce_shard_by_shard():
+    """2 nodes x 2 GPUs, two replicas of the wide pipeline: cross-replica groups exist per fsdp_index ([0, 2] and
+    [1, 3], engine.py:374-392) and reduce the reduce-scattered SHARDS."""
+    M, mb, steps = 4, 1, 2
+    results = run_spawn(worker_sharded, 4, "replicas", M, mb, steps)
+    flats, ms, totals = weighted_reference([2, 2], [2, 2], mb, steps)
+    check_against(results, flats, ms)
+    for rank, _, total, _ in results:
+        assert abs(total - totals[rank // 2]) < 1e-5 * abs(totals[rank // 2])
+
+
+@pytest.mark.timeout(300)
+def test_sharded_pipeline_next_to_an_unsharded_one():
+    """Heterogeneous replicas: node 0 runs one 2-GPU stage (sharded), node 1 two 1-GPU stages.  Rank 2 / 3 hold whole
+    layers and reduce them column by column -- column 0 with rank 0, column 1 with rank 1 (layer.py:279-291)."""
+    M, mb, steps = 4, 1, 2
+    results = run_spawn(worker_sharded, 4, "mixed", M, mb, steps)
+    flats, ms, totals = weighted_reference([2, 2], [2, 1], mb, steps)
+    seen = check_against(results, flats, ms)
+    assert sorted(seen) == [0, 1, 2, 3]
+    for lid, parts in seen.items():          # two half shards on node 0 + the whole layer on rank 2 or 3
+        assert len(parts) == 3 and sorted(p[0] for p in parts)[:2] == [0, 1]
