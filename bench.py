@@ -559,11 +559,83 @@ def run_ours(args, cfg):
     }
     if world == 1 and args.cpu_baseline:
         out["cpu_baseline"] = cpu_baseline_sample(args.model)
+    if world >= RECONFIG_MIN_GPUS and args.replicas == 1 and args.with_reconfig:
+        # second half of BASELINE.json's metric, AFTER the timed region: rank 0 plays the agent for a fresh set of
+        # workers on the same GPUs (tools/reconfig_bench.py), SIGKILLs one inside a step and times the recovery.  The
+        # other ranks wait on the host (store key, no NCCL kernel spinning on the GPUs being measured).
+        torch.cuda.synchronize()
+        store = dist.distributed_c10d._get_default_store()
+        if rank == 0:
+            try:
+                out["reconfiguration"] = embedded_reconfiguration(args.model, world)
+            except Exception as e:  # noqa: BLE001  (never lose the throughput line over the extra measurement)
+                out["reconfiguration"] = {"error": f"{type(e).__name__}: {e}"}
+            store.set("oob_bench_reconfig_done", "1")
+        else:
+            from datetime import timedelta
+            try:
+                store.wait(["oob_bench_reconfig_done"], timedelta(seconds=2 * RECONFIG_BUDGET_S + 120))
+            except Exception:  # noqa: BLE001
+                pass
     if rank == 0:
         print(json.dumps(out), flush=True)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
+
+
+RECONFIG_BUDGET_S = float(os.environ.get("OOB_BENCH_RECONFIG_BUDGET_S", "240"))
+RECONFIG_MIN_GPUS = int(os.environ.get("OOB_BENCH_RECONFIG_MIN_GPUS", "4"))   # 2 replicas x >= 2 stages
+TORCHRUN_ENV = ("RANK", "WORLD_SIZE", "LOCAL_RANK", "MASTER_ADDR", "MASTER_PORT", "LOCAL_WORLD_SIZE", "GROUP_RANK",
+                "GROUP_WORLD_SIZE", "ROLE_RANK", "ROLE_WORLD_SIZE", "ROLE_NAME", "OMP_NUM_THREADS",
+                "TORCH_NCCL_ASYNC_ERROR_HANDLING")
+
+
+def embedded_reconfiguration(model: str, world: int) -> dict:
+    """``python tools/reconfig_bench.py`` twice in its own session: 2 replicas x world/2 stages losing a rank (BASELINE
+    config 4's job; 8 GPUs: 2 x 4 -> 4 + 3) and ONE world-stage pipeline losing a rank (config 5; 8 -> 7, peer
+    shadows).  Each run is bounded by RECONFIG_BUDGET_S; a run that fails or overruns is reported as such."""
+    import signal
+    import subprocess
+    env = {k: v for k, v in os.environ.items() if not (k.startswith("TORCHELASTIC") or k in TORCHRUN_ENV)}
+    out = {"metric": "reconfiguration_latency_s", "unit": "s", "higher_is_better": False,
+           "definition": "lost-node message received on the worker pipe -> first completed post-reconfiguration train "
+                         "step, max over the survivors (SURVEY 8d); one rank SIGKILLed inside a training step"}
+    for name, replicas in (("two_replicas", 2), ("lone_pipeline", 1)):
+        if replicas == 1 and world < 3:
+            continue                   # a lone pipeline needs a neighbour left to restore the lost stage from
+        cmd = [sys.executable, os.path.join(ROOT, "tools", "reconfig_bench.py"), "--gpus", str(world), "--replicas",
+               str(replicas), "--model", model, "--steps", "5", "--kill-step", "2"]
+        t0 = time.perf_counter()
+        p = subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, env=env, cwd=ROOT,
+                             start_new_session=True, text=True)
+        try:
+            stdout, _ = p.communicate(timeout=RECONFIG_BUDGET_S)
+        except subprocess.TimeoutExpired:
+            try:
+                os.killpg(p.pid, signal.SIGKILL)
+            except ProcessLookupError:
+                pass
+            p.wait()
+            out[name] = {"error": f"exceeded {RECONFIG_BUDGET_S:.0f} s"}
+            break                      # do not start another run on GPUs that may still be draining
+        line = next((l for l in reversed(stdout.splitlines()) if l.startswith("{")), None)
+        if line is None:
+            out[name] = {"error": f"no result (exit code {p.returncode})"}
+            continue
+        r = json.loads(line)
+        if "error" in r:
+            out[name] = {"error": str(r["error"])[:400]}
+            continue
+        out[name] = {"value": r["value"], "workload": r["config"]["workload"],
+                     "pipelines_after": r["pipelines_after"],
+                     "message_to_pipelines_rebuilt_s": r["notify_to_pipelines_rebuilt_and_states_copied_s"],
+                     "replicas_identical_after": r["replicas_identical_after"],
+                     "step_s_before": r["step_s_before"], "step_s_after": r["step_s_after"],
+                     "wall_s": time.perf_counter() - t0}
+    vals = [v["value"] for v in out.values() if isinstance(v, dict) and "value" in v]
+    out["value"] = max(vals) if vals else None
+    return out
 
 
 # dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of the dominant GEMM shape in the DEFAULT build (fp16 pairs
@@ -596,6 +668,9 @@ def main():
     ap.add_argument("--parity-check", type=int, default=1, choices=[0, 1],
                     help="check a reduced-depth model of the benchmarked width against the oracle before timing")
     ap.add_argument("--cpu-baseline", type=int, default=1, choices=[0, 1])
+    ap.add_argument("--with-reconfig", type=int, default=int(os.environ.get("OOB_BENCH_RECONFIG", "1")), choices=[0, 1],
+                    help="N >= 4: after the timed region, also kill a rank of a fresh job on the same GPUs and report "
+                         "the recovery time under \"reconfiguration\" (adds 2-3 minutes)")
     ap.add_argument("--reconfig", action="store_true",
                     help="reconfiguration latency after a real kill of one rank (spawns its own workers; see "
                          "tools/reconfig_bench.py)")

@@ -192,7 +192,7 @@ class Layer:
         # bias correction matches the moments (optimizer.py)
         self.opt_step = 0
         if init_values:
-            self.refresh_planes()
+            self._split_planes()
 
         E, V = layer.n_embd, layer.vocab_size
         self.dims = OobDims(self.mb, self.T, E, layer.n_head, V, (V + 63) // 64 * 64, layer.layer_norm_epsilon, nsplit,
