@@ -896,11 +896,12 @@ class OobleckEngine:
             1. unless a loss notification is already pending: run the pipeline's micro-batches, then drain the device;
                a wait on a neighbour that gave up (``transport.aborted()``: the peer is lost, or dropped the step) or a
                torch.distributed error marks the attempt as failed instead of propagating;
-            2. vote: ONE MIN all-reduce of that flag over every rank of the job (``_job_group``).  The step is committed
+            2. vote: ONE MIN all-reduce of that flag over every rank of the job (``_job_group``).  The step goes on
                only if every rank finished its micro-batches and nobody has a notification pending; a dead rank makes
-               the vote itself fail for everybody (gloo: peer reset; NCCL: released by the listener's abort).  Either
-               all surviving ranks commit the step or all of them drop it;
-            3. committed: gradient all-reduce + optimizer, exactly ``_train_step`` (+ the peer-shadow refresh).
+               the vote itself fail for everybody (gloo: peer reset; NCCL: released by the listener's abort);
+            3. gradient exchange (all-reduce across replicas), then a SECOND vote on "my exchange completed": either
+               all surviving ranks apply the optimizer step or none does (two-phase commit; the optimizer step itself
+               is local), then the peer-shadow refresh;
                dropped  : gradients are zeroed, the queued reconfiguration is applied (waiting for the agent's message
                if the failure was noticed first), and the caller runs the step again on the new pipelines.
 
@@ -931,21 +932,33 @@ class OobleckEngine:
             agreed = False
         _dbg(f"step: agreed={agreed}")
         if agreed:
+            # second phase: gradients are exchanged (cross-replica all-reduce; a sharded stage's reduce-scatter), then a
+            # second vote decides whether anybody applies them.  A rank that dies during the exchange fails the
+            # collectives of its partners only -- without this vote those would drop the step while everybody else
+            # commits it.  After a passed second vote the optimizer step is local: nothing can split the job any more.
+            exchanged = True
             try:
                 self._dp_engine.do_allreduce()
+                for layer in self._pipeline.execution._layers:
+                    if hasattr(layer, "prepare_gradient_for_optim"):
+                        layer.prepare_gradient_for_optim()
                 if on_gpu:
                     torch.cuda.synchronize()
                 if self._dp_engine.touches(self._lost_ranks):
                     raise PipelineAborted("a gradient all-reduce ran into a lost rank")   # never apply its output
-                self._pipeline.execution.optimizer_step()
             except (PipelineAborted, RuntimeError) as e:
-                agreed, failure = False, e
+                exchanged, failure = False, e
+            try:
+                agreed = self._vote(exchanged)
+            except (PipelineAborted, RuntimeError) as e:
+                _dbg(f"step: second vote failed: {str(e)[:120]}")
+                agreed = False
+            _dbg(f"step: gradients exchanged={exchanged} commit={agreed}")
+            if agreed:
+                self._pipeline.execution.optimizer_step()
         if agreed:
             if self._shadow is not None:
-                try:
-                    self._shadow.refresh()
-                except RuntimeError:
-                    pass        # the neighbour died right after the commit: its mirror keeps the previous step
+                self._shadow.refresh()      # a neighbour that dies in here leaves its mirror at the previous step
             return True
         self._pipeline._global_step = global_step      # the dropped step never happened
         try:

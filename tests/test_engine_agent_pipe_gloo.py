@@ -30,6 +30,7 @@ M, MB, STEPS_BEFORE, STEPS_TOTAL = 4, 1, 2, 4
 def scenario(mode):
     """(world, model args, global micro-batches, templates factory, initial plan, pipelines expected after the loss)"""
     from oobleck_b200.planning.pipeline_template import even_template
+    mode = mode.split("+")[0]
     if mode == "replicas":
         t = [even_template(4, 1), even_template(4, 2)]
         return 4, MARGS, 4, t, [t[1], t[1]], [[2], [0, 1]]
@@ -87,10 +88,18 @@ def worker(rank, pipe, q, ready, mode):
         def step_hook():
             if count["n"] == STEPS_BEFORE:
                 if rank == victim:
-                    q.put((rank, "gone", None, None))
-                    q.close(); q.join_thread()          # noqa: E702
-                    os._exit(0)                         # the node dies: no goodbye, no barrier
-                ready.put(rank)                         # survivors: tell the "agent" that the failure may be announced
+                    def die(*_a, **_k):
+                        q.put((rank, "gone", None, None))
+                        q.close(); q.join_thread()      # noqa: E702
+                        os._exit(0)                     # the node dies: no goodbye, no barrier
+                    if mode.endswith("+allreduce"):
+                        # dies AFTER the first vote has passed, inside the gradient exchange: only its all-reduce
+                        # partner sees a failed collective; the second vote must keep everybody else from committing
+                        eng._dp_engine.do_allreduce = die
+                    else:
+                        die()
+                else:
+                    ready.put(rank)                     # survivors: tell the "agent" that the failure may be announced
             count["n"] += 1
             return orig_step()
         eng._guarded_train_step = step_hook
@@ -149,7 +158,7 @@ def never_failed_reference(margs=MARGS, M=M):
 
 
 @pytest.mark.timeout(600)
-@pytest.mark.parametrize("mode", ["replicas", "lone", "replicas8", "lone8"])
+@pytest.mark.parametrize("mode", ["replicas", "lone", "replicas8", "lone8", "replicas+allreduce"])
 def test_engine_driven_through_agent_pipe_survives_a_dead_node(mode):
     """``lone``: the same death in a single 4-stage pipeline.  The reference raises "No alive ranks for the layer"
     (engine.py:263-269, its test at tests/execution/test_engine.py:1015-1019); with peer shadows the survivors re-split
