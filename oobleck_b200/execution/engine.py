@@ -262,6 +262,8 @@ class PeerShadow:
         self.enabled = P > 1 and engine._num_gpus_per_node == 1
         self.holder_of_layer: dict[int, int] = {}
         self.held: dict[int, list[torch.Tensor]] = {}      # layer id -> [param, exp_avg, exp_avg_sq, step]
+        self.staging: dict[int, list[torch.Tensor]] = {}   # where a refresh lands before it replaces ``held``
+        self.last_refresh_ok = True
         self.groups: dict[tuple[int, int], Any] = {}
         if not self.enabled:
             return
@@ -285,17 +287,26 @@ class PeerShadow:
 
     def refresh(self):
         """After a committed optimizer step: owners publish, holders receive (all broadcasts asynchronous, then waited:
-        every rank is a source in one pair and a destination in another)."""
+        every rank is a source in one pair and a destination in another).
+
+        The mirror changes atomically: a holder receives into a second set of buffers and swaps the two sets only when
+        every tensor of the mirrored stage has arrived.  Arrival is judged by the step count, the LAST tensor broadcast
+        for a layer on the pair's communicator (collectives of one communicator complete in order): the receive buffer
+        is preset to -1 and must come back as one non-negative count, the same for every layer of the stage.  An owner
+        that dies in here (gloo: the wait raises; NCCL: the listener aborts the communicator and the count never
+        arrives) leaves the mirror exactly as the previous step left it."""
         if not self.enabled:
             return
         engine = self._engine()
         me = engine._rank
         works = []
         P = len(self.stage_ranks)
+        mine = engine._pipeline.execution._layers
+        receiving: list[int] = []
         for s in range(P):
             a, b = self.stage_ranks[(s - 1) % P], self.stage_ranks[s]
             if me == b:
-                for layer in engine._pipeline.execution._layers:
+                for layer in mine:
                     if layer.layer_id in self.stage_layers[s]:
                         step = torch.tensor([int(getattr(layer, "opt_step", 0))], dtype=torch.int64,
                                             device=layer.flat_param.device)
@@ -303,10 +314,28 @@ class PeerShadow:
                             works.append(dist.broadcast(t, src=b, group=self.groups[(a, b)], async_op=True))
             if me == a:
                 for l in self.stage_layers[s]:
-                    for t in self.held[l]:
+                    if l not in self.staging:
+                        self.staging[l] = [torch.zeros_like(t) for t in self.held[l]]
+                    self.staging[l][3].fill_(-1)
+                    receiving.append(l)
+                    for t in self.staging[l]:
                         works.append(dist.broadcast(t, src=b, group=self.groups[(a, b)], async_op=True))
+        failed = False
         for w in works:
-            w.wait()
+            try:
+                w.wait()
+            except RuntimeError:
+                failed = True
+        if receiving and not failed:
+            try:
+                counts = {int(self.staging[l][3].item()) for l in receiving}
+                failed = len(counts) != 1 or min(counts) < 0
+            except RuntimeError:
+                failed = True
+        if receiving and not failed:
+            for l in receiving:
+                self.held[l], self.staging[l] = self.staging[l], self.held[l]
+        self.last_refresh_ok = not failed
 
 
 # ---- reconfiguration -----------------------------------------------------------------------------------------------
