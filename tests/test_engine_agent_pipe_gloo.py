@@ -121,7 +121,7 @@ def worker(rank, pipe, q, ready, mode):
         raise
 
 
-def never_failed_reference(margs=MARGS, M=M):
+def never_failed_reference(margs=MARGS, M=M, grad_scale=1.0):
     """Single process, all layers: steps 0..STEPS_BEFORE-1 on global batches 0.., then the sampler restarts (the new
     loaders start a fresh epoch-0 iterator) and the remaining steps consume global batches 0.. again."""
     from oobleck_b200.execution.dataloader import OobleckSampler, SyntheticTokenDataset
@@ -149,7 +149,7 @@ def never_failed_reference(margs=MARGS, M=M):
                 for l in layers:
                     x = l(*x)
                 x[0].backward()
-            grads = [og.flat_grads(l) for l in layers]
+            grads = [og.flat_grads(l) * grad_scale for l in layers]
             for i, l in enumerate(layers):
                 oo.adamw_step_(flats[i], grads[i], ms[i], vs[i], step + 1, lrs[step])
                 og.load_flat_(l, flats[i])

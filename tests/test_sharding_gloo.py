@@ -215,3 +215,125 @@ def test_sharded_pipeline_next_to_an_unsharded_one():
     assert sorted(seen) == [0, 1, 2, 3]
     for lid, parts in seen.items():          # two half shards on node 0 + the whole layer on rank 2 or 3
         assert len(parts) == 3 and sorted(p[0] for p in parts)[:2] == [0, 1]
+
+
+# ---- elastic: sharded stages lose a node -----------------------------------------------------------------------------
+NODE_IPS = ["127.0.0.1", "127.0.0.2", "127.0.0.3", "127.0.0.4"]
+GPN, STEPS_BEFORE, STEPS_TOTAL = 2, 2, 4
+
+
+def worker_nodes(rank, pipe, q, ready):
+    torch.set_num_threads(1)
+    try:
+        from unittest.mock import patch
+
+        from oracle_layer import OracleLayer
+
+        from oobleck_b200.execution.dataloader import SyntheticTokenDataset
+        from oobleck_b200.execution.engine import JobArguments, ModelArguments, OobleckArguments, OobleckEngine
+        node, local_rank = divmod(rank, GPN)
+        patch("socket.gethostbyname", return_value=NODE_IPS[node]).start()      # test_engine.py:676
+        real_tcpstore = torch.distributed.TCPStore
+        patch("torch.distributed.TCPStore", lambda host_name, *a, **kw: real_tcpstore("127.0.0.1", *a, **kw)).start()
+        M, mb = 4, 1
+        args = OobleckArguments(job=JobArguments(microbatch_size=mb, global_microbatch_size=mb * M, steps=STEPS_TOTAL),
+                                model=ModelArguments(model_name="gpt2", model_tag="t", model_args=dict(MARGS)))
+        ds = SyntheticTokenDataset(num_samples=256, seq_len=32, vocab_size=211, pin_memory=False)
+        one_node = wide_template(4, 1, GPN, 1, GPN)          # one 2-GPU stage
+        two_nodes = wide_template(4, 2, GPN, 2, GPN)         # two 2-GPU stages
+        # worker_main's call sequence (elastic/worker.py:23-34), two workers per node
+        eng = OobleckEngine(local_rank, len(NODE_IPS), GPN, pipe, args, dataset=ds, layer_cls=OracleLayer,
+                            templates=[one_node, two_nodes], backend="gloo", comm_timeout_s=20)
+        eng.initialize_distributed()
+        assert eng._rank == rank and eng._rank_map[NODE_IPS[node]] == [node * GPN, node * GPN + 1]
+        eng.instantiate_pipelines(M, plan=[two_nodes, two_nodes])
+        assert all(l.sharded for l in eng._pipeline.execution._layers)
+        orig_step = eng._guarded_train_step
+        count = {"n": 0}
+
+        def step_hook():
+            if count["n"] == STEPS_BEFORE:
+                if node == len(NODE_IPS) - 1:
+                    q.put((rank, "gone", None))
+                    q.close(); q.join_thread()          # noqa: E702
+                    os._exit(0)                         # the whole node dies: both of its workers
+                ready.put(rank)
+            count["n"] += 1
+            return orig_step()
+        eng._guarded_train_step = step_hook
+        eng.train()
+        assert [p._ranks for p in eng._reconfiguration._pipelines] == [[4, 5], [0, 1, 2, 3]]
+        assert eng._dist_info.world_size == 6 and NODE_IPS[3] not in eng._rank_map
+        layers = eng._pipeline.execution._layers
+        assert sorted(l.layer_id for l in layers) == ([0, 1, 2, 3] if rank in (4, 5) else ([0, 1] if rank < 2 else [2, 3]))
+        out = {l.layer_id: (l._state.lo, l._state.param_shard.numpy().copy(), l.exp_avg.numpy().copy(), l.sharded,
+                            l.opt_step) for l in layers}
+        q.put((rank, out, len(eng.step_seconds)))
+    except Exception:  # noqa: BLE001
+        import traceback
+        q.put((rank, traceback.format_exc(), None))
+        raise
+
+
+@pytest.mark.timeout(600)
+def test_sharded_stages_survive_a_lost_node():
+    """4 nodes x 2 GPUs, two replicas of a 2-stage pipeline whose stages own a node each (every layer sharded 2-way).
+    Node 3 dies inside a step: the reference's policy shrinks the second replica to ONE 2-GPU stage on node 2
+    ([4, 5]); the layers node 3 held arrive shard by shard from the first replica (rank 2 -> 4, rank 3 -> 5:
+    engine.py:278-303 pairs by fsdp_index), parameters and moments, and are gathered inside the new stage on the next
+    forward.  The run matches the never-failed oracle (2 x the gradient: both shard columns run the micro-batches)."""
+    import threading
+
+    import torch.multiprocessing as mp
+
+    from oobleck_b200.execution.engine import DistributionInfo
+    world = len(NODE_IPS) * GPN
+    ctx = mp.get_context("spawn")
+    q, ready = ctx.Queue(), ctx.Queue()
+    pipes = [ctx.Pipe(duplex=True) for _ in range(world)]
+    procs = [ctx.Process(target=worker_nodes, args=(r, pipes[r][1], q, ready)) for r in range(world)]
+    for p in procs:
+        p.start()
+
+    def broadcast_rank0_port(ps):                      # tests/execution/test_engine.py:650-657
+        port = ps[0][0].recv()
+        for pipe, _ in ps:
+            pipe.send(port)
+
+    def agent():
+        for pipe, _ in pipes:
+            pipe.send(DistributionInfo(list(NODE_IPS), world))
+        broadcast_rank0_port(pipes)
+        for _ in range(world - GPN):
+            ready.get(timeout=300)
+        for p in procs[world - GPN:]:
+            p.join(timeout=60)
+        for pipe, _ in pipes[:world - GPN]:
+            pipe.send(NODE_IPS[-1])
+        broadcast_rank0_port(pipes[:world - GPN])
+
+    t = threading.Thread(target=agent, daemon=True)
+    t.start()
+    results = {}
+    for _ in range(world):
+        r = q.get(timeout=500)
+        results[r[0]] = r
+    t.join(timeout=60)
+    for p in procs:
+        p.join(timeout=60)
+    assert results[6][1] == "gone" and results[7][1] == "gone"
+    for r in range(6):
+        assert not isinstance(results[r][1], str), results[r][1]
+        assert results[r][2] == STEPS_TOTAL
+
+    # never-failed run: one process, all micro-batches, 2 x the gradient; the sampler restarts after the reconfiguration
+    from test_engine_agent_pipe_gloo import never_failed_reference
+    flats, ms = never_failed_reference(MARGS, 4, grad_scale=2.0)
+    for r in range(6):
+        for lid, (lo, shard, m, sharded, opt_step) in results[r][1].items():
+            assert sharded and opt_step == STEPS_TOTAL
+            n = flats[lid].numel()
+            want_p = torch.zeros(max(n, lo + shard.size)); want_p[:n] = flats[lid]
+            want_m = torch.zeros_like(want_p); want_m[:n] = ms[lid]
+            torch.testing.assert_close(torch.from_numpy(shard), want_p[lo:lo + shard.size], rtol=1e-4, atol=2e-6)
+            torch.testing.assert_close(torch.from_numpy(m), want_m[lo:lo + m.size], rtol=1e-3, atol=1e-7)
