@@ -65,6 +65,7 @@ class OracleLayer:
         self.module = {"embed": og.EmbeddingLayer, "block": og.BlockLayer, "head": og.HeadLayer}[spec.kind](d)
         flat = torch.full((spec.num_params,), 0.01) if self.fast_init else spec.init_flat()
         k = process_group.size() if hasattr(process_group, "size") else 1
+        self._group_size = k
         st = self._state = ShardedFlatState(spec.num_params, process_group, max(columns, k), "cpu")
         st.install_full_(flat)
         og.load_flat_(self.module, st.compute_param)

@@ -337,3 +337,88 @@ def test_sharded_stages_survive_a_lost_node():
             want_m = torch.zeros_like(want_p); want_m[:n] = ms[lid]
             torch.testing.assert_close(torch.from_numpy(shard), want_p[lo:lo + shard.size], rtol=1e-4, atol=2e-6)
             torch.testing.assert_close(torch.from_numpy(m), want_m[lo:lo + m.size], rtol=1e-3, atol=1e-7)
+
+
+# ---- the reference's own FSDP test, restated (tests/execution/test_engine.py:805-881) --------------------------------
+def worker_fsdp_engine(rank, pipe, q, num_stages):
+    torch.set_num_threads(2)
+    try:
+        from unittest.mock import patch
+
+        from oracle_layer import OracleLayer
+
+        from oobleck_b200.execution.dataloader import SyntheticTokenDataset
+        from oobleck_b200.execution.engine import JobArguments, ModelArguments, OobleckArguments, OobleckEngine
+        num_gpus_per_node, M, mb, steps = 4, 2, 1, 2                     # "Assume all GPUs are in one node" (:814-816)
+        patch("socket.gethostbyname", return_value="127.0.0.1").start()
+        args = OobleckArguments(job=JobArguments(microbatch_size=mb, global_microbatch_size=mb * M, steps=steps),
+                                model=ModelArguments(model_name="gpt2", model_tag="t", model_args=dict(MARGS)))
+        ds = SyntheticTokenDataset(num_samples=128, seq_len=32, vocab_size=211, pin_memory=False)
+        template = wide_template(4, num_stages, num_gpus_per_node // num_stages, 1, num_gpus_per_node)
+        eng = OobleckEngine(rank, 1, num_gpus_per_node, pipe, args, dataset=ds, layer_cls=OracleLayer,
+                            templates=[template], backend="gloo", listen=False)
+        eng.initialize_distributed()
+        eng.instantiate_pipelines(M)
+        assert len(eng._reconfiguration._pipelines) == 1                 # :841-842
+        assert len(eng._pipeline._ranks) == 4                            # :844-845
+        for layer in eng._pipeline.execution._layers:                    # :847-860
+            if num_stages == 4:
+                assert layer._param_handle._sharding_strategy == "NO_SHARD" and layer._group_size == 1
+            else:
+                assert layer._param_handle._sharding_strategy == "FULL_SHARD"
+                assert layer._group_size == 4 // num_stages
+        for _ in range(steps):
+            eng._train_step()                                            # :862
+        out = {l.layer_id: (l._state.lo, l._state.param_shard.numpy().copy(), l.exp_avg.numpy().copy(), l.sharded)
+               for l in eng._pipeline.execution._layers}
+        q.put((rank, out, float(eng._pipeline.execution.total_loss) if eng._pipeline.is_last_stage() else None, None))
+        dist.barrier()
+    except Exception:  # noqa: BLE001
+        import traceback
+        q.put((rank, None, None, traceback.format_exc()))
+        raise
+
+
+@pytest.mark.timeout(300)
+@pytest.mark.parametrize("num_stages", [1, 2, 4])
+def test_fsdp_engine_train(num_stages):
+    """The reference's ``test_fsdp_engine_train``: 4 GPUs of ONE node, ``num_stages`` stages of 4 / num_stages GPUs, the
+    engine driven through the agent pipe.  Same assertions (one pipeline, 4 ranks, sharding strategy and group size per
+    layer, a train step runs) -- plus the result: two steps against the oracle, the gradient entering 4 / num_stages
+    times (every shard column runs the micro-batches; with 2 stages the grid rows are [0, 0, 1, 1] / [2, 2, 3, 3]: four
+    columns over two holders, each holding two units)."""
+    import threading
+
+    import torch.multiprocessing as mp
+
+    from oobleck_b200.execution.engine import DistributionInfo
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    pipes = [ctx.Pipe(duplex=True) for _ in range(4)]
+    for pipe, _ in pipes:
+        pipe.send(DistributionInfo(["127.0.0.1"], 4))                    # :870-872
+
+    def broadcast_rank0_port():                                          # :650-657
+        port = pipes[0][0].recv()
+        for pipe, _ in pipes:
+            pipe.send(port)
+    t = threading.Thread(target=broadcast_rank0_port, daemon=True)
+    t.start()
+    procs = [ctx.Process(target=worker_fsdp_engine, args=(r, pipes[r][1], q, num_stages)) for r in range(4)]
+    for p in procs:
+        p.start()
+    results = sorted((q.get(timeout=240) for _ in range(4)), key=lambda r: r[0])
+    for p in procs:
+        p.join(timeout=60)
+    t.join(timeout=30)
+    for r in results:
+        assert r[3] is None, r[3]
+    k = 4 // num_stages
+    flats, ms, totals = weighted_reference([2], [k], 1, 2)
+    seen = check_against(results, flats, ms)
+    assert sorted(seen) == [0, 1, 2, 3]
+    for lid, parts in seen.items():
+        assert len(parts) == k and sorted(p[1] for p in parts) == [i * parts[0][2] for i in range(k)] if k > 1 else True
+    for _, _, total, _ in results:
+        if total is not None:
+            assert abs(total - totals[0]) < 1e-5 * abs(totals[0])
