@@ -197,6 +197,17 @@ def _cpu_worker(rank, world, port, model, replicas, seq, steps, warmup, threads,
 
 
 def cpu_pipeline_sample(model: str, gpus: int, replicas: int, steps: int, warmup: int, timeout: float = 800.0):
+    """``_cpu_pipeline_sample_once`` with one retry if the gloo rendezvous itself failed (the free port found for it was
+    taken by another process before rank 0 bound it)."""
+    try:
+        return _cpu_pipeline_sample_once(model, gpus, replicas, steps, warmup, timeout)
+    except RuntimeError as e:
+        if not any(t in str(e) for t in ("Address already in use", "EADDRINUSE", "Connection refused")):
+            raise
+    return _cpu_pipeline_sample_once(model, gpus, replicas, steps, warmup, timeout)
+
+
+def _cpu_pipeline_sample_once(model: str, gpus: int, replicas: int, steps: int, warmup: int, timeout: float = 800.0):
     """Spawn the P gloo processes of the CPU arm and return (seconds per step list, tokens per step, description)."""
     import torch.multiprocessing as mp
     cfg = MODELS[model]
