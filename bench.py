@@ -11,6 +11,11 @@ V=50257), micro-batch 2, global batch 128 sequences (64 micro-batches) per optim
 stages (N = --gpus; N=1 runs all 50 stage layers on one GPU), fp32 AdamW.  Synthetic wikitext-2-shaped tokens,
 seed-42 HF-style initial weights.  One "step" = pipeline.train() + DP all-reduce + optimizer step, i.e.
 ``OobleckEngine._train_step`` (oobleck/execution/engine.py:645-649).  Prints ONE JSON line on rank 0.
+
+At N >= 4 the line also carries ``"reconfiguration"``: after the timed region rank 0 runs tools/reconfig_bench.py twice on
+the same GPUs (2 replicas x N/2 stages, and one N-stage pipeline with peer shadows), each SIGKILLing a worker inside a
+training step, and records the time from the lost-node message to the first completed step.  ``--with-reconfig 0`` /
+``OOB_BENCH_RECONFIG=0`` turns it off; ``OOB_BENCH_RECONFIG_BUDGET_S`` (240) bounds each of the two runs.
 """
 from __future__ import annotations
 
