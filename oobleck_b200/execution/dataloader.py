@@ -83,6 +83,77 @@ class SyntheticTokenDataset:
         return self
 
 
+class TokenFileDataset(SyntheticTokenDataset):
+    """A tokenised corpus read from disk, cut into training blocks exactly as the reference's ``group_texts`` does
+    (oobleck/execution/dataset.py:183-206): documents are concatenated ``group_size`` at a time (``Dataset.map(batched=
+    True)`` hands ``group_texts`` 1000 examples per call), each concatenation is cut into ``seq_len``-token blocks, the
+    remainder of every group is dropped (a group shorter than one block is kept whole by the reference -- a ragged
+    sample the fixed-shape stage kernels cannot take: it is dropped here and counted in ``dropped_short_groups``),
+    ``attention_mask`` is all ones and ``labels = input_ids``.  SURVEY 8(f4): tokenising needs the GPT-2 vocabulary
+    files (no network here), so the input is what a tokeniser run leaves behind:
+
+    * ``path``: a flat array of token ids -- ``.npy``, or raw little-endian ``uint16`` / ``int32`` (``dtype=``) as
+      written by the usual GPT-2 corpus preparation scripts -- memory-mapped, never loaded whole;
+    * ``doc_offsets`` (optional): start index of every document (``.npy`` or a sequence), so that the grouping sees the
+      reference's document batches; without it the whole stream is ONE group.
+
+    The blocks are materialised once into one pinned int64 host tensor (what the loader gathers micro-batches from)."""
+
+    def __init__(self, path: str, seq_len: int = 1024, vocab_size: int = 50257, dtype: str = "uint16",
+                 doc_offsets=None, group_size: int = 1000, max_samples: int | None = None, pin_memory: bool = True):
+        import numpy as np
+        if str(path).endswith(".npy"):
+            tokens = np.load(path, mmap_mode="r")
+        else:
+            tokens = np.memmap(path, dtype=np.dtype(dtype).newbyteorder("<"), mode="r")
+        assert tokens.ndim == 1, "expected a flat token stream"
+        n = int(tokens.shape[0])
+        if doc_offsets is None:
+            bounds = [0, n]
+        else:
+            offs = np.load(doc_offsets) if isinstance(doc_offsets, str) else np.asarray(doc_offsets)
+            offs = [int(o) for o in offs]
+            assert offs and offs[0] == 0 and all(a <= b for a, b in zip(offs, offs[1:])) and offs[-1] <= n
+            starts = offs[::group_size]                       # first document of every group
+            bounds = starts + [n]
+        blocks = []
+        self.dropped_tokens = 0
+        self.dropped_short_groups = 0
+        for lo, hi in zip(bounds, bounds[1:]):
+            total = hi - lo
+            if total < seq_len:
+                self.dropped_short_groups += 1 if total else 0
+                self.dropped_tokens += total
+                continue
+            usable = (total // seq_len) * seq_len
+            self.dropped_tokens += total - usable
+            blocks.append((lo, usable // seq_len))
+            if max_samples is not None and sum(b for _, b in blocks) >= max_samples:
+                break
+        count = sum(b for _, b in blocks)
+        if max_samples is not None:
+            count = min(count, max_samples)
+        ids = torch.empty((count, seq_len), dtype=torch.int64)
+        row = 0
+        for lo, nb in blocks:
+            nb = min(nb, count - row)
+            if nb <= 0:
+                break
+            chunk = np.asarray(tokens[lo: lo + nb * seq_len]).astype(np.int64, copy=False)
+            ids[row: row + nb] = torch.from_numpy(chunk.reshape(nb, seq_len))
+            row += nb
+        if count and int(ids.max()) >= vocab_size:
+            raise ValueError(f"token id {int(ids.max())} outside the vocabulary ({vocab_size})")
+        if pin_memory and torch.cuda.is_available():
+            ids = ids.pin_memory()
+        self.input_ids = ids
+        self.seq_len = seq_len
+        self.vocab_size = vocab_size
+        self.sample = ({"input_ids": ids[0], "attention_mask": torch.ones_like(ids[0]), "labels": ids[0].clone()}
+                       if count else None)
+        self.dataset = {"train": self, "validation": self}
+
+
 class OobleckDataLoader:
     """Iterable over this pipeline's micro-batches: dicts of int64 [mb, T] tensors in the reference's field order
     (input_ids, attention_mask, labels)."""
