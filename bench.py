@@ -649,6 +649,14 @@ def embedded_reconfiguration(model: str, world: int) -> dict:
                      "replicas_identical_after": r["replicas_identical_after"],
                      "step_s_before": r["step_s_before"], "step_s_after": r["step_s_after"],
                      "wall_s": time.perf_counter() - t0}
+        # training throughput of that job itself (wall clock of whole engine steps incl. the per-step votes of an
+        # elastic run): with 2 replicas on 8 GPUs this is BASELINE config 4's shape (2 x 4 stages + the cross-replica
+        # all-reduce) before the loss and 4 + 3 stages after it
+        tps = r.get("tokens_per_step")
+        for key in ("before", "after"):
+            st = r.get("step_s_" + key)
+            if tps and st and st.get("median"):
+                out[name][f"tokens_per_s_{key}"] = tps / st["median"]
     vals = [v["value"] for v in out.values() if isinstance(v, dict) and "value" in v]
     out["value"] = max(vals) if vals else None
     return out

@@ -74,7 +74,7 @@ def worker(rank, world, pipe, q, started, model, replicas, steps, kill_step):
         ma = dict(cfg["model_args"])
         mb = cfg["microbatch"]
         stages = world // replicas
-        gb = mb * 8 * world                 # 8 micro-batches per GPU and step: enough for a 1F1B steady state
+        gb = mb * 8 * world                 # 8 micro-batches per GPU and step (tokens_per_step below): a 1F1B steady state
         oargs = OobleckArguments(job=JobArguments(microbatch_size=mb, global_microbatch_size=gb, steps=steps),
                                  model=ModelArguments(model_name="gpt2", model_tag=model, model_args=ma))
         ds = SyntheticTokenDataset(num_samples=max(2334, gb * (steps + 4)), seq_len=ma["n_positions"],
@@ -203,6 +203,7 @@ def main(args=None):
                                        "post-reconfiguration train step, max over the survivors (SURVEY 8d)",
         "config": {"workload": f"{args.model}: {args.replicas} replicas x {world // args.replicas} stages, rank {victim} "
                                f"SIGKILLed inside training step {args.kill_step}", "model": args.model},
+        "tokens_per_step": tokens_per_step(args.model, world),
         "notify_to_pipelines_rebuilt_and_states_copied_s": worst_rebuilt,
         "agent_kill_to_announce_s": marks["announce"] - marks["kill"],
         "pipelines_after": next(iter(results.values()))["pipelines"],
@@ -214,6 +215,13 @@ def main(args=None):
                      for r, v in sorted(results.items())},
     }
     print(json.dumps(out), flush=True)
+
+
+def tokens_per_step(model: str, world: int) -> int:
+    """Tokens one optimizer step of the job consumes (all replicas): the worker's global batch x T."""
+    from bench import MODELS
+    cfg = MODELS[model]
+    return cfg["microbatch"] * 8 * world * cfg["model_args"]["n_positions"]
 
 
 def statistics_of(xs):
