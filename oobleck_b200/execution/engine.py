@@ -667,6 +667,24 @@ def layer_cost_model(model: OobleckModel, microbatch: int) -> list[float]:
     return costs
 
 
+def node_range(profile_results, num_nodes: int, num_gpus_per_node: int, device_memory_bytes: int) -> tuple[int, int]:
+    """``(min_num_nodes, max_num_nodes)`` handed to ``create_pipeline_templates`` -- engine.py:490-514, same arithmetic
+    and the same assertion text (golden table: tests/execution/test_engine.py:394-406).  A pipeline needs six copies of
+    every layer's parameter bytes (weights, gradients, optimizer state, ...) plus the largest single activation
+    footprint; the minimum node count is that total over the memory of one node's GPUs, at least 1."""
+    import math
+    layers = profile_results.get()
+    total_memory_consumption = 6 * sum(r._mem_required[0] for r in layers)
+    total_memory_consumption += max(r._mem_required[1] for r in layers)
+    min_num_nodes = max(1, math.ceil(total_memory_consumption / (device_memory_bytes * num_gpus_per_node)))
+    max_num_nodes = num_nodes
+    assert min_num_nodes <= max_num_nodes, (
+        "Minimum required number of nodes is larger than maximum number of nodes "
+        f"(minimum required: {min_num_nodes}, you have: {max_num_nodes})."
+    )
+    return min_num_nodes, max_num_nodes
+
+
 class OobleckEngine:
     """engine.py:415-668.  ``pipe`` is the agent connection (may be None when launched by torchrun; rank/world then
     come from the environment)."""
@@ -872,8 +890,11 @@ class OobleckEngine:
             if os.environ.get("OOB_TEMPLATE_SOURCE", "planner") == "planner":
                 # the reference's flow (engine.py:453-500): profile -> PipelineTemplateGenerator.create_pipeline_templates
                 from ..planning.pipeline_template import PipelineTemplateGenerator
+                device_memory = torch.cuda.get_device_properties(torch.cuda.current_device()).total_memory
+                lo, hi = node_range(results, self._num_nodes, self._num_gpus_per_node, device_memory)   # :490-512
+                self.min_num_nodes = lo
                 self._pipeline_templates = PipelineTemplateGenerator().create_pipeline_templates(
-                    results, (1, min(self._num_nodes, len(self.layer_costs))), self._num_gpus_per_node)
+                    results, (lo, min(hi, len(self.layer_costs))), self._num_gpus_per_node)
                 self.layer_costs_source += " -> template search (csrc/planning/template_search.cpp)"
             else:
                 self._pipeline_templates = [balanced_template(self.layer_costs, n, self._num_gpus_per_node)

@@ -122,3 +122,49 @@ def test_pipeline_wiring_matches_oracle():
             assert mine == bk.my_layers(p.rank_grid, me)
         finally:
             P._my_rank = orig
+
+
+# ---- minimum node count (engine.py:490-512; golden table: tests/execution/test_engine.py:394-406) -------------------
+@pytest.mark.parametrize(
+    ["num_nodes", "num_gpus_per_node", "gpu_mem", "num_layers", "expected_min_num_nodes", "expect_fail"],
+    [
+        (1, 1, 1024 * 32 * 6, 32, 1, False),
+        (1, 1, 1024 * 32 * 6, 64, 2, True),
+        (1, 1, 1024 * 128 * 6, 64, 1, False),
+        (4, 1, 1024 * 32 * 6, 64, 2, False),
+        (4, 1, 1024 * 16 * 6, 64, 4, False),
+        (4, 1, 1024 * 16 * 6, 128, 8, True),
+        (1, 4, 1024 * 16 * 6, 128, 2, True),
+        (1, 4, 1024 * 32 * 6, 128, 1, False),
+        (4, 4, 1024 * 16 * 6, 128, 2, False),
+        (4, 4, 1024 * 1 * 6, 32, 8, True),
+    ],
+)
+def test_multi_nodes_template_configuration(num_nodes, num_gpus_per_node, gpu_mem, num_layers, expected_min_num_nodes,
+                                            expect_fail):
+    """The reference's own table, with its fake profile (every layer: 1024 bytes of parameters, no activations)."""
+    import re
+
+    from oobleck_b200.execution.engine import node_range
+    from oobleck_b200.planning.pipeline_template import LayerExecutionResult, LayerExecutionResults
+    fake_profile = LayerExecutionResults([
+        LayerExecutionResult(i, 0.1, 0.1, {g + 1: 0.1 for g in range(8)}, {n + 1: 0.1 for n in range(64)}, (1024, 0))
+        for i in range(num_layers)])
+    if expect_fail:
+        with pytest.raises(AssertionError) as e:
+            node_range(fake_profile, num_nodes, num_gpus_per_node, gpu_mem)
+        assert e.value.args[0].startswith("Minimum required number of nodes")
+        match = re.search(r"minimum required: (\d+),", e.value.args[0])
+        assert int(match[1]) == expected_min_num_nodes
+    else:
+        assert node_range(fake_profile, num_nodes, num_gpus_per_node, gpu_mem) == (expected_min_num_nodes, num_nodes)
+
+
+def test_node_range_counts_the_largest_activation_once():
+    from oobleck_b200.execution.engine import node_range
+    from oobleck_b200.planning.pipeline_template import LayerExecutionResult, LayerExecutionResults
+    prof = LayerExecutionResults([LayerExecutionResult(i, 1.0, 1.0, {}, {}, (100, a)) for i, a in enumerate((5, 700, 30))])
+    # 6 * 300 + max(5, 700, 30) = 2500 bytes
+    assert node_range(prof, 4, 1, 2500) == (1, 4)
+    assert node_range(prof, 4, 1, 2499) == (2, 4)
+    assert node_range(prof, 4, 2, 1250) == (1, 4)
