@@ -98,7 +98,11 @@ int oob_attention_bwd(const void* qkv_planes, long qkv_plane_stride, int operand
                       void* dqkv_planes, long plane_stride, int nplanes, int batch, int seq, int n_head, int head_dim,
                       void* stream);
 
-/* ---- fx layer 0 (wte[ids] + wpe[pos]) and its backward --------------------------------------------------- */
+/* ---- fx layer 0 (wte[ids] + wpe[pos]) and its backward ---------------------------------------------------
+ * Precondition: 0 <= ids[i] < vocab (rows of wte).  Like torch.nn.Embedding on CUDA the gather is not clamped; the
+ * vocabulary size is not part of this signature, so the range is the caller's contract -- the loaders enforce it
+ * (TokenFileDataset raises on an id outside the vocabulary, SyntheticTokenDataset draws inside it).  Labels, in
+ * contrast, MAY be out of range (HF's ignore_index = -100): oob_cross_entropy skips such targets. */
 int oob_embedding_fwd(const long long* ids, const float* wte, const float* wpe, float* hidden, int rows, int seq,
                       int n_embd, void* stream);
 int oob_embedding_bwd(const long long* ids, const float* dhidden, float* dwte, float* dwpe, int batch, int seq,
