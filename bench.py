@@ -15,7 +15,9 @@ seed-42 HF-style initial weights.  One "step" = pipeline.train() + DP all-reduce
 At N >= 4 the line also carries ``"reconfiguration"``: after the timed region rank 0 runs tools/reconfig_bench.py twice on
 the same GPUs (2 replicas x N/2 stages, and one N-stage pipeline with peer shadows), each SIGKILLing a worker inside a
 training step, and records the time from the lost-node message to the first completed step.  ``--with-reconfig 0`` /
-``OOB_BENCH_RECONFIG=0`` turns it off; ``OOB_BENCH_RECONFIG_BUDGET_S`` (240) bounds each of the two runs.
+``OOB_BENCH_RECONFIG=0`` turns it off; ``OOB_BENCH_RECONFIG_BUDGET_S`` (240) bounds each of the two runs.  At N = 8 a third
+bounded extra follows, ``"config4_dp2_x_pp4"``: BASELINE config 4 itself (GPT-2 124M, 2 replicas x 4 stages) through this
+script in a torchrun of its own (``OOB_BENCH_CONFIG4=0`` skips it).
 """
 from __future__ import annotations
 
@@ -586,11 +588,16 @@ def run_ours(args, cfg):
                 out["reconfiguration"] = embedded_reconfiguration(args.model, world)
             except Exception as e:  # noqa: BLE001  (never lose the throughput line over the extra measurement)
                 out["reconfiguration"] = {"error": f"{type(e).__name__}: {e}"}
+            if world == 8 and CONFIG4_IN_LINE and "error" not in out["reconfiguration"].get("two_replicas", {}):
+                try:
+                    out["config4_dp2_x_pp4"] = embedded_config4(world)
+                except Exception as e:  # noqa: BLE001
+                    out["config4_dp2_x_pp4"] = {"error": f"{type(e).__name__}: {e}"}
             store.set("oob_bench_reconfig_done", "1")
         else:
             from datetime import timedelta
             try:
-                store.wait(["oob_bench_reconfig_done"], timedelta(seconds=2 * RECONFIG_BUDGET_S + 120))
+                store.wait(["oob_bench_reconfig_done"], timedelta(seconds=3 * RECONFIG_BUDGET_S + 120))
             except Exception:  # noqa: BLE001
                 pass
     if rank == 0:
@@ -605,6 +612,45 @@ RECONFIG_MIN_GPUS = int(os.environ.get("OOB_BENCH_RECONFIG_MIN_GPUS", "4"))   # 
 TORCHRUN_ENV = ("RANK", "WORLD_SIZE", "LOCAL_RANK", "MASTER_ADDR", "MASTER_PORT", "LOCAL_WORLD_SIZE", "GROUP_RANK",
                 "GROUP_WORLD_SIZE", "ROLE_RANK", "ROLE_WORLD_SIZE", "ROLE_NAME", "OMP_NUM_THREADS",
                 "TORCH_NCCL_ASYNC_ERROR_HANDLING")
+
+
+CONFIG4_IN_LINE = os.environ.get("OOB_BENCH_CONFIG4", "1") == "1"
+
+
+def embedded_config4(world: int) -> dict:
+    """BASELINE config 4, literally: GPT-2 124M as 2 replica pipelines x 4 stages on the 8 GPUs (cross-replica gradient
+    all-reduce path), measured by this very script in a torchrun of its own after the timed region of the headline run
+    (``bench.py --gpus 8 --replicas 2 --model gpt2``): throughput, end-to-end throughput and the oracle parity check of
+    that job.  Bounded by RECONFIG_BUDGET_S; a failure is reported, never raised."""
+    import signal
+    import subprocess
+    env = {k: v for k, v in os.environ.items() if not (k.startswith("TORCHELASTIC") or k in TORCHRUN_ENV)}
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}", "--master-addr",
+           "127.0.0.1", "--master-port", str(free_port()), os.path.join(ROOT, "bench.py"), "--gpus", str(world),
+           "--replicas", "2", "--model", "gpt2", "--steps", "3", "--warmup", "3", "--cpu-baseline", "0",
+           "--with-reconfig", "0"]
+    t0 = time.perf_counter()
+    p = subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, env=env, cwd=ROOT,
+                         start_new_session=True, text=True)
+    try:
+        stdout, _ = p.communicate(timeout=RECONFIG_BUDGET_S)
+    except subprocess.TimeoutExpired:
+        try:
+            os.killpg(p.pid, signal.SIGKILL)
+        except ProcessLookupError:
+            pass
+        p.wait()
+        return {"error": f"exceeded {RECONFIG_BUDGET_S:.0f} s"}
+    line = next((l for l in reversed(stdout.splitlines()) if l.startswith("{")), None)
+    if line is None:
+        return {"error": f"no result (exit code {p.returncode})"}
+    r = json.loads(line)
+    keep = ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "scaling", "config", "parity_check",
+            "stage_busy_ms", "bubble_ms", "gpu_launches", "e2e")
+    out = {k: r.get(k) for k in keep}
+    out["stage_layers"] = (r.get("engine") or {}).get("stage_layers")
+    out["wall_s"] = time.perf_counter() - t0
+    return out
 
 
 def embedded_reconfiguration(model: str, world: int) -> dict:
