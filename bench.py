@@ -15,7 +15,8 @@ seed-42 HF-style initial weights.  One "step" = pipeline.train() + DP all-reduce
 At N >= 4 the line also carries ``"reconfiguration"``: after the timed region rank 0 runs tools/reconfig_bench.py twice on
 the same GPUs (2 replicas x N/2 stages, and one N-stage pipeline with peer shadows), each SIGKILLing a worker inside a
 training step, and records the time from the lost-node message to the first completed step.  ``--with-reconfig 0`` /
-``OOB_BENCH_RECONFIG=0`` turns it off; ``OOB_BENCH_RECONFIG_BUDGET_S`` (240) bounds each of the two runs.  At N = 8 a third
+``OOB_BENCH_RECONFIG=0`` turns it off; ``OOB_BENCH_RECONFIG_BUDGET_S`` (150) bounds each run, ``OOB_BENCH_EXTRAS_BUDGET_S``
+(400) all extras of a line together (the driver allows one bench.py run 870 s).  At N = 8 a third
 bounded extra follows, ``"config4_dp2_x_pp4"``: BASELINE config 4 itself (GPT-2 124M, 2 replicas x 4 stages) through this
 script in a torchrun of its own (``OOB_BENCH_CONFIG4=0`` skips it).
 """
@@ -584,20 +585,21 @@ def run_ours(args, cfg):
         torch.cuda.synchronize()
         store = dist.distributed_c10d._get_default_store()
         if rank == 0:
+            deadline = time.perf_counter() + EXTRAS_BUDGET_S
             try:
-                out["reconfiguration"] = embedded_reconfiguration(args.model, world)
+                out["reconfiguration"] = embedded_reconfiguration(args.model, world, deadline)
             except Exception as e:  # noqa: BLE001  (never lose the throughput line over the extra measurement)
                 out["reconfiguration"] = {"error": f"{type(e).__name__}: {e}"}
             if world == 8 and CONFIG4_IN_LINE and "error" not in out["reconfiguration"].get("two_replicas", {}):
                 try:
-                    out["config4_dp2_x_pp4"] = embedded_config4(world)
+                    out["config4_dp2_x_pp4"] = embedded_config4(world, deadline)
                 except Exception as e:  # noqa: BLE001
                     out["config4_dp2_x_pp4"] = {"error": f"{type(e).__name__}: {e}"}
             store.set("oob_bench_reconfig_done", "1")
         else:
             from datetime import timedelta
             try:
-                store.wait(["oob_bench_reconfig_done"], timedelta(seconds=3 * RECONFIG_BUDGET_S + 120))
+                store.wait(["oob_bench_reconfig_done"], timedelta(seconds=EXTRAS_BUDGET_S + 120))
             except Exception:  # noqa: BLE001
                 pass
     if rank == 0:
@@ -607,7 +609,11 @@ def run_ours(args, cfg):
         dist.destroy_process_group()
 
 
-RECONFIG_BUDGET_S = float(os.environ.get("OOB_BENCH_RECONFIG_BUDGET_S", "240"))
+# The driver gives one bench.py run 870 s (SCALE_r01.json per_n_timeout_s).  The extras after the timed region are bounded
+# twice: each run by RECONFIG_BUDGET_S (typical: 40-60 s), all of them together by EXTRAS_BUDGET_S -- a run that would
+# start with less than 45 s left is skipped and says so -- so the throughput line is printed in time whatever happens.
+RECONFIG_BUDGET_S = float(os.environ.get("OOB_BENCH_RECONFIG_BUDGET_S", "150"))
+EXTRAS_BUDGET_S = float(os.environ.get("OOB_BENCH_EXTRAS_BUDGET_S", "400"))
 RECONFIG_MIN_GPUS = int(os.environ.get("OOB_BENCH_RECONFIG_MIN_GPUS", "4"))   # 2 replicas x >= 2 stages
 TORCHRUN_ENV = ("RANK", "WORLD_SIZE", "LOCAL_RANK", "MASTER_ADDR", "MASTER_PORT", "LOCAL_WORLD_SIZE", "GROUP_RANK",
                 "GROUP_WORLD_SIZE", "ROLE_RANK", "ROLE_WORLD_SIZE", "ROLE_NAME", "OMP_NUM_THREADS",
@@ -617,7 +623,14 @@ TORCHRUN_ENV = ("RANK", "WORLD_SIZE", "LOCAL_RANK", "MASTER_ADDR", "MASTER_PORT"
 CONFIG4_IN_LINE = os.environ.get("OOB_BENCH_CONFIG4", "1") == "1"
 
 
-def embedded_config4(world: int) -> dict:
+def _run_budget(deadline: float | None) -> float:
+    """Seconds the next extra run may take: its own bound, cut by what is left of the extras' common budget."""
+    if deadline is None:
+        return RECONFIG_BUDGET_S
+    return min(RECONFIG_BUDGET_S, deadline - time.perf_counter())
+
+
+def embedded_config4(world: int, deadline: float | None = None) -> dict:
     """BASELINE config 4, literally: GPT-2 124M as 2 replica pipelines x 4 stages on the 8 GPUs (cross-replica gradient
     all-reduce path), measured by this very script in a torchrun of its own after the timed region of the headline run
     (``bench.py --gpus 8 --replicas 2 --model gpt2``): throughput, end-to-end throughput and the oracle parity check of
@@ -629,18 +642,21 @@ def embedded_config4(world: int) -> dict:
            "127.0.0.1", "--master-port", str(free_port()), os.path.join(ROOT, "bench.py"), "--gpus", str(world),
            "--replicas", "2", "--model", "gpt2", "--steps", "3", "--warmup", "3", "--cpu-baseline", "0",
            "--with-reconfig", "0"]
+    budget = _run_budget(deadline)
+    if budget < 45:
+        return {"skipped": f"{max(budget, 0):.0f} s left of the extras' budget ({EXTRAS_BUDGET_S:.0f} s)"}
     t0 = time.perf_counter()
     p = subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, env=env, cwd=ROOT,
                          start_new_session=True, text=True)
     try:
-        stdout, _ = p.communicate(timeout=RECONFIG_BUDGET_S)
+        stdout, _ = p.communicate(timeout=budget)
     except subprocess.TimeoutExpired:
         try:
             os.killpg(p.pid, signal.SIGKILL)
         except ProcessLookupError:
             pass
         p.wait()
-        return {"error": f"exceeded {RECONFIG_BUDGET_S:.0f} s"}
+        return {"error": f"exceeded {budget:.0f} s"}
     line = next((l for l in reversed(stdout.splitlines()) if l.startswith("{")), None)
     if line is None:
         return {"error": f"no result (exit code {p.returncode})"}
@@ -653,10 +669,11 @@ def embedded_config4(world: int) -> dict:
     return out
 
 
-def embedded_reconfiguration(model: str, world: int) -> dict:
+def embedded_reconfiguration(model: str, world: int, deadline: float | None = None) -> dict:
     """``python tools/reconfig_bench.py`` twice in its own session: 2 replicas x world/2 stages losing a rank (BASELINE
     config 4's job; 8 GPUs: 2 x 4 -> 4 + 3) and ONE world-stage pipeline losing a rank (config 5; 8 -> 7, peer
-    shadows).  Each run is bounded by RECONFIG_BUDGET_S; a run that fails or overruns is reported as such."""
+    shadows).  Each run is bounded by RECONFIG_BUDGET_S and by what is left of the extras' common budget (``deadline``); a run
+    that fails, overruns or no longer fits is reported as such."""
     import signal
     import subprocess
     env = {k: v for k, v in os.environ.items() if not (k.startswith("TORCHELASTIC") or k in TORCHRUN_ENV)}
@@ -668,18 +685,22 @@ def embedded_reconfiguration(model: str, world: int) -> dict:
             continue                   # a lone pipeline needs a neighbour left to restore the lost stage from
         cmd = [sys.executable, os.path.join(ROOT, "tools", "reconfig_bench.py"), "--gpus", str(world), "--replicas",
                str(replicas), "--model", model, "--steps", "5", "--kill-step", "2"]
+        budget = _run_budget(deadline)
+        if budget < 45:
+            out[name] = {"skipped": f"{max(budget, 0):.0f} s left of the extras' budget ({EXTRAS_BUDGET_S:.0f} s)"}
+            continue
         t0 = time.perf_counter()
         p = subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, env=env, cwd=ROOT,
                              start_new_session=True, text=True)
         try:
-            stdout, _ = p.communicate(timeout=RECONFIG_BUDGET_S)
+            stdout, _ = p.communicate(timeout=budget)
         except subprocess.TimeoutExpired:
             try:
                 os.killpg(p.pid, signal.SIGKILL)
             except ProcessLookupError:
                 pass
             p.wait()
-            out[name] = {"error": f"exceeded {RECONFIG_BUDGET_S:.0f} s"}
+            out[name] = {"error": f"exceeded {budget:.0f} s"}
             break                      # do not start another run on GPUs that may still be draining
         line = next((l for l in reversed(stdout.splitlines()) if l.startswith("{")), None)
         if line is None:
