@@ -142,6 +142,9 @@ class ClockSampler:
 # micro-batch 1 x REF_SEQ tokens, P micro-batches per step.  Nothing is extrapolated: ``value`` is the tokens the sample
 # really processed divided by the wall time it really took (max over the processes).
 REF_SEQ = int(os.environ.get("OOB_REF_SEQ", "256"))
+# wall-clock budget of one CPU-arm run (the driver gives `bench.py --impl reference` 870 s; typical on a 16-core quota:
+# 7-9 s per step, 25 steps in about 220 s): past it the run stops after the current step and reports what it timed
+CPU_ARM_BUDGET_S = float(os.environ.get("OOB_CPU_ARM_BUDGET_S", "600"))
 
 
 def _cpu_worker(rank, world, port, model, replicas, seq, steps, warmup, threads, depth, q):
@@ -188,12 +191,18 @@ def _cpu_worker(rank, world, port, model, replicas, seq, steps, warmup, threads,
             except StopIteration:
                 eng._pipeline.reset_iterator()
                 eng._train_step()
-            dt = torch.tensor([time.perf_counter() - t0], dtype=torch.float64)
+            now = time.perf_counter()
+            dt = torch.tensor([now - t0, now - t_start], dtype=torch.float64)
             if world > 1:
-                dist.all_reduce(dt, op=dist.ReduceOp.MAX)
-            note(f"step {it} took {float(dt):.2f} s")
+                dist.all_reduce(dt, op=dist.ReduceOp.MAX)      # every rank sees the same two numbers
+            note(f"step {it} took {float(dt[0]):.2f} s")
             if it >= warmup:
-                times.append(float(dt))
+                times.append(float(dt[0]))
+            # a host much slower than expected: stop while the run still fits the caller's window and report the steps
+            # that were really timed (same decision on every rank: it is taken on the reduced numbers)
+            if times and float(dt[1]) + 1.5 * float(dt[0]) > CPU_ARM_BUDGET_S and it < warmup + steps - 1:
+                note(f"budget of {CPU_ARM_BUDGET_S:.0f} s reached after {len(times)} timed step(s): stopping early")
+                break
         if rank == 0:
             q.put(("ok", times, M * seq))
         if world > 1:
@@ -288,9 +297,11 @@ def run_reference(args, cfg):
     times, tokens, info = cpu_pipeline_sample(args.model, args.gpus, args.replicas, args.steps, args.warmup)
     sec = sum(times) / len(times)
     value = tokens / sec
+    if len(times) < args.steps:
+        info["sample"] += f"; stopped after {len(times)} of {args.steps} timed steps ({CPU_ARM_BUDGET_S:.0f} s budget)"
     print(json.dumps({
         "impl": "reference", "metric": "training_tokens_per_s", "value": value, "unit": "tokens/s",
-        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec * 1e3,
+        "n_gpus": args.gpus, "steps": len(times), "warmup": args.warmup, "ms_per_step": sec * 1e3,
         "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": workload_config(args.model, cfg, args.gpus, args.replicas),
         "cpu_baseline": {"value": value, "unit": "tokens/s", "cores": info["cores"], "kind": "port",
