@@ -68,7 +68,7 @@ def reference_run(M, mb, steps, num_pipelines=1):
                 for l in layers:
                     x = l(*x)
                 x[0].backward()
-                tot[pi] += float(x[0])
+                tot[pi] += float(x[0].detach())
         losses.append(tot)
         grads = [og.flat_grads(l) for l in layers]
         for i, l in enumerate(layers):
@@ -179,3 +179,52 @@ def test_two_replicas_dp_allreduce_gloo():
             torch.testing.assert_close(torch.from_numpy(f), flats[lid], rtol=1e-5, atol=1e-7)
         want = sum(t[rank] for t in losses)
         assert abs(total - want) < 1e-5 * abs(want)
+
+
+def worker_dp2_pp4(rank, world, port, M, mb, steps, q):
+    """The construction bench.py uses for ``--gpus 8 --replicas 2`` (BASELINE config 4): the engine is told the
+    pipeline depth (4 "nodes"), the world size says how many replicas fit."""
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    torch.set_num_threads(1)
+    try:
+        stages = world // 2
+        eng = make_engine(rank, stages, 1, M, mb, steps)
+        eng._world_size = world
+        eng.initialize_distributed("gloo")
+        eng.instantiate_pipelines(M)
+        pipes = eng._reconfiguration._pipelines
+        assert [p._ranks for p in pipes] == [list(range(stages)), list(range(stages, world))]
+        # one cross-replica communicator per stage position, created in the same order on every rank (engine.py:374-392)
+        assert eng._dp_engine.group_creation_order == [[s, s + stages] for s in range(stages)]
+        sampler = eng._pipeline._dataloader.batch_sampler
+        assert sampler.num_microbatches == [M // 2, M // 2] and sampler.pipeline_index == rank // stages
+        pipe = eng._pipeline
+        me = rank % stages
+        assert pipe.communication.prev_rank == (None if me == 0 else rank - 1)
+        assert pipe.communication.next_rank == (None if me == stages - 1 else rank + 1)
+        for _ in range(steps):
+            eng._train_step()
+        out = {l.layer_id: l.flat_param.numpy().copy() for l in pipe.execution._layers}
+        q.put((rank, out, float(pipe.execution.total_loss) if pipe.is_last_stage() else None, None))
+        dist.barrier()
+    except Exception:  # noqa: BLE001
+        import traceback
+        q.put((rank, None, None, traceback.format_exc()))
+        raise
+
+
+@pytest.mark.timeout(400)
+def test_two_replicas_of_four_stages_on_eight_ranks():
+    """BASELINE config 4's shape, built the way bench.py builds it, against the single-process oracle run."""
+    M, mb, steps = 8, 1, 2
+    results = run_spawn(worker_dp2_pp4, 8, M, mb, steps)
+    flats, losses, _ = reference_run(M, mb, steps, num_pipelines=2)
+    seen = {}
+    for rank, out, total, _ in results:
+        for lid, f in out.items():
+            torch.testing.assert_close(torch.from_numpy(f), flats[lid], rtol=1e-5, atol=1e-7)
+            seen.setdefault(lid, []).append(rank)
+        if total is not None:
+            want = sum(t[rank // 4] for t in losses)
+            assert abs(total - want) < 1e-5 * abs(want)
+    assert sorted(seen) == [0, 1, 2, 3] and all(len(r) == 2 for r in seen.values())   # every layer lives on two ranks
