@@ -168,3 +168,62 @@ def test_node_range_counts_the_largest_activation_once():
     assert node_range(prof, 4, 1, 2500) == (1, 4)
     assert node_range(prof, 4, 1, 2499) == (2, 4)
     assert node_range(prof, 4, 2, 1250) == (1, 4)
+
+
+def test_measured_profile_feeds_node_range_and_template_search(monkeypatch):
+    """The branch of ``instantiate_pipelines`` that only runs on a GPU box (profile -> node range -> template search,
+    engine.py:453-523 in the reference), driven here with a fake profile and a fake device."""
+    import torch
+
+    from oobleck_b200.execution import engine as E
+    from oobleck_b200.execution.dataloader import SyntheticTokenDataset
+    from oobleck_b200.planning import profiler as P
+    from oobleck_b200.planning.pipeline_template import LayerExecutionResult, LayerExecutionResults
+
+    margs = dict(n_embd=64, n_head=1, num_hidden_layers=6, n_positions=32, vocab_size=211)
+    args = E.OobleckArguments(job=E.JobArguments(microbatch_size=1, global_microbatch_size=8, steps=1),
+                              model=E.ModelArguments(model_name="gpt2", model_tag="t", model_args=margs))
+    ds = SyntheticTokenDataset(num_samples=64, seq_len=32, vocab_size=211, pin_memory=False)
+    eng = E.OobleckEngine(0, 4, 1, None, args, dataset=ds)
+    assert not eng._templates_injected and eng.layer_costs_source == "FLOP model"
+
+    cost = {"embed": (0.05, 0.1), "block": (1.0, 2.0), "head": (2.5, 5.0)}
+
+    def fake_results(model, microbatch, device=None):
+        return LayerExecutionResults([
+            LayerExecutionResult(i, cost[l.kind][0], cost[l.kind][1], {}, {}, (4 * l.num_params, l.activation_bytes(1)))
+            for i, l in enumerate(model.layers)])
+
+    class Props:
+        total_memory = 178 * 2 ** 30
+
+    class Stop(Exception):
+        pass
+
+    def stop(self):
+        raise Stop
+
+    monkeypatch.setattr(torch.cuda, "is_available", lambda: True)
+    monkeypatch.setattr(torch.cuda, "current_device", lambda: 0)
+    monkeypatch.setattr(torch.cuda, "get_device_properties", lambda d: Props)
+    monkeypatch.setattr(P, "measured_layer_results", fake_results)
+    monkeypatch.setattr(E.OobleckEngine, "choose_plan", stop)
+    with pytest.raises(Stop):
+        eng.instantiate_pipelines(8)
+    assert eng.min_num_nodes == 1
+    assert eng.layer_costs == [sum(cost[l.kind]) for l in eng._model.layers]
+    assert "template search" in eng.layer_costs_source
+    assert [t._num_nodes for t in eng._pipeline_templates] == [1, 2, 3, 4]
+    four = eng._pipeline_templates[-1]
+    splits = [list(s._layer_indices) for s in four.get_stages()]
+    assert [i for s in splits for i in s] == list(range(8))                  # contiguous, complete
+    stage_cost = [sum(eng.layer_costs[i] for i in s) for s in splits]
+    assert max(stage_cost) <= 9.0 + 1e-9                                      # 25.65 ms over 4 stages: best max is 3 blocks
+
+    # a device too small for the model on the nodes at hand: the reference's assertion, from the same place
+    class Tiny:
+        total_memory = 1 << 20
+    monkeypatch.setattr(torch.cuda, "get_device_properties", lambda d: Tiny)
+    eng2 = E.OobleckEngine(0, 2, 1, None, args, dataset=ds)
+    with pytest.raises(AssertionError, match="Minimum required number of nodes"):
+        eng2.instantiate_pipelines(8)
