@@ -641,21 +641,18 @@ def _run_budget(deadline: float | None) -> float:
     return min(RECONFIG_BUDGET_S, deadline - time.perf_counter())
 
 
-def embedded_config4(world: int, deadline: float | None = None) -> dict:
-    """BASELINE config 4, literally: GPT-2 124M as 2 replica pipelines x 4 stages on the 8 GPUs (cross-replica gradient
-    all-reduce path), measured by this very script in a torchrun of its own after the timed region of the headline run
-    (``bench.py --gpus 8 --replicas 2 --model gpt2``): throughput, end-to-end throughput and the oracle parity check of
-    that job.  Bounded by RECONFIG_BUDGET_S; a failure is reported, never raised."""
+def _bounded_json_run(cmd: list[str], deadline: float | None) -> tuple[dict | None, dict | None, float]:
+    """Run ``cmd`` in a session of its own, without anything of the surrounding torchrun in its environment, for at most
+    ``_run_budget(deadline)`` seconds (the whole process group is SIGKILLed past that), and parse the last JSON line of
+    its stdout.  Returns (result, problem, wall seconds): exactly one of the first two is not None; ``problem`` is
+    ``{"skipped": ...}`` when the run no longer fits the budget, ``{"error": ...}`` when it overran (``"exceeded"``) or
+    printed no JSON line."""
     import signal
     import subprocess
-    env = {k: v for k, v in os.environ.items() if not (k.startswith("TORCHELASTIC") or k in TORCHRUN_ENV)}
-    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}", "--master-addr",
-           "127.0.0.1", "--master-port", str(free_port()), os.path.join(ROOT, "bench.py"), "--gpus", str(world),
-           "--replicas", "2", "--model", "gpt2", "--steps", "3", "--warmup", "3", "--cpu-baseline", "0",
-           "--with-reconfig", "0"]
     budget = _run_budget(deadline)
     if budget < 45:
-        return {"skipped": f"{max(budget, 0):.0f} s left of the extras' budget ({EXTRAS_BUDGET_S:.0f} s)"}
+        return None, {"skipped": f"{max(budget, 0):.0f} s left of the extras' budget ({EXTRAS_BUDGET_S:.0f} s)"}, 0.0
+    env = {k: v for k, v in os.environ.items() if not (k.startswith("TORCHELASTIC") or k in TORCHRUN_ENV)}
     t0 = time.perf_counter()
     p = subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, env=env, cwd=ROOT,
                          start_new_session=True, text=True)
@@ -667,27 +664,39 @@ def embedded_config4(world: int, deadline: float | None = None) -> dict:
         except ProcessLookupError:
             pass
         p.wait()
-        return {"error": f"exceeded {budget:.0f} s"}
+        return None, {"error": f"exceeded {budget:.0f} s"}, time.perf_counter() - t0
+    wall = time.perf_counter() - t0
     line = next((l for l in reversed(stdout.splitlines()) if l.startswith("{")), None)
     if line is None:
-        return {"error": f"no result (exit code {p.returncode})"}
-    r = json.loads(line)
+        return None, {"error": f"no result (exit code {p.returncode})"}, wall
+    return json.loads(line), None, wall
+
+
+def embedded_config4(world: int, deadline: float | None = None) -> dict:
+    """BASELINE config 4, literally: GPT-2 124M as 2 replica pipelines x 4 stages on the 8 GPUs (cross-replica gradient
+    all-reduce path), measured by this very script in a torchrun of its own after the timed region of the headline run
+    (``bench.py --gpus 8 --replicas 2 --model gpt2``): throughput, end-to-end throughput and the oracle parity check of
+    that job.  Bounded like every extra (``_bounded_json_run``); a failure is reported, never raised."""
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}", "--master-addr",
+           "127.0.0.1", "--master-port", str(free_port()), os.path.join(ROOT, "bench.py"), "--gpus", str(world),
+           "--replicas", "2", "--model", "gpt2", "--steps", "3", "--warmup", "3", "--cpu-baseline", "0",
+           "--with-reconfig", "0"]
+    r, problem, wall = _bounded_json_run(cmd, deadline)
+    if problem is not None:
+        return problem
     keep = ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "scaling", "config", "parity_check",
             "stage_busy_ms", "bubble_ms", "gpu_launches", "e2e")
     out = {k: r.get(k) for k in keep}
     out["stage_layers"] = (r.get("engine") or {}).get("stage_layers")
-    out["wall_s"] = time.perf_counter() - t0
+    out["wall_s"] = wall
     return out
 
 
 def embedded_reconfiguration(model: str, world: int, deadline: float | None = None) -> dict:
     """``python tools/reconfig_bench.py`` twice in its own session: 2 replicas x world/2 stages losing a rank (BASELINE
     config 4's job; 8 GPUs: 2 x 4 -> 4 + 3) and ONE world-stage pipeline losing a rank (config 5; 8 -> 7, peer
-    shadows).  Each run is bounded by RECONFIG_BUDGET_S and by what is left of the extras' common budget (``deadline``); a run
-    that fails, overruns or no longer fits is reported as such."""
-    import signal
-    import subprocess
-    env = {k: v for k, v in os.environ.items() if not (k.startswith("TORCHELASTIC") or k in TORCHRUN_ENV)}
+    shadows).  Each run is bounded by RECONFIG_BUDGET_S and by what is left of the extras' common budget (``deadline``); a
+    run that fails, overruns or no longer fits is reported as such."""
     out = {"metric": "reconfiguration_latency_s", "unit": "s", "higher_is_better": False,
            "definition": "lost-node message received on the worker pipe -> first completed post-reconfiguration train "
                          "step, max over the survivors (SURVEY 8d); one rank SIGKILLed inside a training step"}
@@ -696,28 +705,12 @@ def embedded_reconfiguration(model: str, world: int, deadline: float | None = No
             continue                   # a lone pipeline needs a neighbour left to restore the lost stage from
         cmd = [sys.executable, os.path.join(ROOT, "tools", "reconfig_bench.py"), "--gpus", str(world), "--replicas",
                str(replicas), "--model", model, "--steps", "5", "--kill-step", "2"]
-        budget = _run_budget(deadline)
-        if budget < 45:
-            out[name] = {"skipped": f"{max(budget, 0):.0f} s left of the extras' budget ({EXTRAS_BUDGET_S:.0f} s)"}
+        r, problem, wall = _bounded_json_run(cmd, deadline)
+        if problem is not None:
+            out[name] = problem
+            if "exceeded" in problem.get("error", ""):
+                break                  # do not start another run on GPUs that may still be draining
             continue
-        t0 = time.perf_counter()
-        p = subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, env=env, cwd=ROOT,
-                             start_new_session=True, text=True)
-        try:
-            stdout, _ = p.communicate(timeout=budget)
-        except subprocess.TimeoutExpired:
-            try:
-                os.killpg(p.pid, signal.SIGKILL)
-            except ProcessLookupError:
-                pass
-            p.wait()
-            out[name] = {"error": f"exceeded {budget:.0f} s"}
-            break                      # do not start another run on GPUs that may still be draining
-        line = next((l for l in reversed(stdout.splitlines()) if l.startswith("{")), None)
-        if line is None:
-            out[name] = {"error": f"no result (exit code {p.returncode})"}
-            continue
-        r = json.loads(line)
         if "error" in r:
             out[name] = {"error": str(r["error"])[:400]}
             continue
@@ -725,8 +718,7 @@ def embedded_reconfiguration(model: str, world: int, deadline: float | None = No
                      "pipelines_after": r["pipelines_after"],
                      "message_to_pipelines_rebuilt_s": r["notify_to_pipelines_rebuilt_and_states_copied_s"],
                      "replicas_identical_after": r["replicas_identical_after"],
-                     "step_s_before": r["step_s_before"], "step_s_after": r["step_s_after"],
-                     "wall_s": time.perf_counter() - t0}
+                     "step_s_before": r["step_s_before"], "step_s_after": r["step_s_after"], "wall_s": wall}
         # training throughput of that job itself (wall clock of whole engine steps incl. the per-step votes of an
         # elastic run): with 2 replicas on 8 GPUs this is BASELINE config 4's shape (2 x 4 stages + the cross-replica
         # all-reduce) before the loss and 4 + 3 stages after it
