@@ -567,7 +567,9 @@ def run_ours(args, cfg):
         "stage_busy_ms": stage_busy, "bubble_ms": stage_bubble,
         "clocks": clocks,
         "gpu_launches": int(launches),
-        "e2e": {"value": e2e, "unit": "tokens/s", "h2d_bytes_per_step": 2 * 8 * gb * T,
+        # every micro-batch crosses PCIe as the loader's three int64 [mb, T] fields (input_ids, attention_mask, labels:
+        # PipelineExecution._prepare_inputs copies each dict value, pipeline.py:150-156), on the first stage of each replica
+        "e2e": {"value": e2e, "unit": "tokens/s", "h2d_bytes_per_step": 3 * 8 * gb * T,
                 "d2h_bytes_per_step": 4 * args.replicas, "loss": last_loss},
         "model_flops_fraction_of_bf16_peak": value * fpt / (world * peaks["bf16_tflops"] * 1e12),
         "roofline": {
