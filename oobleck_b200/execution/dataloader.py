@@ -185,4 +185,6 @@ class OobleckDataLoader:
                     ids = ids.pin_memory()
             if self._ones is None or self._ones.shape != ids.shape or self._ones.device != ids.device:
                 self._ones = torch.ones_like(ids)
+                if ids.device.type == "cpu" and ids.is_pinned():
+                    self._ones = self._ones.pin_memory()      # every field leaves pinned memory (async H2D)
             yield {"input_ids": ids, "attention_mask": self._ones, "labels": ids}
