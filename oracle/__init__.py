@@ -21,6 +21,14 @@ What it restates (reference = /root/reference @ 3b7a0c2f, never copied):
 * ``optim.py``        -- torch AdamW(fused) arithmetic + deepspeed WarmupLR as the reference
                          constructs them (pipeline.py:117-127).
 
+* ``_ref/``          -- not a restatement: the REFERENCE's own C++ planner module (``pipeline_template``,
+                         oobleck/csrc/planning/{pipeline_template.cpp,bind.cpp}) built by ``make -C oracle``
+                         from the sources where they lie under /root/reference, with single-threaded
+                         stand-ins (``shims/``) for cppcoro and oneTBB, which this image lacks.  It pins the
+                         product's template search and ``get_rank_grid`` (tests/test_planner_vs_reference.py,
+                         golden vectors tests/golden/planner.json).  Git-ignored; built by
+                         ``__graft_entry__.build()`` where /root/reference exists.
+
 Parity pins: the integer bookkeeping is pinned by golden vectors generated from the
 reference's own Python (tests/golden/gen_golden.py imports /root/reference with the missing
 third-party modules stubbed) plus the tables of the reference's tests

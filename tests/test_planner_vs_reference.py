@@ -1,0 +1,156 @@
+"""The planner objects against the reference's OWN C++ planner (oobleck/csrc/planning/pipeline_template.{h,cpp},
+execution_result.h, bound by bind.cpp).
+
+* ``tests/golden/planner.json`` was produced by that module itself (tests/golden/gen_planner_golden.py; oracle/Makefile
+  builds it from the sources under /root/reference with single-threaded stand-ins for cppcoro / oneTBB): for 17 seeded
+  layer profiles -- 1, 2 and 4 GPUs per node, node ranges up to 8, cheap and expensive in-node all-reduce -- the templates
+  ``PipelineTemplateGenerator.create_pipeline_templates`` returns and the rank grid of each.  This repo's template search
+  (csrc/planning/template_search.cpp behind ``oob_plan_pipeline_templates``) and ``PipelineTemplate.get_rank_grid`` must
+  reproduce them: same stage boundaries, same GPUs per stage, iteration time to 1e-12, rank grids equal.
+* when oracle/_ref holds the built module (this container), the same comparison runs live on further random profiles,
+  and the reference's own planner tests (tests/planning/test_pipeline_template.py:27-93) are replayed on both.
+"""
+import importlib
+import json
+import os
+import random
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests", "golden"))
+
+from oobleck_b200.planning import pipeline_template as P  # noqa: E402
+
+GOLDEN = json.load(open(os.path.join(ROOT, "tests", "golden", "planner.json")))
+
+
+def reference_module():
+    d = os.path.join(ROOT, "oracle", "_ref")
+    if not os.path.isdir(d) or not any(f.startswith("pipeline_template") and f.endswith(".so") for f in os.listdir(d)):
+        return None
+    sys.path.insert(0, d)
+    try:
+        return importlib.import_module("pipeline_template")
+    except ImportError:
+        return None
+    finally:
+        sys.path.remove(d)
+
+
+def results_from_rows(mod, rows):
+    return mod.LayerExecutionResults([
+        mod.LayerExecutionResult(i, r["forward"], r["backward"], {int(k): v for k, v in r["allreduce_in_node"].items()},
+                                 {int(k): v for k, v in r["allreduce_across_nodes"].items()}, tuple(r["mem_required"]))
+        for i, r in enumerate(rows)])
+
+
+def shape(t):
+    return t._num_nodes, [(list(s._layer_indices), s._num_gpus) for s in t.get_stages()]
+
+
+@pytest.mark.parametrize("case", GOLDEN, ids=[f"seed{c['seed']}-{c['layers']}L-{c['gpus_per_node']}gpn" for c in GOLDEN])
+def test_template_search_reproduces_the_reference_planner(case):
+    prof = results_from_rows(P, case["profile"])
+    mine = P.PipelineTemplateGenerator().create_pipeline_templates(prof, tuple(case["node_range"]), case["gpus_per_node"])
+    assert len(mine) == len(case["templates"])
+    for got, want in zip(mine, case["templates"]):
+        assert got._num_nodes == want["num_nodes"] and got._num_gpus_per_node == want["num_gpus_per_node"]
+        assert [(list(s._layer_indices), s._num_gpus) for s in got.get_stages()] == \
+               [(s["layer_indices"], s["num_gpus"]) for s in want["stages"]]
+        assert got._iteration_time == pytest.approx(want["iteration_time"], rel=1e-12)
+        for s, ws in zip(got.get_stages(), want["stages"]):
+            assert s._mem_required == ws["mem_required"]          # 6 x parameter bytes + activation bytes per layer
+        grid = got.get_rank_grid(want["ranks"])
+        assert {str(k): v for k, v in grid.items()} == want["rank_grid"]
+        assert list(grid) == sorted(grid)                          # std::map order
+
+
+def test_rank_grid_of_hand_built_templates_matches_the_reference_module():
+    """pipeline_template.h:57-84 directly (before: pinned only through the reference's test tables)."""
+    R = reference_module()
+    if R is None:
+        pytest.skip("oracle/_ref not built (make -C oracle needs /root/reference)")
+    rnd = random.Random(5)
+    for _ in range(60):
+        gpn = rnd.choice([1, 2, 4, 8])
+        nodes = rnd.randint(1, 4)
+        # stages: every node's GPUs are dealt out in power-of-two pieces
+        gpus = []
+        for _n in range(nodes):
+            left = gpn
+            while left:
+                g = rnd.choice([x for x in (1, 2, 4, 8) if x <= left])
+                gpus.append(g)
+                left -= g
+        layers = len(gpus) + rnd.randint(0, 6)
+        cuts = sorted(rnd.sample(range(1, layers), len(gpus) - 1)) if len(gpus) > 1 else []
+        bounds = list(zip([0] + cuts, cuts + [layers]))
+        rows = [{"forward": 1.0, "backward": 2.0, "allreduce_in_node": {str(g): 0.1 for g in range(1, 9)},
+                 "allreduce_across_nodes": {"1": 0.1}, "mem_required": [8, 8]} for _ in range(layers)]
+        rprof = results_from_rows(R, rows)
+        rt = R.PipelineTemplate([R.StageExecutionResult(rprof, (a, b), g) for (a, b), g in zip(bounds, gpus)], 1.0,
+                                layers, nodes, gpn)
+        mt = P.PipelineTemplate([P.StageExecutionResult(range(a, b), g) for (a, b), g in zip(bounds, gpus)], 1.0,
+                                layers, nodes, gpn)
+        ranks = rnd.sample(range(1000), sum(gpus))
+        assert mt.get_rank_grid(ranks) == rt.get_rank_grid(ranks)
+
+
+@pytest.mark.parametrize("seed", range(100, 124))
+def test_live_comparison_on_random_profiles(seed):
+    R = reference_module()
+    if R is None:
+        pytest.skip("oracle/_ref not built (make -C oracle needs /root/reference)")
+    from gen_planner_golden import profile_rows
+    rnd = random.Random(seed)
+    gpn = rnd.choice([1, 1, 2, 4])
+    layers = rnd.randint(3, 11)
+    lo = rnd.randint(1, 3)
+    hi = rnd.randint(lo, min(layers, lo + 4))
+    rows = profile_rows(seed, layers, gpn, rnd.choice([1, 1, 10, 40]))
+    theirs = R.PipelineTemplateGenerator().create_pipeline_templates(results_from_rows(R, rows), (lo, hi), gpn)
+    mine = P.PipelineTemplateGenerator().create_pipeline_templates(results_from_rows(P, rows), (lo, hi), gpn)
+    assert [shape(t) for t in mine] == [shape(t) for t in theirs]
+    for a, b in zip(mine, theirs):
+        assert a._iteration_time == pytest.approx(b._iteration_time, rel=1e-12)
+
+
+# ---- the reference's own planner tests (tests/planning/test_pipeline_template.py), replayed on both ------------------
+def dummy_profile(mod, num_layers):
+    # tests/conftest.py get_dummy_profile: every layer 0.05 / 0.1 s, all-reduce 0.2 * gpus resp. nodes, 1 KiB
+    return mod.LayerExecutionResults([
+        mod.LayerExecutionResult(i, 0.05, 0.1, {g + 1: 0.2 * (g + 1) for g in range(8)}, {n + 1: 0.2 * (n + 1) for n in range(64)},
+                                 (1024, 1024)) for i in range(num_layers)])
+
+
+def both():
+    mods = [("this repo", P)]
+    R = reference_module()
+    if R is not None:
+        mods.append(("reference", R))
+    return mods
+
+
+@pytest.mark.parametrize("who,mod", both(), ids=[w for w, _ in both()])
+def test_reference_planner_tests_replayed(who, mod):
+    layers = 24
+    prof = dummy_profile(mod, layers)
+    gen = mod.PipelineTemplateGenerator()
+    # test_create_pipeline_templates_onegpu / _maxnode / _node_range / _multiple_gpus_in_node / _fsdp
+    for node_range, gpn in [((1, 1), 1), ((1, 8), 1), ((2, 8), 1), ((1, 6), 4), ((2, 5), 2)]:
+        ts = gen.create_pipeline_templates(prof, node_range, gpn)
+        assert len(ts) == node_range[1] - node_range[0] + 1
+        for n, t in zip(range(node_range[0], node_range[1] + 1), ts):
+            assert t._num_nodes == n and t._num_gpus_per_node == gpn
+            assert t._iteration_time > 0
+            stages = t.get_stages()
+            assert sum(s._num_gpus for s in stages) == n * gpn
+            covered = [i for s in stages for i in s._layer_indices]
+            assert covered == list(range(layers))                      # contiguous stages covering every layer once
+            assert n <= len(stages) <= layers
+    # a single GPU: exactly one stage holding everything
+    one = gen.create_pipeline_templates(prof, (1, 1), 1)[0]
+    assert len(one.get_stages()) == 1 and list(one.get_stages()[0]._layer_indices) == list(range(layers))
