@@ -17,11 +17,14 @@ installs *inert stubs* for exactly those third-party modules, then imports the r
 * ``OobleckPipelineSchedule.steps``             (pipeline.py:34-84)          -> schedule.json
 * ``DTYPE_TO_ID``                               (utils.py:4-18)              -> dtype_ids.json
 
-Two stand-ins carry logic and are therefore NOT pinned by this script (they are pinned by the tables of
-the reference's own tests instead, ported in tests/test_bookkeeping.py):
-  - ``PipelineTemplate.get_rank_grid`` (C++, pipeline_template.h:57-84) -> oracle.bookkeeping.Template
+One stand-in carries logic and is therefore NOT pinned by this script:
   - deepspeed ``TrainSchedule`` helper math (third party)                -> oracle.schedule helpers
-The reference's ``steps()`` override itself runs unmodified on top of the latter.
+The reference's ``steps()`` override itself runs unmodified on top of it.
+
+The C++ planner objects (``PipelineTemplate.get_rank_grid``, pipeline_template.h:57-84) come from the reference's OWN
+module when oracle/_ref holds it (``make -C oracle``; the default here) and from the restatement
+``oracle.bookkeeping.Template`` otherwise (``--restated-planner`` forces that).  Both produce byte-identical JSON files
+(checked by ``--check``, which regenerates into memory with each and compares with what is committed).
 """
 from __future__ import annotations
 
@@ -42,6 +45,38 @@ sys.path.insert(0, REF)
 
 from oracle import bookkeeping as bk  # noqa: E402
 from oracle import schedule as osched  # noqa: E402
+
+def real_planner_module():
+    """The reference's pybind11 module built by oracle/Makefile, or None."""
+    d = os.path.join(ROOT, "oracle", "_ref")
+    if not os.path.isdir(d):
+        return None
+    sys.path.insert(0, d)
+    try:
+        return importlib.import_module("pipeline_template")
+    except ImportError:
+        return None
+    finally:
+        sys.path.remove(d)
+
+
+REAL_PLANNER = None          # set by main()
+
+
+def make_template(num_layers: int, num_stages: int, num_gpus_per_node: int, num_nodes: int):
+    """tests/conftest.py:144-213 (get_dummy_pipeline_template): the same stage / GPU split either as the reference's
+    own C++ objects or as the restatement."""
+    t = bk.dummy_template(num_layers, num_stages, num_gpus_per_node, num_nodes)
+    if REAL_PLANNER is None:
+        return t
+    R = REAL_PLANNER
+    prof = R.LayerExecutionResults([
+        R.LayerExecutionResult(i, 0.5, 1.5, {g + 1: 0.1 for g in range(8)}, {n + 1: 0.1 for n in range(64)}, (1024, 1024))
+        for i in range(num_layers)])
+    stages = [R.StageExecutionResult(prof, (st._layer_indices[0], st._layer_indices[-1] + 1), st._num_gpus)
+              for st in t.get_stages()]
+    return R.PipelineTemplate(stages, 0.1, num_layers, num_nodes, num_gpus_per_node)
+
 
 STUB_ROOTS = {"deepspeed", "accelerate", "pyomo", "simple_parsing", "evaluate", "asyncssh", "aiofiles",
               "torchvision", "datasets"}
@@ -122,11 +157,14 @@ def install_stubs():
     _p.schedule = sched
 
     # C++ planner module stand-in (bookkeeping only)
-    pt = types.ModuleType("oobleck.csrc.planning.pipeline_template")
-    pt.PipelineTemplate = bk.Template
-    pt.StageExecutionResult = bk.Stage
-    for n in ["LayerExecutionResults", "LayerExecutionResult", "PipelineTemplateGenerator", "get_profile_results"]:
-        setattr(pt, n, MagicMock(name=n))
+    if REAL_PLANNER is not None:
+        pt = REAL_PLANNER
+    else:
+        pt = types.ModuleType("oobleck.csrc.planning.pipeline_template")
+        pt.PipelineTemplate = bk.Template
+        pt.StageExecutionResult = bk.Stage
+        for n in ["LayerExecutionResults", "LayerExecutionResult", "PipelineTemplateGenerator", "get_profile_results"]:
+            setattr(pt, n, MagicMock(name=n))
     for name in ["oobleck.csrc", "oobleck.csrc.planning"]:
         m = types.ModuleType(name)
         m.__path__ = []
@@ -170,7 +208,7 @@ def gen_reconfigure(engine_mod, out):
     cases = []
     rng = random.Random(1234)
     for gpn in (1, 2, 4):
-        templates = [bk.dummy_template(NUM_LAYERS, i, gpn, i) for i in range(2, 6)]
+        templates = [make_template(NUM_LAYERS, i, gpn, i) for i in range(2, 6)]
         total = sum(i * gpn for i in range(2, 6))
         node_sets = []
         for _ in range(40):
@@ -224,7 +262,7 @@ def gen_dp_groups(engine_mod, out):
     cases = []
     for gpn, nodes, npipes, nstages in [(4, [1, 2], [1, 1], [2, 2]), (4, [3], [2], [4]), (4, [3, 5], [2, 1], [4, 5]),
                                         (1, [4], [2], [4]), (1, [2, 3], [1, 2], [2, 3]), (2, [2, 4], [2, 1], [3, 5])]:
-        templates = [bk.dummy_template(NUM_LAYERS, s, gpn, n) for n, s in zip(nodes, nstages)]
+        templates = [make_template(NUM_LAYERS, s, gpn, n) for n, s in zip(nodes, nstages)]
         pipelines, used = [], 0
         for t, k in zip(templates, npipes):
             for _ in range(k):
@@ -271,17 +309,35 @@ def gen_schedule(out):
     out["schedule"] = cases
 
 
-def main():
-    install_stubs()
+def generate() -> dict:
     import oobleck.execution.utils as ref_utils
     import oobleck.execution.engine as engine_mod
-
     out = {}
     gen_reconfigure(engine_mod, out)
     gen_dp_groups(engine_mod, out)
     gen_sampler(out)
     gen_schedule(out)
     out["dtype_ids"] = {str(k).replace("torch.", ""): v for k, v in ref_utils.DTYPE_TO_ID.items()}
+    return out
+
+
+def main():
+    global REAL_PLANNER
+    check = "--check" in sys.argv
+    if "--restated-planner" not in sys.argv:
+        REAL_PLANNER = real_planner_module()
+    print("planner objects:", "the reference's own module (oracle/_ref)" if REAL_PLANNER is not None
+          else "oracle.bookkeeping restatement", file=sys.stderr)
+    install_stubs()
+    out = generate()
+    if check:
+        bad = []
+        for k, v in out.items():
+            with open(os.path.join(HERE, f"{k}.json")) as f:
+                if f.read() != json.dumps(v, separators=(",", ":")):
+                    bad.append(k)
+        print("check:", "all golden files reproduced" if not bad else f"DIFFERENT: {bad}", file=sys.stderr)
+        sys.exit(1 if bad else 0)
     for k, v in out.items():
         with open(os.path.join(HERE, f"{k}.json"), "w") as f:
             json.dump(v, f, separators=(",", ":"))

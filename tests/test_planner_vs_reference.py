@@ -154,3 +154,16 @@ def test_reference_planner_tests_replayed(who, mod):
     # a single GPU: exactly one stage holding everything
     one = gen.create_pipeline_templates(prof, (1, 1), 1)[0]
     assert len(one.get_stages()) == 1 and list(one.get_stages()[0]._layer_indices) == list(range(layers))
+
+
+def test_golden_bookkeeping_vectors_reproduce_with_the_references_own_planner_objects():
+    """tests/golden/{reconfigure,dp_groups,sampler,schedule,dtype_ids}.json come from the reference's own Python
+    (tests/golden/gen_golden.py).  With oracle/_ref built, the C++ ``PipelineTemplate`` objects inside that run are the
+    reference's own too -- and every committed file must come out byte for byte (``--check``)."""
+    import subprocess
+    if reference_module() is None or not os.path.isdir("/root/reference/oobleck"):
+        pytest.skip("needs /root/reference and oracle/_ref (make -C oracle)")
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "golden", "gen_golden.py"), "--check"],
+                       capture_output=True, text=True, timeout=600)
+    assert "the reference's own module" in r.stderr, r.stderr[-2000:]
+    assert r.returncode == 0 and "all golden files reproduced" in r.stderr, r.stderr[-2000:]
