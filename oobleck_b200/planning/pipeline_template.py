@@ -31,8 +31,16 @@ class LayerExecutionResult:
         self._mem_required = (int(mem_required[0]), int(mem_required[1]))
 
 
+class _Size(int):
+    """``LayerExecutionResults.size``: a read-only PROPERTY in the reference's binding (bind.cpp:38, and how its tests use
+    it: ``profile.size``), a METHOD in its stub file (pipeline_template.pyi:21).  Both spellings work here."""
+
+    def __call__(self) -> int:
+        return int(self)
+
+
 class LayerExecutionResults:
-    """pipeline_template.pyi:18-21."""
+    """pipeline_template.pyi:18-21 / bind.cpp:33-38."""
 
     def __init__(self, data: list[LayerExecutionResult]):
         self._data = list(data)
@@ -43,18 +51,45 @@ class LayerExecutionResults:
     def at(self, index: int) -> LayerExecutionResult:
         return self._data[index]
 
-    def size(self) -> int:
-        return len(self._data)
+    @property
+    def size(self) -> _Size:
+        return _Size(len(self._data))
 
 
 class StageExecutionResult:
-    def __init__(self, layer_indices: Sequence[int], num_gpus: int = 1):
-        self._layer_indices = list(layer_indices)
-        self._num_gpus = num_gpus
-        self._size = len(self._layer_indices)
+    """execution_result.h:60-112.  Two ways to build one: the reference's ``StageExecutionResult(layer_results,
+    (begin, end), num_gpus)`` (bind.cpp:40-43), which aggregates the layers' times and memory like the C++ constructor,
+    and the bookkeeping-only ``StageExecutionResult(layer_indices, num_gpus)`` used where only the shape matters."""
+
+    def __init__(self, layers_or_indices, layer_indices_or_num_gpus=1, num_gpus: int | None = None):
+        self._forward = 0.0
+        self._backward = 0.0
         self._mem_required = 0
+        if isinstance(layers_or_indices, LayerExecutionResults):
+            begin, end = layer_indices_or_num_gpus
+            assert num_gpus is not None and end <= layers_or_indices.size
+            self._num_gpus = int(num_gpus)
+            self._layer_indices = []
+            for i in range(begin, end):
+                layer = layers_or_indices.at(i)
+                assert layer._forward > 0 and layer._backward > 0                      # execution_result.h:74-75
+                self._layer_indices.append(layer._index)
+                self._forward += layer._forward / self._num_gpus
+                self._backward += layer._backward / self._num_gpus
+                if self._num_gpus > 1:                                                  # :81-84 (``.at``: must exist)
+                    self._forward += layer._allreduce_in_node[self._num_gpus]
+                    self._backward += layer._allreduce_in_node[self._num_gpus]
+                self._mem_required += 6 * layer._mem_required[0] + layer._mem_required[1]
+        else:
+            self._layer_indices = list(layers_or_indices)
+            self._num_gpus = int(layer_indices_or_num_gpus if num_gpus is None else num_gpus)
+        self._size = len(self._layer_indices)
 
     def num_layers(self) -> int:
+        return len(self._layer_indices)
+
+    @property
+    def _num_layers(self) -> int:          # bind.cpp:48
         return len(self._layer_indices)
 
 
