@@ -201,8 +201,12 @@ class PipelineTemplateGenerator:
                 begin, end, gpus = out[pos], out[pos + 1], out[pos + 2]
                 pos += 3
                 st = StageExecutionResult(range(begin, end), gpus)
-                st._mem_required = sum(6 * layer_execution_results.at(i)._mem_required[0]
-                                       + layer_execution_results.at(i)._mem_required[1] for i in range(begin, end))
+                for i in range(begin, end):            # the aggregates the search itself used (execution_result.h:66-100)
+                    layer = layer_execution_results.at(i)
+                    ar = float(layer._allreduce_in_node.get(gpus, 0.0)) if gpus > 1 else 0.0
+                    st._forward += layer._forward / gpus + ar
+                    st._backward += layer._backward / gpus + ar
+                    st._mem_required += 6 * layer._mem_required[0] + layer._mem_required[1]
                 stages.append(st)
             templates.append(PipelineTemplate(stages, times[t], n, nodes, num_gpus_per_node))
         return templates

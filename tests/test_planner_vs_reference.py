@@ -63,6 +63,8 @@ def test_template_search_reproduces_the_reference_planner(case):
         assert got._iteration_time == pytest.approx(want["iteration_time"], rel=1e-12)
         for s, ws in zip(got.get_stages(), want["stages"]):
             assert s._mem_required == ws["mem_required"]          # 6 x parameter bytes + activation bytes per layer
+            assert s._forward == pytest.approx(ws["forward"], rel=1e-13)
+            assert s._backward == pytest.approx(ws["backward"], rel=1e-13)
         grid = got.get_rank_grid(want["ranks"])
         assert {str(k): v for k, v in grid.items()} == want["rank_grid"]
         assert list(grid) == sorted(grid)                          # std::map order
