@@ -123,6 +123,12 @@ class _ParamHandle:
     def uses_sharded_strategy(self) -> bool:
         return self._sharding_strategy != "NO_SHARD"
 
+    @property
+    def world_size(self) -> int:
+        """FlatParamHandle.world_size: ranks the layer's state is spread over (read by the reference's tests,
+        tests/execution/test_engine.py:996)."""
+        return self.process_group.size() if hasattr(self.process_group, "size") else 1
+
 
 class Layer:
     """Constructor keeps the reference's positional order (layer.py:71-78)."""

@@ -19,6 +19,10 @@ class _Handle:
         self.process_group = process_group
         self._sharding_strategy = "FULL_SHARD" if sharded else "NO_SHARD"
 
+    @property
+    def world_size(self) -> int:
+        return self.process_group.size() if hasattr(self.process_group, "size") else 1
+
 
 class OracleAdamW:
     def __init__(self, layers, lr, betas, eps, weight_decay=0.01):
