@@ -93,3 +93,36 @@ def measured_layer_results(model, microbatch: int, device: torch.device | None =
     return LayerExecutionResults([
         LayerExecutionResult(i, t[l.kind][0], t[l.kind][1], {}, {}, (4 * l.num_params, l.activation_bytes(microbatch)))
         for i, l in enumerate(model.layers)])
+
+
+# ---- the reference's profile cache (planning/profiler.py:246-320 writes it, csrc get_profile_results reads it) -----------
+PROFILE_CACHE = "/tmp/oobleck/profiles"       # profiler.py:23
+
+
+def get_profile_path(model_name: str, model_tag: str, cache: str | None = None):
+    """profiler.py:246-247."""
+    from pathlib import Path
+    return Path(cache or PROFILE_CACHE) / f"{model_name}-{model_tag}"
+
+
+def save_profile_results(results, model_name: str, model_tag: str, microbatch_size: int, cache: str | None = None):
+    """Write a ``LayerExecutionResults`` where the reference's control plane looks for it, in its own file format, so that
+    its unchanged ``get_profile_results(model_name, model_tag, microbatch_size)`` (C++, pipeline_template.cpp:26-79; called
+    from ``OobleckEngine._initialize_engine``, engine.py:485-489) reads back exactly this profile:
+
+        <cache>/<model_name>-<model_tag>/mb<microbatch_size>.json      [{"forward", "backward", "mem_required": [p, a]}, ...]
+        <cache>/<model_name>-<model_tag>/allreduce_in_node.json        [{"<gpus>": ms, ...}, ...]       one dict per layer
+        <cache>/<model_name>-<model_tag>/allreduce_across_nodes.json   [{"<nodes>": ms, ...}, ...]
+
+    (what ``profile()`` dumps at profiler.py:296-320).  Returns the directory."""
+    import json
+    directory = get_profile_path(model_name, model_tag, cache)
+    directory.mkdir(parents=True, exist_ok=True)
+    layers = results.get()
+    with (directory / f"mb{microbatch_size}.json").open("w") as f:
+        json.dump([{"forward": l._forward, "backward": l._backward, "mem_required": list(l._mem_required)} for l in layers], f)
+    with (directory / "allreduce_in_node.json").open("w") as f:
+        json.dump([{str(k): v for k, v in l._allreduce_in_node.items()} for l in layers], f)
+    with (directory / "allreduce_across_nodes.json").open("w") as f:
+        json.dump([{str(k): v for k, v in l._allreduce_across_nodes.items()} for l in layers], f)
+    return directory

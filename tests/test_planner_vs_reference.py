@@ -231,3 +231,26 @@ def test_golden_bookkeeping_vectors_reproduce_with_the_references_own_planner_ob
                        capture_output=True, text=True, timeout=600)
     assert "the reference's own module" in r.stderr, r.stderr[-2000:]
     assert r.returncode == 0 and "all golden files reproduced" in r.stderr, r.stderr[-2000:]
+
+
+def test_saved_profile_is_what_the_references_get_profile_results_reads():
+    """planning/profiler.py::save_profile_results -> the reference's C++ ``get_profile_results`` (it reads
+    /tmp/oobleck/profiles/<model>-<tag>/, pipeline_template.cpp:26-79)."""
+    R = reference_module()
+    if R is None:
+        pytest.skip("oracle/_ref not built (make -C oracle needs /root/reference)")
+    from gen_planner_golden import profile_rows
+    from oobleck_b200.planning.profiler import save_profile_results
+    rows = profile_rows(21, 7, 4)
+    mine = results_from_rows(P, rows)
+    tag = "b200_saved_profile_test"
+    directory = save_profile_results(mine, "gpt2", tag, 3)
+    assert str(directory) == f"/tmp/oobleck/profiles/gpt2-{tag}"
+    back = R.get_profile_results("gpt2", tag, 3)
+    assert back.size == mine.size == 7
+    for a, b in zip(mine.get(), back.get()):
+        assert b._index == a._index
+        assert b._forward == a._forward and b._backward == a._backward            # JSON round-trips doubles exactly
+        assert dict(b._allreduce_in_node) == a._allreduce_in_node
+        assert dict(b._allreduce_across_nodes) == a._allreduce_across_nodes
+        assert tuple(b._mem_required) == a._mem_required

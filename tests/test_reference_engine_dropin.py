@@ -22,7 +22,6 @@ pyomo (``_distribute_batch``, a MINLP: an even integer split), HF ``TrainingArgu
 it), the wikitext download (``OobleckDataset`` -> the synthetic corpus), CUDA / NCCL (``backend="nccl"`` -> gloo, the oracle's
 torch layers as stage compute, ``torch.cuda.synchronize`` a no-op).  The trained parameters must match a single-process run.
 """
-import json
 import os
 import sys
 import threading
@@ -51,19 +50,18 @@ def available() -> bool:
 
 def write_profile_files():
     """What the reference's profiler leaves under /tmp/oobleck/profiles/<model>-<tag>/ and ``get_profile_results`` (C++,
-    pipeline_template.cpp:26-79) reads back: per-layer forward / backward / mem_required, and the two all-reduce tables."""
+    pipeline_template.cpp:26-79) reads back -- written by this package's ``save_profile_results``."""
     from oobleck_b200.execution.engine import layer_cost_model
     from oobleck_b200.module.model import OobleckModel
+    from oobleck_b200.planning.pipeline_template import LayerExecutionResult, LayerExecutionResults
+    from oobleck_b200.planning.profiler import save_profile_results
     model = OobleckModel("gpt2", {"input_ids": None}, None, TAG, dict(MARGS))
     costs = layer_cost_model(model, 1)
-    d = f"/tmp/oobleck/profiles/gpt2-{TAG}"
-    os.makedirs(d, exist_ok=True)
-    mb = [{"forward": c / 3e6, "backward": 2 * c / 3e6, "mem_required": [4 * l.num_params, l.activation_bytes(1)]}
-          for c, l in zip(costs, model.layers)]
-    json.dump(mb, open(os.path.join(d, "mb1.json"), "w"))
-    json.dump([{str(g + 1): 1e-4 * (g + 1) for g in range(8)} for _ in mb], open(os.path.join(d, "allreduce_in_node.json"), "w"))
-    json.dump([{str(n + 1): 1e-3 * (n + 1) for n in range(64)} for _ in mb],
-              open(os.path.join(d, "allreduce_across_nodes.json"), "w"))
+    results = LayerExecutionResults([
+        LayerExecutionResult(i, c / 3e6, 2 * c / 3e6, {g + 1: 1e-4 * (g + 1) for g in range(8)},
+                             {n + 1: 1e-3 * (n + 1) for n in range(64)}, (4 * l.num_params, l.activation_bytes(1)))
+        for i, (c, l) in enumerate(zip(costs, model.layers))])
+    save_profile_results(results, "gpt2", TAG, 1)
 
 
 def bind_reference():
