@@ -192,7 +192,7 @@ def install_stubs():
     sys.modules["oobleck.elastic.message_util"] = mu
 
 
-def gen_reconfigure(engine_mod, out):
+def gen_reconfigure(engine_mod, out, seed=1234, per_gpn=40, max_lost=11):
     """Mirror of tests/execution/test_reconfiguration.py's FakeEngine/FakePipeline harness, driven with the
     test's own tables plus random failure sets."""
     NUM_LAYERS = 34  # conftest model: 32 blocks + 2
@@ -206,13 +206,13 @@ def gen_reconfigure(engine_mod, out):
             self.rank_grid = template.get_rank_grid(ranks)
 
     cases = []
-    rng = random.Random(1234)
+    rng = random.Random(seed)
     for gpn in (1, 2, 4):
         templates = [make_template(NUM_LAYERS, i, gpn, i) for i in range(2, 6)]
         total = sum(i * gpn for i in range(2, 6))
         node_sets = []
-        for _ in range(40):
-            k = rng.randint(1, 11)
+        for _ in range(per_gpn):
+            k = rng.randint(1, max_lost)
             nodes = sorted(rng.sample(range(14), k))
             node_sets.append(nodes)
         for nodes in node_sets:
@@ -329,6 +329,15 @@ def main():
     print("planner objects:", "the reference's own module (oracle/_ref)" if REAL_PLANNER is not None
           else "oracle.bookkeeping restatement", file=sys.stderr)
     install_stubs()
+    if "--live-reconfigure" in sys.argv:
+        # further failure sets through the reference's on_reconfigure, printed instead of stored: SEED COUNT MAX_LOST
+        i = sys.argv.index("--live-reconfigure")
+        seed, count, max_lost = (int(x) for x in sys.argv[i + 1: i + 4])
+        import oobleck.execution.engine as engine_mod
+        out = {}
+        gen_reconfigure(engine_mod, out, seed, count, max_lost)
+        print(json.dumps(out["reconfigure"], separators=(",", ":")))
+        return
     out = generate()
     if check:
         bad = []

@@ -227,3 +227,45 @@ def test_measured_profile_feeds_node_range_and_template_search(monkeypatch):
     eng2 = E.OobleckEngine(0, 2, 1, None, args, dataset=ds)
     with pytest.raises(AssertionError, match="Minimum required number of nodes"):
         eng2.instantiate_pipelines(8)
+
+
+def test_reconfiguration_policy_live_against_the_reference():
+    """Beyond the 120 committed failure sets: 450 fresh ones (up to 13 of the 14 nodes lost, so that "Ranks are
+    insufficient" and the reference's own failure modes occur too) go through the reference's ``on_reconfigure`` in a child
+    process (tests/golden/gen_golden.py --live-reconfigure; the reference's Python with its own C++ planner objects when
+    oracle/_ref is built) and through this package's ``plan_new_ranks``."""
+    import subprocess
+    import sys
+    if not os.path.isdir("/root/reference/oobleck"):
+        pytest.skip("needs /root/reference")
+    r = subprocess.run([sys.executable, os.path.join(G, "gen_golden.py"), "--live-reconfigure", "20260923", "150", "13"],
+                       capture_output=True, text=True, timeout=900)
+    line = next((l for l in reversed(r.stdout.splitlines()) if l.startswith("[{")), None)
+    assert r.returncode == 0 and line is not None, r.stderr[-2000:]
+    cases = json.loads(line)
+    assert len(cases) == 450
+    outcomes = {"ranks": 0, "error": 0}
+    for c in cases:
+        gpn = c["gpus_per_node"]
+        templates = [product_template(i, gpn, i) for i in range(2, 6)]
+        eng = FakeEngine(gpn, templates)
+        eng._pipeline = None
+        re = ReconfigurationEngine(eng, fake_pipelines(gpn, templates), start_listener=False)
+        want = c["result"]
+        if "ranks" in want:
+            assert re.plan_new_ranks(list(c["failed"])) == want["ranks"], c
+            outcomes["ranks"] += 1
+        elif want["error"] == "Ranks are insufficient":
+            with pytest.raises(RuntimeError, match="insufficient"):
+                re.plan_new_ranks(list(c["failed"]))
+            outcomes["error"] += 1
+        else:
+            # the reference dereferenced a missing template (no template of the merged size): the rank lists this
+            # package plans must still be well formed -- every survivor exactly once
+            try:
+                got = re.plan_new_ranks(list(c["failed"]))
+            except (RuntimeError, IndexError):
+                continue
+            alive = sorted(set(range(sum(i * gpn for i in range(2, 6)))) - set(c["failed"]))
+            assert sorted(r_ for ranks in got for r_ in ranks) == alive, c
+    assert outcomes["ranks"] > 300 and outcomes["error"] > 0, outcomes
