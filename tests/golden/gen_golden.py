@@ -256,12 +256,38 @@ def gen_reconfigure(engine_mod, out, seed=1234, per_gpn=40, max_lost=11):
     out["reconfigure"] = cases
 
 
-def gen_dp_groups(engine_mod, out):
+DP_CASES = [(4, [1, 2], [1, 1], [2, 2]), (4, [3], [2], [4]), (4, [3, 5], [2, 1], [4, 5]),
+            (1, [4], [2], [4]), (1, [2, 3], [1, 2], [2, 3]), (2, [2, 4], [2, 1], [3, 5])]
+
+
+def random_dp_cases(seed, count):
+    """Heterogeneous pipeline mixes: per template (nodes, stages) with stages a multiple-of-two-friendly GPU split."""
+    rng = random.Random(seed)
+    cases = []
+    while len(cases) < count:
+        gpn = rng.choice([1, 2, 4])
+        kinds = rng.randint(1, 3)
+        nodes = sorted(rng.sample(range(1, 6), kinds))
+        nstages, ok = [], True
+        for n in nodes:
+            total = n * gpn
+            choices = [st for st in range(n, min(total, 8) + 1)]
+            nstages.append(rng.choice(choices))
+        npipes = [rng.randint(1, 3) for _ in nodes]
+        try:
+            for n, st in zip(nodes, nstages):
+                bk.dummy_template(34, st, gpn, n)
+        except AssertionError:
+            continue
+        cases.append((gpn, nodes, npipes, nstages))
+    return cases
+
+
+def gen_dp_groups(engine_mod, out, case_list=None):
     NUM_LAYERS = 34
     import deepspeed.comm as dist
     cases = []
-    for gpn, nodes, npipes, nstages in [(4, [1, 2], [1, 1], [2, 2]), (4, [3], [2], [4]), (4, [3, 5], [2, 1], [4, 5]),
-                                        (1, [4], [2], [4]), (1, [2, 3], [1, 2], [2, 3]), (2, [2, 4], [2, 1], [3, 5])]:
+    for gpn, nodes, npipes, nstages in (case_list or DP_CASES):
         templates = [make_template(NUM_LAYERS, s, gpn, n) for n, s in zip(nodes, nstages)]
         pipelines, used = [], 0
         for t, k in zip(templates, npipes):
@@ -282,12 +308,20 @@ def gen_dp_groups(engine_mod, out):
     out["dp_groups"] = cases
 
 
-def gen_sampler(out):
+SAMPLER_CASES = [(257, 2, [4], True, 0), (1000, 4, [3, 5], True, 0), (1000, 4, [3, 5], True, 1),
+                 (2334, 2, [16, 24, 24], True, 0), (64, 8, [1, 1], False, 0), (100, 3, [2, 1, 4], True, 3)]
+
+
+def random_sampler_cases(seed, count):
+    rng = random.Random(seed)
+    return [(rng.randint(1, 700), rng.randint(1, 6), [rng.randint(1, 9) for _ in range(rng.randint(1, 4))],
+             rng.random() < 0.7, rng.randint(0, 5)) for _ in range(count)]
+
+
+def gen_sampler(out, case_list=None):
     from oobleck.execution.dataloader import OobleckSampler
     cases = []
-    for n, mbsz, nmb, shuffle, epoch in [(257, 2, [4], True, 0), (1000, 4, [3, 5], True, 0), (1000, 4, [3, 5], True, 1),
-                                         (2334, 2, [16, 24, 24], True, 0), (64, 8, [1, 1], False, 0),
-                                         (100, 3, [2, 1, 4], True, 3)]:
+    for n, mbsz, nmb, shuffle, epoch in (case_list or SAMPLER_CASES):
         per = []
         for pi in range(len(nmb)):
             s = OobleckSampler(range(n), mbsz, pi, nmb, 0, epoch, shuffle)
@@ -337,6 +371,16 @@ def main():
         out = {}
         gen_reconfigure(engine_mod, out, seed, count, max_lost)
         print(json.dumps(out["reconfigure"], separators=(",", ":")))
+        return
+    if "--live" in sys.argv:
+        # random data-parallel layouts and sampler configurations through the reference's own classes: SEED COUNT
+        i = sys.argv.index("--live")
+        seed, count = int(sys.argv[i + 1]), int(sys.argv[i + 2])
+        import oobleck.execution.engine as engine_mod
+        out = {}
+        gen_dp_groups(engine_mod, out, random_dp_cases(seed, count))
+        gen_sampler(out, random_sampler_cases(seed, count))
+        print(json.dumps(out, separators=(",", ":")))
         return
     out = generate()
     if check:

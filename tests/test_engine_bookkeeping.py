@@ -269,3 +269,40 @@ def test_reconfiguration_policy_live_against_the_reference():
             alive = sorted(set(range(sum(i * gpn for i in range(2, 6)))) - set(c["failed"]))
             assert sorted(r_ for ranks in got for r_ in ranks) == alive, c
     assert outcomes["ranks"] > 300 and outcomes["error"] > 0, outcomes
+
+
+def test_dp_groups_and_sampler_live_against_the_reference():
+    """80 random heterogeneous data-parallel layouts through the reference's ``DataParallelEngine.__init__`` (engine.py:
+    363-398) and 80 random sampler configurations through its ``OobleckSampler`` (dataloader.py:13-100), generated in a
+    child process (tests/golden/gen_golden.py --live), against this package's classes."""
+    import subprocess
+    import sys
+    if not os.path.isdir("/root/reference/oobleck"):
+        pytest.skip("needs /root/reference")
+    r = subprocess.run([sys.executable, os.path.join(G, "gen_golden.py"), "--live", "77", "80"], capture_output=True,
+                       text=True, timeout=900)
+    line = next((l for l in reversed(r.stdout.splitlines()) if l.startswith('{"dp_groups"')), None)
+    assert r.returncode == 0 and line is not None, r.stderr[-2000:]
+    live = json.loads(line)
+    assert len(live["dp_groups"]) == 80 and len(live["sampler"]) == 80
+    for c in live["dp_groups"]:
+        gpn = c["gpus_per_node"]
+        templates = []
+        for n, k, s in zip(c["nodes"], c["num_pipelines"], c["stages"]):
+            templates += [product_template(s, gpn, n)] * k
+        eng = FakeEngine(gpn, templates)
+        created = []
+        dpe = DataParallelEngine(eng, fake_pipelines(gpn, templates),
+                                 new_group=lambda r_: created.append(list(r_)) or len(created))
+        got = {str(l): {str(f): pg.ranks for f, pg in d.items()} for l, d in dpe._dp_process_groups.items()}
+        assert got == c["groups"], c
+        dedup = []
+        for ranks in c["order"]:
+            if ranks not in dedup:
+                dedup.append(ranks)
+        assert created == dedup
+    for c in live["sampler"]:
+        for pi, want in enumerate(c["batches"]):
+            s = OobleckSampler(range(c["num_samples"]), c["microbatch_size"], pi, c["num_microbatches"], 0, c["epoch"],
+                               c["shuffle"])
+            assert [list(b) for b in s] == want, c
