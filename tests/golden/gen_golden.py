@@ -318,6 +318,44 @@ def random_sampler_cases(seed, count):
              rng.random() < 0.7, rng.randint(0, 5)) for _ in range(count)]
 
 
+def gen_wiring(out, seed, count):
+    """The reference's unmodified ``OobleckPipeline.__init__`` / ``initialize_distributed_fsdp`` /
+    ``initialize_distributed_pipeline`` (pipeline.py:431-456, 565-617) for every rank of random templates: who is my
+    previous / next stage, which per-layer and per-shard-column groups exist (``list(set(ranks))`` order included)."""
+    import deepspeed.comm as dist
+    from oobleck.execution.pipeline import OobleckPipeline
+    rng = random.Random(seed)
+    cases = []
+    while len(cases) < count:
+        gpn = rng.choice([1, 1, 2, 4])
+        nodes = rng.randint(1, 5)
+        stages = rng.randint(nodes, min(nodes * gpn, 8))
+        try:
+            bk.dummy_template(34, stages, gpn, nodes)
+        except AssertionError:
+            continue
+        template = make_template(34, stages, gpn, nodes)
+        first = rng.randint(0, 40)
+        ranks = list(range(first, first + nodes * gpn))
+        per_rank = {}
+        for me in ranks + [first + nodes * gpn + 3]:                 # every member, and one outsider
+            groups = []
+            dist.is_initialized = lambda: True
+            dist.get_rank = lambda *a, me=me, **k: me
+            dist.new_group = lambda r: groups.append(list(r)) or types.SimpleNamespace(ranks=list(r))
+            p = OobleckPipeline(0, template, list(ranks), None, 0, None)
+            p.initialize_distributed_fsdp()
+            layer_groups, groups[:] = [list(g) for g in groups], []
+            p.initialize_distributed_pipeline()
+            comm = p.communication
+            per_rank[str(me)] = {"my_pipeline": p.my_pipeline, "layer_groups": layer_groups,
+                                 "shard_groups": [list(g) for g in groups],
+                                 "prev": None if comm is None else comm.prev_rank,
+                                 "next": None if comm is None else comm.next_rank, "has_comm": comm is not None}
+        cases.append({"gpus_per_node": gpn, "nodes": nodes, "stages": stages, "ranks": ranks, "per_rank": per_rank})
+    out["wiring"] = cases
+
+
 def gen_sampler(out, case_list=None):
     from oobleck.execution.dataloader import OobleckSampler
     cases = []
@@ -380,6 +418,7 @@ def main():
         out = {}
         gen_dp_groups(engine_mod, out, random_dp_cases(seed, count))
         gen_sampler(out, random_sampler_cases(seed, count))
+        gen_wiring(out, seed, count)
         print(json.dumps(out, separators=(",", ":")))
         return
     out = generate()

@@ -306,3 +306,52 @@ def test_dp_groups_and_sampler_live_against_the_reference():
             s = OobleckSampler(range(c["num_samples"]), c["microbatch_size"], pi, c["num_microbatches"], 0, c["epoch"],
                                c["shuffle"])
             assert [list(b) for b in s] == want, c
+
+
+def test_pipeline_wiring_live_against_the_reference():
+    """The reference's unmodified ``OobleckPipeline.__init__`` / ``initialize_distributed_fsdp`` /
+    ``initialize_distributed_pipeline`` (pipeline.py:431-456, 565-617), run for every rank of 60 random templates in a child
+    process (gen_golden.py --live), against this package's methods of the same names: membership of the pipeline, previous /
+    next stage rank, per-layer holders, per-shard-column groups in the reference's ``list(set(ranks))`` order.  Templates
+    whose stages own different numbers of GPUs are the stated limit (the reference leaves sends without a receiver there,
+    pipeline.py:602-610): this package refuses them, and says so."""
+    import subprocess
+    import sys
+
+    import oobleck_b200.execution.pipeline as P
+    if not os.path.isdir("/root/reference/oobleck"):
+        pytest.skip("needs /root/reference")
+    r = subprocess.run([sys.executable, os.path.join(G, "gen_golden.py"), "--live", "4242", "60"], capture_output=True,
+                       text=True, timeout=900)
+    line = next((l for l in reversed(r.stdout.splitlines()) if l.startswith('{"dp_groups"')), None)
+    assert r.returncode == 0 and line is not None, r.stderr[-2000:]
+    cases = json.loads(line)["wiring"]
+    assert len(cases) == 60
+    compared = refused = 0
+    orig = P._my_rank
+    try:
+        for c in cases:
+            t = product_template(c["stages"], c["gpus_per_node"], c["nodes"])
+            widths = {s._num_gpus for s in t.get_stages()}
+            for me_s, want in c["per_rank"].items():
+                me = int(me_s)
+                P._my_rank = lambda me=me: me
+                p = OobleckPipeline(0, t, list(c["ranks"]), None, 0, None, layer_cls=types.SimpleNamespace(device_type="cpu"),
+                                    stage_group_factory=lambda ranks: ("comm", tuple(ranks)))
+                assert p.my_pipeline == want["my_pipeline"]
+                if len(widths) > 1:
+                    with pytest.raises(NotImplementedError, match="different widths"):
+                        p.initialize_distributed_fsdp()
+                    refused += 1
+                    continue
+                p.initialize_distributed_fsdp()
+                p.initialize_distributed_pipeline()
+                assert [sorted(pg.ranks) for pg in p._per_layer_pgs.values()] == [sorted(g) for g in want["layer_groups"]]
+                assert [pg.ranks for pg in p._per_sharded_pp_pgs.values()] == want["shard_groups"]
+                assert (p.communication is not None) == want["has_comm"]
+                if want["has_comm"]:
+                    assert (p.communication.prev_rank, p.communication.next_rank) == (want["prev"], want["next"]), (c, me)
+                compared += 1
+    finally:
+        P._my_rank = orig
+    assert compared > 100 and refused > 0, (compared, refused)
