@@ -15,3 +15,16 @@ def pytest_configure(config):
 @pytest.fixture(scope="session")
 def golden_dir():
     return os.path.join(ROOT, "tests", "golden")
+
+
+@pytest.fixture(autouse=True)
+def _no_workers_left_behind():
+    """Multi-process tests spawn gloo workers.  When one of them fails, its peers may sit in a collective for minutes; left
+    alive they load the host and make the tests that follow time out in turn.  Whatever a test leaves behind is terminated
+    here."""
+    yield
+    import multiprocessing
+    for p in multiprocessing.active_children():
+        p.terminate()
+    for p in multiprocessing.active_children():
+        p.join(5)

@@ -25,6 +25,10 @@ sys.path.insert(0, os.path.join(ROOT, "tests"))
 MARGS = dict(n_embd=64, n_head=1, num_hidden_layers=2, n_positions=32, vocab_size=211)
 AGENT_IPS = ["127.0.0.1", "127.0.0.2", "127.0.0.3", "127.0.0.4"]
 M, MB, STEPS_BEFORE, STEPS_TOTAL = 4, 1, 2, 4
+# gloo's per-operation timeout.  Nothing in a passing run waits for it (a dead peer closes its sockets: the survivors'
+# operations fail at once, and the listener's abort releases everything else); it only decides how long a merely SLOW
+# neighbour -- a loaded CI host, eight single-threaded workers on fewer cores -- is waited for before the step is given up.
+COMM_TIMEOUT_S = 90
 
 
 def scenario(mode):
@@ -76,7 +80,7 @@ def worker(rank, pipe, q, ready, mode):
         # worker_main's call sequence: ctor(local_rank, num_nodes, gpus_per_node, pipe, args) -> initialize_distributed
         # -> instantiate_pipelines -> train
         eng = OobleckEngine(0, len(AGENT_IPS), 1, pipe, args, dataset=ds, layer_cls=OracleLayer, templates=templates,
-                            backend="gloo", comm_timeout_s=20, peer_shadow=mode.startswith("lone"))
+                            backend="gloo", comm_timeout_s=COMM_TIMEOUT_S, peer_shadow=mode.startswith("lone"))
         eng.initialize_distributed()
         assert eng._rank == rank and eng._world_size == world and eng._rank_map[AGENT_IPS[rank]] == [rank]
         eng.instantiate_pipelines(M, plan=plan)
@@ -194,12 +198,17 @@ def test_engine_driven_through_agent_pipe_survives_a_dead_node(mode):
     t = threading.Thread(target=agent, daemon=True)
     t.start()
     results = {}
-    for _ in range(world):
-        r = q.get(timeout=500)
-        results[r[0]] = r
-    t.join(timeout=60)
-    for p in procs:
-        p.join(timeout=60)
+    try:
+        for _ in range(world):
+            r = q.get(timeout=500)
+            results[r[0]] = r
+        t.join(timeout=60)
+        for p in procs:
+            p.join(timeout=60)
+    finally:
+        for p in procs:              # never leave workers behind: they would load the host for the tests that follow
+            if p.is_alive():
+                p.terminate()
     assert results[victim][1] == "gone"
     survivors = range(victim)
     for r in survivors:

@@ -52,7 +52,7 @@ def worker(rank, pipe, q, ready):
                                 model=ModelArguments(model_name="gpt2", model_tag="t", model_args=dict(MARGS)))
         ds = SyntheticTokenDataset(num_samples=256, seq_len=32, vocab_size=211, pin_memory=False)
         eng = OobleckEngine(0, WORLD, 1, pipe, args, dataset=ds, layer_cls=OracleLayer, templates=templates,
-                            backend="gloo", comm_timeout_s=30, peer_shadow=True)
+                            backend="gloo", comm_timeout_s=90, peer_shadow=True)
         eng.initialize_distributed()
         eng.instantiate_pipelines(M, plan=[templates[1], templates[1]])
         orig_step = eng._guarded_train_step
@@ -147,12 +147,17 @@ def test_two_nodes_lost_one_after_the_other():
     t = threading.Thread(target=agent, daemon=True)
     t.start()
     results = {}
-    for _ in range(WORLD):
-        r = q.get(timeout=800)
-        results[r[0]] = r
-    t.join(timeout=60)
-    for p in procs:
-        p.join(timeout=60)
+    try:
+        for _ in range(WORLD):
+            r = q.get(timeout=800)
+            results[r[0]] = r
+        t.join(timeout=60)
+        for p in procs:
+            p.join(timeout=60)
+    finally:
+        for p in procs:
+            if p.is_alive():
+                p.terminate()
     victims = [v for _, v in LOSSES]
     for v in victims:
         assert results[v][1] == "gone"

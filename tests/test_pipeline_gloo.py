@@ -120,9 +120,14 @@ def run_spawn(fn, world, *a):
         procs = [ctx.Process(target=fn, args=(r, world, port, *a, q)) for r in range(world)]
         for p in procs:
             p.start()
-        results = [q.get(timeout=240) for _ in range(world)]
-        for p in procs:
-            p.join(timeout=60)
+        try:
+            results = [q.get(timeout=240) for _ in range(world)]
+            for p in procs:
+                p.join(timeout=60)
+        finally:
+            for p in procs:          # never leave workers behind: they would load the host for the tests that follow
+                if p.is_alive():
+                    p.terminate()
         errors = [r[3] for r in results if r[3] is not None]
         if errors and attempt == 0 and any("init_process_group" in e and any(t in e for t in RENDEZVOUS_TROUBLE)
                                            for e in errors):

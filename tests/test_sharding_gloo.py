@@ -244,7 +244,7 @@ def worker_nodes(rank, pipe, q, ready):
         two_nodes = wide_template(4, 2, GPN, 2, GPN)         # two 2-GPU stages
         # worker_main's call sequence (elastic/worker.py:23-34), two workers per node
         eng = OobleckEngine(local_rank, len(NODE_IPS), GPN, pipe, args, dataset=ds, layer_cls=OracleLayer,
-                            templates=[one_node, two_nodes], backend="gloo", comm_timeout_s=20)
+                            templates=[one_node, two_nodes], backend="gloo", comm_timeout_s=90)
         eng.initialize_distributed()
         assert eng._rank == rank and eng._rank_map[NODE_IPS[node]] == [node * GPN, node * GPN + 1]
         eng.instantiate_pipelines(M, plan=[two_nodes, two_nodes])
