@@ -419,6 +419,8 @@ def main():
         gen_dp_groups(engine_mod, out, random_dp_cases(seed, count))
         gen_sampler(out, random_sampler_cases(seed, count))
         gen_wiring(out, seed, count)
+        if len(sys.argv) > i + 4:          # ... RECONFIGURE_COUNT MAX_LOST: failure sets through on_reconfigure as well
+            gen_reconfigure(engine_mod, out, seed, int(sys.argv[i + 3]), int(sys.argv[i + 4]))
         print(json.dumps(out, separators=(",", ":")))
         return
     out = generate()

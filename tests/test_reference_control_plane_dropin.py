@@ -162,8 +162,8 @@ def worker(rank, world, port, option, M, steps, q):
 
 
 @pytest.mark.timeout(400)
-@pytest.mark.parametrize("world,option,replicas", [(2, {2: 1}, 1), (4, {2: 2}, 2), (3, {1: 1, 2: 1}, 2)],
-                         ids=["one-2-stage-pipeline", "two-2-stage-replicas", "heterogeneous-1+2-stages"])
+@pytest.mark.parametrize("world,option,replicas", [(4, {2: 2}, 2), (3, {1: 1, 2: 1}, 2)],
+                         ids=["two-2-stage-replicas", "heterogeneous-1+2-stages"])
 def test_reference_planner_and_instantiator_drive_this_pipeline(world, option, replicas):
     if not available():
         pytest.skip("needs /root/reference and oracle/_ref (make -C oracle)")
