@@ -58,6 +58,12 @@ class OracleLayer:
 
     supports_sharding = True   # same intra-stage sharding as the CUDA layer (oobleck_b200/execution/sharding.py)
 
+    # Re-read the torch module's weights from ``flat_param`` before the first forward of every step.  For callers that write ``flat_param``
+    # behind the layer's back and never say so -- the reference's own ``_copy_model_states`` broadcasts straight into it
+    # (engine.py:284-306), which works there because FSDP's module parameters are views of the flat parameter.  Off by
+    # default: bench.py's CPU arm would copy 6 GB per GPT-2-XL micro-batch for nothing.
+    reload_every_forward = False
+
     def __init__(self, layer_id, spec, process_group=None, pre_stream=None, post_stream=None, *, microbatch_size,
                  num_pipe_buffers, workspace=None, nsplit=3, columns=1):
         self.layer_id = layer_id
@@ -152,6 +158,9 @@ class OracleLayer:
 
     def __call__(self, inputs, buffer_id=0, total_loss=None):
         self.unshard_params()
+        if self.reload_every_forward and not self._state.sharded and all(x is None for x in self.saved):
+            # no micro-batch in flight (the first forward of a step): autograd holds no reference to the weights
+            og.load_flat_(self.module, self._state.compute_param)
         ins = tuple(t.detach().requires_grad_(t.is_floating_point()) for t in inputs)
         outs = self.module(*ins)
         self.saved[buffer_id] = (ins, outs)

@@ -48,7 +48,7 @@ def available() -> bool:
         any(f.startswith("pipeline_template") and f.endswith(".so") for f in os.listdir(REF_SO_DIR))
 
 
-def write_profile_files():
+def write_profile_files(allreduce_across_nodes=None):
     """What the reference's profiler leaves under /tmp/oobleck/profiles/<model>-<tag>/ and ``get_profile_results`` (C++,
     pipeline_template.cpp:26-79) reads back -- written by this package's ``save_profile_results``."""
     from oobleck_b200.execution.engine import layer_cost_model
@@ -59,7 +59,8 @@ def write_profile_files():
     costs = layer_cost_model(model, 1)
     results = LayerExecutionResults([
         LayerExecutionResult(i, c / 3e6, 2 * c / 3e6, {g + 1: 1e-4 * (g + 1) for g in range(8)},
-                             {n + 1: 1e-3 * (n + 1) for n in range(64)}, (4 * l.num_params, l.activation_bytes(1)))
+                             allreduce_across_nodes or {n + 1: 1e-3 * (n + 1) for n in range(64)},
+                             (4 * l.num_params, l.activation_bytes(1)))
         for i, (c, l) in enumerate(zip(costs, model.layers))])
     save_profile_results(results, "gpt2", TAG, 1)
 
@@ -120,6 +121,9 @@ def bind_reference():
     comm = types.ModuleType("deepspeed.comm")
     comm.__getattr__ = lambda name: getattr(tdist, name)             # get_rank, new_group, broadcast, barrier, ...
     comm.init_distributed = lambda *a, **k: None
+    # _copy_model_states issues ``broadcast(..., async_op=True)`` and never waits (engine.py:301-306): on NCCL the CUDA
+    # stream orders it before everything that follows, gloo has no stream -- the stand-in completes it before returning
+    comm.broadcast = lambda tensor, src, group=None, async_op=False: tdist.broadcast(tensor, src, group=group)
     comm.cdb = None
     ds.comm = comm
     sys.modules["deepspeed.comm"] = comm
