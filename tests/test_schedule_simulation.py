@@ -155,3 +155,23 @@ def test_program_length_and_idle_steps():
             assert len(prog) == 2 * (M + P - 1)                        # pipeline.py:36
             busy = sum(1 for step in prog if any(isinstance(c, (ForwardPass, BackwardPass)) for c in step))
             assert busy == 2 * M
+
+
+def test_compute_order_is_the_canonical_1f1b():
+    """An independent statement of 1F1B that IS in this image: torch.distributed.pipelining.Schedule1F1B (schedules.py,
+    ``_step_microbatches``): ``warmup_chunks = min(n_microbatches, num_stages - stage_index)`` forwards, then one backward
+    and one forward in turn while forwards remain, then the remaining backwards.  The per-stage order of forward / backward
+    passes of ``OobleckPipelineSchedule`` (deepspeed's ``TrainSchedule`` restated) must be exactly that."""
+    import inspect
+
+    from torch.distributed.pipelining import schedules
+    src = inspect.getsource(schedules.Schedule1F1B)
+    assert "self._num_stages - self._stage.stage_index" in src      # the rule quoted above is the installed torch's
+    for M, P in GRID:
+        for s in range(P):
+            got = "".join("F" if isinstance(c, ForwardPass) else "B"
+                          for c in itertools.chain.from_iterable(OobleckPipelineSchedule(M, P, s).program)
+                          if isinstance(c, (ForwardPass, BackwardPass)))
+            warmup = min(M, P - s)
+            want = "F" * warmup + "BF" * (M - warmup) + "B" * warmup
+            assert got == want, (M, P, s)
